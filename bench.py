@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""Benchmark of the MODIS geolocation interpolation hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repository (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path
+
+Metric (BASELINE.json): interpolated lon/lat output pixels per second, 1 km -> 250 m, and the
+fraction of the HBM roofline.  A *step* is one pass of the CVIIRS interpolator over one batch
+of synthetic granules that is already resident in HBM: ``--granules-per-gpu`` (default 36)
+MODIS-shaped granules of 2030 x 1354 float64 tie points per GPU -> 36 x 8120 x 5416 output
+pixels x (lon, lat).  The per-GPU batch is fixed (weak scaling); at 8 GPUs the job is exactly
+the "full day" of 288 granules of BASELINE configs[3], scan-sharded with no collective on
+the data path (scans are independent).  One step = one kernel launch per rank.
+
+Prints ONE JSON line (rank 0).  `value` is whole-job px/s with inputs resident in HBM;
+`e2e` is the same metric through the public numpy API (pinned host buffers, H2D + D2H inside
+the timed region); `roofline` is the dominant kernel against MEASURED_PEAKS.json;
+`cpu_baseline` is the reference (oracle/_ref) timed on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "python-geotiepoints_b200"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "interpolated lon/lat pixels/sec (1km->250m)"
+UNIT = "px/s"
+SCANS_PER_GRANULE = 203
+TIE_ROWS, TIE_COLS = 2030, 1354
+OUT_ROWS, OUT_COLS = 8120, 5416
+PX_PER_GRANULE = OUT_ROWS * OUT_COLS
+FALLBACK_HBM_GBS = 6650.0            # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def algorithmic_bytes_per_px(itemsize, n_in=3, ratio=16):
+    """Each input element read once, each output written once: 17.5 B f64."""
+    return 2 * itemsize + n_in * itemsize / ratio
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--dtype", choices=["f64", "f32"], default="f64")
+    ap.add_argument("--granules-per-gpu", type=int, default=36)
+    ap.add_argument("--e2e-granules", type=int, default=4)
+    ap.add_argument("--kernel", choices=["auto", "generic"], default="auto",
+                    help="auto = what the public API runs; generic = force the rounding-faithful kernel")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------
+# synthetic inputs
+# ------------------------------------------------------------------------------------
+def make_granules(first, count, dtype):
+    """`count` consecutive synthetic granules of the day, stacked along the scan axis."""
+    from concurrent.futures import ThreadPoolExecutor
+    from geotiepoints_b200 import testing
+    with ThreadPoolExecutor(min(8, max(1, count))) as pool:
+        parts = list(pool.map(lambda g: testing.modis_granule(g % 288, dtype=dtype), range(first, first + count)))
+    return tuple(np.concatenate([p[k] for p in parts]) for k in range(3))
+
+
+# ------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, sm_max, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1])); sm_max.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(sm_max)) if sm_max else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------
+# CPU baseline = the reference itself on the host cores
+# ------------------------------------------------------------------------------------
+def load_reference():
+    """(kind, callable(lon, lat, satz) -> (lon, lat)) for float64 1 km -> 250 m.
+
+    kind == "reference": the reference's Cython code built from /root/reference into
+    oracle/_ref by oracle/build_ref.py - the float64 twin with the 2-line dtype patch the
+    stock CVIIRS path needs to accept float64 at all.  Falls back to the C
+    restatement (kind == "port") when oracle/_ref is not importable.
+    """
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    try:
+        if ref_dir not in sys.path:
+            sys.path.insert(0, ref_dir)
+        import geotiepoints._modis_interpolator as stock
+        import geotiepoints_f64._modis_interpolator as f64
+
+        def run(lon, lat, satz):
+            mod = stock if lon.dtype == np.float32 else f64
+            return mod.interpolate(lon, lat, satz, coarse_resolution=1000, fine_resolution=250)
+        return "reference", run
+    except ImportError:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import gtp_oracle
+        return "port", lambda lon, lat, satz: gtp_oracle.cviirs(lon, lat, satz, 1000, 250)
+
+
+def time_reference_step(run, lon, lat, satz, threads):
+    """One pass of the reference over one granule, scans split over `threads` host threads
+    (the Cython scan loop is nogil: _modis_interpolator.pyx:175; stands in for dask map_blocks)."""
+    from concurrent.futures import ThreadPoolExecutor
+    n_scans = lon.shape[0] // 10
+    bounds = [(k * n_scans // threads, (k + 1) * n_scans // threads) for k in range(threads)]
+    bounds = [(a, b) for a, b in bounds if b > a]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(len(bounds)) as pool:
+        list(pool.map(lambda ab: run(lon[ab[0] * 10:ab[1] * 10], lat[ab[0] * 10:ab[1] * 10], satz[ab[0] * 10:ab[1] * 10]), bounds))
+    return time.perf_counter() - t0
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline(dtype, reps=3):
+    kind, run = load_reference()
+    lon, lat, satz = make_granules(0, 1, dtype)
+    threads = host_threads()
+    time_reference_step(run, lon[:200], lat[:200], satz[:200], min(threads, 4))      # warm-up
+    best = min(time_reference_step(run, lon, lat, satz, threads) for _ in range(reps))
+    return {"value": PX_PER_GRANULE / best, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"1 synthetic granule 2030x1354 {np.dtype(dtype).name} 1km->250m, best of {reps}, "
+                      f"scans split over {threads} threads" + (" (f64 = reference + 2-line dtype patch)" if kind == "reference" and dtype == np.float64 else "")}
+
+
+def run_reference_arm(args, dtype):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kind, run = load_reference()
+    lon, lat, satz = make_granules(0, 1, dtype)
+    threads = host_threads()
+    for _ in range(max(1, min(args.warmup, 2))):
+        time_reference_step(run, lon, lat, satz, threads)
+    t = [time_reference_step(run, lon, lat, satz, threads) for _ in range(args.steps)]
+    total = sum(t)
+    value = PX_PER_GRANULE * args.steps / total
+    sample = (f"each step = 1 synthetic granule 2030x1354 {np.dtype(dtype).name} 1km->250m (bounded sample of the "
+              f"workload), scans split over {threads} host threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": "CVIIRS 1km->250m, synthetic MODIS granules 2030x1354 tie points, " + args.dtype,
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------
+# this repository's arm
+# ------------------------------------------------------------------------------------
+def run_b200_arm(args, dtype):
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from geotiepoints_b200 import _capi, modisinterpolator, sharding
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus != world:
+        raise SystemExit(f"--gpus {args.gpus} needs {args.gpus} ranks: launch with python -m torch.distributed.run "
+                         f"--nnodes=1 --nproc-per-node {args.gpus} --master-addr 127.0.0.1 bench.py --gpus {args.gpus} ...")
+    if _capi.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: geotiepoints_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    tdtype = torch.float64 if dtype == np.float64 else torch.float32
+    itemsize = np.dtype(dtype).itemsize
+    G = args.granules_per_gpu
+    # rank r owns the contiguous scan range of granules [r*G, (r+1)*G) of the day
+    g_lo, g_hi = sharding.granule_range(rank, world, G * world)
+    lon, lat, satz = make_granules(g_lo, g_hi - g_lo, dtype)
+    n_scans = lon.shape[0] // 10
+    d_in = [torch.from_numpy(a).to(device) for a in (lon, lat, satz)]
+    out_lon = torch.empty((n_scans * 40, OUT_COLS), dtype=tdtype, device=device)
+    out_lat = torch.empty_like(out_lon)
+    lib = _capi.lib()
+    suffix = "f64" if dtype == np.float64 else "f32"
+    fn = lib.gtp_cviirs_interp_generic_f64 if (args.kernel == "generic" and suffix == "f64") \
+        else getattr(lib, f"gtp_cviirs_interp_{suffix}")
+    stream = torch.cuda.current_stream(device)
+
+    def step():
+        rc = fn(d_in[0].data_ptr(), d_in[1].data_ptr(), d_in[2].data_ptr(), n_scans, 1000, 250, 0,
+                out_lon.data_ptr(), out_lat.data_ptr(), local_rank, ctypes.c_void_p(stream.cuda_stream))
+        _capi.check(rc)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # -- timed region: exactly K steps, one kernel launch each -------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches_before = _capi.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_begin.record(stream)
+    for a, b in ev:
+        a.record(stream)
+        step()
+        b.record(stream)
+    t_end.record(stream)
+    barrier()
+    elapsed_ms = t_begin.elapsed_time(t_end)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    launches = _capi.launch_count() - launches_before
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = sharding.max_over_ranks(elapsed_ms, dist if world > 1 else None)
+    kernel_ms_max = sharding.max_over_ranks(kernel_ms, dist if world > 1 else None)
+
+    px_per_rank_step = n_scans * 40 * OUT_COLS
+    total_px = px_per_rank_step * world * args.steps
+    value = total_px / (elapsed_ms * 1e-3)
+
+    # -- parity spot check (not timed): 8 scans of this rank against the oracle ---------
+    parity = None
+    if rank == 0:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import gtp_oracle
+            from parity import compare
+            ns = 8
+            exp = gtp_oracle.cviirs(lon[:ns * 10], lat[:ns * 10], satz[:ns * 10], 1000, 250, n_threads=8)
+            parity = compare(out_lon[:ns * 40].cpu().numpy(), out_lat[:ns * 40].cpu().numpy(), *exp)
+        except Exception as exc:  # the checker must never take the measurement down
+            parity = {"error": repr(exc)}
+
+    # -- end to end through the public API: pinned host buffers, H2D + D2H inside --------
+    e2e = None
+    if not args.no_e2e:
+        ge = min(args.e2e_granules, G)
+        rows = ge * TIE_ROWS
+        h_in = []
+        for a in (lon, lat, satz):
+            pinned = _capi.pinned_pool.empty((rows, TIE_COLS), dtype)
+            pinned[...] = a[:rows]
+            h_in.append(pinned)
+        res = modisinterpolator.modis_1km_to_250m(*h_in)      # warm-up (pinned pool, stream pool)
+        del res
+        e2e_steps = max(1, min(args.steps, 5))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            res = modisinterpolator.modis_1km_to_250m(*h_in)
+            checksum = float(res[0][-1, -1]) + float(res[1][-1, -1])
+            del res
+        torch.cuda.synchronize(device)
+        dt = time.perf_counter() - t0
+        dt = sharding.max_over_ranks(dt, dist if world > 1 else None)
+        e2e_px = ge * PX_PER_GRANULE
+        e2e = {"value": e2e_px * world * e2e_steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(3 * rows * TIE_COLS * itemsize),
+               "d2h_bytes_per_step": int(2 * e2e_px * itemsize),
+               "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
+               "sample": f"{ge} granules per GPU per call through geotiepoints_b200.modisinterpolator."
+                         f"modis_1km_to_250m(numpy), pinned host inputs, pinned host outputs",
+               "checksum": checksum}
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+        else:
+            peak, peak_src = FALLBACK_HBM_GBS, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+        bpp = algorithmic_bytes_per_px(itemsize)
+        achieved = bpp * px_per_rank_step / (kernel_ms_max * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {
+                "workload": f"CVIIRS 1km->250m, {G} synthetic MODIS granules (2030x1354 {np.dtype(dtype).name} tie points "
+                            f"-> 8120x5416 lon+lat each) per GPU per step, one launch per step; BASELINE configs[1] "
+                            f"batched x{G}; {G * world} granules whole-job" + (" = configs[3] full day" if G * world == 288 else ""),
+                "granules_per_gpu": G, "kernel": args.kernel,
+                "l2": f"working set per step {(bpp * px_per_rank_step) / 1e9:.1f} GB per GPU >> 126 MB L2 (no flush needed)",
+                "sharding": "contiguous scan ranges per rank, outputs resident per rank, no collective on the data path",
+            },
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "kernel_ms": kernel_ms_max, "algorithmic_bytes_per_px": bpp,
+                         "px_per_launch": int(px_per_rank_step)},
+            "parity": parity,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline(dtype)
+            except Exception as exc:
+                line["cpu_baseline"] = {"error": repr(exc)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    dtype = np.float64 if args.dtype == "f64" else np.float32
+    if args.impl == "reference":
+        run_reference_arm(args, dtype)
+    else:
+        run_b200_arm(args, dtype)
+
+
+if __name__ == "__main__":
+    main()

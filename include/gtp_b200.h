@@ -1,0 +1,108 @@
+/*
+ * gtp_b200.h - C ABI of libgtp_b200.so: MODIS geolocation tie-point interpolation on
+ * NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the hot path of pytroll/python-geotiepoints 1.9.0.
+ * Each entry point replaces one compiled operator of the reference (paths relative to
+ * the reference tree, geotiepoints/...):
+ *
+ *   gtp_cviirs_interp_{f32,f64}        _modis_interpolator.pyx:17-38  `interpolate(lon1, lat1,
+ *                                      satz1, coarse_resolution, fine_resolution,
+ *                                      coarse_scan_width)` -> MODISInterpolator.interpolate
+ *                                      (:130-194), i.e. what modisinterpolator.py:21-62
+ *                                      (modis_1km_to_250m / _500m, modis_5km_to_1km /
+ *                                      _500m / _250m) call.
+ *   gtp_simple_interp_{f32,f64}        _simple_modis_interpolator.pyx:13-64
+ *                                      `interpolate_geolocation_cartesian(lon_array,
+ *                                      lat_array, coarse_resolution, fine_resolution)`,
+ *                                      i.e. what simple_modis_interpolator.py:45-61 call.
+ *   gtp_*_interp_host_{f32,f64}        the same operators for HOST buffers (numpy
+ *                                      callers): pipelined H2D / kernel / D2H inside.
+ *
+ * Conventions: plain pointers and sizes, no exceptions, no global mutable state other
+ * than a thread-local error string.  Every function returns 0 on success, a GTP_E_*
+ * code (>0) for invalid arguments, or -(cudaError_t) for CUDA failures;
+ * gtp_last_error() describes the last failure on the calling thread.  The *_interp_*
+ * device entry points are asynchronous on `stream` (a cudaStream_t, NULL = default
+ * stream); the caller owns and pre-allocates every buffer.  Arrays are C-contiguous
+ * row-major, rows = scans * rows_per_scan.  There is no CPU fallback: without a CUDA
+ * device every compute entry point fails.
+ *
+ * Shapes: CVIIRS  in  3 x (n_scans*L, W)      L=10,W=1354 (1 km) | L=2,W=270|271 (5 km)
+ *                                 out 2 x (n_scans*L*f, 1354*p) p=1000/fine_res, f=p*coarse_res/1000
+ *                        simple  in  2 x (n_scans*10, width)
+ *                                 out 2 x (n_scans*10*res, width*res)  res = 2 | 4
+ */
+#ifndef GTP_B200_H
+#define GTP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GTP_OK 0
+#define GTP_E_RESOLUTION 1   /* unsupported coarse/fine resolution pair                         */
+#define GTP_E_WIDTH_5KM 2    /* 5 km tie points with a width other than 270/271 (reference:     */
+                             /* NotImplementedError, _modis_interpolator.pyx:33-36)             */
+#define GTP_E_NULL 3         /* null pointer with n_scans > 0                                   */
+#define GTP_E_SHAPE 4        /* negative n_scans / width too small                              */
+#define GTP_E_NO_DEVICE 5    /* no usable CUDA device                                           */
+
+const char* gtp_version(void);
+const char* gtp_last_error(void);
+/* number of CUDA devices visible (0 when none / no driver); never fails */
+int gtp_device_count(void);
+
+/* Output geometry for a configuration: rows per scan in / out, columns in / out.
+ * coarse_width is only read for coarse_res == 5000 (0 means 271). */
+int gtp_cviirs_geometry(int coarse_res, int fine_res, int coarse_width,
+                        int* rows_per_scan_in, int* cols_in, int* rows_per_scan_out, int* cols_out);
+
+/* ---- device-pointer entry points (asynchronous on `stream`) -------------------- */
+int gtp_cviirs_interp_f32(const float* lon, const float* lat, const float* satz, int64_t n_scans,
+                          int coarse_res, int fine_res, int coarse_width,
+                          float* out_lon, float* out_lat, int device, void* stream);
+int gtp_cviirs_interp_f64(const double* lon, const double* lat, const double* satz, int64_t n_scans,
+                          int coarse_res, int fine_res, int coarse_width,
+                          double* out_lon, double* out_lat, int device, void* stream);
+int gtp_simple_interp_f32(const float* lon, const float* lat, int64_t n_scans, int64_t width, int res_factor,
+                          float* out_lon, float* out_lat, int device, void* stream);
+int gtp_simple_interp_f64(const double* lon, const double* lat, int64_t n_scans, int64_t width, int res_factor,
+                          double* out_lon, double* out_lat, int device, void* stream);
+
+/* Same as gtp_cviirs_interp_f64 but always through the rounding-faithful generic
+ * kernel (never the anchor-relative fast path); used by tests and by the bench to
+ * show the two side by side. */
+int gtp_cviirs_interp_generic_f64(const double* lon, const double* lat, const double* satz, int64_t n_scans,
+                                  int coarse_res, int fine_res, int coarse_width,
+                                  double* out_lon, double* out_lat, int device, void* stream);
+
+/* ---- host-pointer entry points (synchronous; copies inside) -------------------- */
+/* Inputs and outputs are host buffers (pageable or pinned).  The call splits the scans
+ * into chunks and overlaps H2D, kernel and D2H on three streams; it returns when the
+ * outputs are complete.  Pinned buffers (gtp_host_alloc) reach PCIe line rate. */
+int gtp_cviirs_interp_host_f32(const float* lon, const float* lat, const float* satz, int64_t n_scans,
+                               int coarse_res, int fine_res, int coarse_width,
+                               float* out_lon, float* out_lat, int device);
+int gtp_cviirs_interp_host_f64(const double* lon, const double* lat, const double* satz, int64_t n_scans,
+                               int coarse_res, int fine_res, int coarse_width,
+                               double* out_lon, double* out_lat, int device);
+int gtp_simple_interp_host_f32(const float* lon, const float* lat, int64_t n_scans, int64_t width, int res_factor,
+                               float* out_lon, float* out_lat, int device);
+int gtp_simple_interp_host_f64(const double* lon, const double* lat, int64_t n_scans, int64_t width, int res_factor,
+                               double* out_lon, double* out_lat, int device);
+
+/* page-locked host memory for the host entry points */
+int gtp_host_alloc(void** ptr, uint64_t bytes);
+int gtp_host_free(void* ptr);
+
+/* Number of kernels this library has launched in the calling process (all threads);
+ * bench.py reports the delta over its timed region as `gpu_launches`. */
+uint64_t gtp_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GTP_B200_H */

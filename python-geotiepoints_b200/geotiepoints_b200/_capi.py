@@ -1,0 +1,151 @@
+"""ctypes binding of ``libgtp_b200.so`` (C ABI: ``include/gtp_b200.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` /
+``python -m geotiepoints_b200.build``.  Loading fails loudly when it is missing and every
+compute call fails loudly when there is no CUDA device: there is no CPU fallback.
+"""
+import ctypes
+import os
+import threading
+import weakref
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgtp_b200.so")
+
+GTP_E_WIDTH_5KM = 2
+GTP_E_NO_DEVICE = 5
+
+_lib = None
+_lock = threading.Lock()
+
+_c_f32p = ctypes.POINTER(ctypes.c_float)
+_c_f64p = ctypes.POINTER(ctypes.c_double)
+_i64, _int, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p
+
+#: every symbol include/gtp_b200.h declares -> (restype, argtypes)
+SIGNATURES = {
+    "gtp_version": (ctypes.c_char_p, []),
+    "gtp_last_error": (ctypes.c_char_p, []),
+    "gtp_device_count": (_int, []),
+    "gtp_launch_count": (ctypes.c_uint64, []),
+    "gtp_cviirs_geometry": (_int, [_int, _int, _int] + [ctypes.POINTER(_int)] * 4),
+    "gtp_host_alloc": (_int, [ctypes.POINTER(_vp), ctypes.c_uint64]),
+    "gtp_host_free": (_int, [_vp]),
+}
+for _suf in ("f32", "f64"):
+    SIGNATURES[f"gtp_cviirs_interp_{_suf}"] = (_int, [_vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _int, _vp])
+    SIGNATURES[f"gtp_simple_interp_{_suf}"] = (_int, [_vp, _vp, _i64, _i64, _int, _vp, _vp, _int, _vp])
+    SIGNATURES[f"gtp_cviirs_interp_host_{_suf}"] = (_int, [_vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _int])
+    SIGNATURES[f"gtp_simple_interp_host_{_suf}"] = (_int, [_vp, _vp, _i64, _i64, _int, _vp, _vp, _int])
+SIGNATURES["gtp_cviirs_interp_generic_f64"] = SIGNATURES["gtp_cviirs_interp_f64"]
+
+
+class GtpError(RuntimeError):
+    """A failure reported by libgtp_b200 (CUDA error or invalid argument)."""
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raise if the CUDA library is not built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise ImportError(
+                        f"{LIB_PATH} is missing: build the sm_100a CUDA library first "
+                        "(python -m geotiepoints_b200.build).  geotiepoints_b200 has no CPU fallback.")
+                handle = ctypes.CDLL(LIB_PATH)
+                for name, (restype, argtypes) in SIGNATURES.items():
+                    fn = getattr(handle, name)
+                    fn.restype, fn.argtypes = restype, argtypes
+                _lib = handle
+    return _lib
+
+
+def last_error():
+    return lib().gtp_last_error().decode()
+
+
+def check(rc):
+    """Translate a libgtp_b200 return code into the exception the reference raises."""
+    if rc == 0:
+        return
+    msg = last_error()
+    if rc == GTP_E_WIDTH_5KM:
+        # _modis_interpolator.pyx:33-36
+        raise NotImplementedError(msg)
+    if rc > 0 and rc != GTP_E_NO_DEVICE:
+        raise ValueError(msg)
+    raise GtpError(f"libgtp_b200 rc={rc}: {msg}")
+
+
+def suffix(dtype):
+    dtype = np.dtype(dtype)
+    if dtype == np.float32:
+        return "f32"
+    if dtype == np.float64:
+        return "f64"
+    # what Cython's fused-type dispatch raises for any other buffer dtype
+    raise TypeError("No matching signature found")
+
+
+# -- page-locked host buffers ------------------------------------------------------
+class _PinnedPool:
+    """Free-list of page-locked blocks keyed by size.
+
+    ``cudaHostAlloc`` costs about as much as copying the buffer, so blocks handed out as
+    numpy outputs go back to the pool when the arrays are garbage collected and are
+    reused by the next call of the same shape.  Bounded by ``max_cached_bytes``.
+    """
+
+    def __init__(self, max_cached_bytes=8 << 30):
+        self.max_cached_bytes = max_cached_bytes
+        self._free = {}
+        self._cached = 0
+        self._lock = threading.Lock()
+
+    def _release(self, ptr, nbytes):
+        with self._lock:
+            if self._cached + nbytes <= self.max_cached_bytes:
+                self._free.setdefault(nbytes, []).append(ptr)
+                self._cached += nbytes
+                return
+        lib().gtp_host_free(ptr)
+
+    def empty(self, shape, dtype):
+        dtype = np.dtype(dtype)
+        nbytes = max(int(np.prod(shape)) * dtype.itemsize, 1)
+        ptr = None
+        with self._lock:
+            blocks = self._free.get(nbytes)
+            if blocks:
+                ptr = blocks.pop()
+                self._cached -= nbytes
+        if ptr is None:
+            out = _vp()
+            check(lib().gtp_host_alloc(ctypes.byref(out), nbytes))
+            ptr = out.value
+        buf = (ctypes.c_char * nbytes).from_address(ptr)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        weakref.finalize(buf, self._release, ptr, nbytes)
+        return arr
+
+    def trim(self):
+        with self._lock:
+            blocks, self._free, self._cached = self._free, {}, 0
+        for ptrs in blocks.values():
+            for ptr in ptrs:
+                lib().gtp_host_free(ptr)
+
+
+pinned_pool = _PinnedPool()
+
+
+def device_count():
+    return lib().gtp_device_count()
+
+
+def launch_count():
+    return int(lib().gtp_launch_count())

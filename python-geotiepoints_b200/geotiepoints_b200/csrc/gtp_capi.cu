@@ -1,0 +1,275 @@
+// gtp_capi.cu - the extern "C" boundary of libgtp_b200.so (declared in include/gtp_b200.h).
+//
+// Thin by design: argument validation with the reference's error conditions
+// (/root/reference/geotiepoints/_modis_interpolator.pyx:33-36), kernel selection, and
+// the chunked H2D / kernel / D2H pipeline of the host-buffer entry points.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+#include <cuda_runtime.h>
+#include "../../../include/gtp_b200.h"
+#include "gtp_kernels.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, const char* detail = "")
+{
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* where)
+{
+    snprintf(g_err, sizeof(g_err), "CUDA error in %s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
+    return -(int)e;
+}
+
+int cfg_error(int rc)
+{
+    if (rc == 2) return fail(GTP_E_WIDTH_5KM, "Can't interpolate if 5km tiepoints have less than 270 columns.%s");
+    return fail(GTP_E_RESOLUTION, "unsupported coarse/fine resolution pair%s");
+}
+
+// RAII "run on this device, then put the caller's device back"
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device)
+    {
+        err = cudaGetDevice(&prev);
+        if (err != cudaSuccess) return;
+        if (device >= 0 && device != prev) {
+            err = cudaSetDevice(device);
+            switched = (err == cudaSuccess);
+        }
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
+template <typename T>
+int cviirs_device(const T* lon, const T* lat, const T* satz, int64_t n_scans, int coarse_res, int fine_res,
+                  int coarse_width, T* out_lon, T* out_lat, int device, void* stream, bool allow_fast)
+{
+    CviirsCfg cfg;
+    int rc = gtp_make_cfg(coarse_res, fine_res, coarse_width, &cfg);
+    if (rc) return cfg_error(rc);
+    if (n_scans < 0) return fail(GTP_E_SHAPE, "n_scans must be >= 0%s");
+    if (n_scans == 0) return GTP_OK;
+    if (!lon || !lat || !satz || !out_lon || !out_lat) return fail(GTP_E_NULL, "null buffer%s");
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) { cudaGetLastError(); return fail(GTP_E_NO_DEVICE, "no usable CUDA device: %s", cudaGetErrorString(guard.err)); }
+    cudaError_t e;
+    if constexpr (sizeof(T) == 8) {
+        if (allow_fast && gtp_cviirs_fast_f64_supported(cfg))
+            e = gtp_launch_cviirs_fast_f64(lon, lat, satz, out_lon, out_lat, n_scans, cfg, (cudaStream_t)stream);
+        else
+            e = gtp_launch_cviirs_generic<T>(lon, lat, satz, out_lon, out_lat, n_scans, cfg, (cudaStream_t)stream);
+    } else {
+        e = gtp_launch_cviirs_generic<T>(lon, lat, satz, out_lon, out_lat, n_scans, cfg, (cudaStream_t)stream);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "cviirs launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return GTP_OK;
+}
+
+template <typename T>
+int simple_device(const T* lon, const T* lat, int64_t n_scans, int64_t width, int res, T* out_lon, T* out_lat,
+                  int device, void* stream)
+{
+    if (res != 2 && res != 4) return fail(GTP_E_RESOLUTION, "simple interpolator: res_factor must be 2 or 4%s");
+    if (n_scans < 0) return fail(GTP_E_SHAPE, "n_scans must be >= 0%s");
+    if (width < 4 || width > (1 << 24)) return fail(GTP_E_SHAPE, "simple interpolator: width must be in [4, 2^24]%s");
+    if (n_scans == 0) return GTP_OK;
+    if (!lon || !lat || !out_lon || !out_lat) return fail(GTP_E_NULL, "null buffer%s");
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) { cudaGetLastError(); return fail(GTP_E_NO_DEVICE, "no usable CUDA device: %s", cudaGetErrorString(guard.err)); }
+    cudaError_t e = gtp_launch_simple_generic<T>(lon, lat, out_lon, out_lat, n_scans, (int)width, res, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "simple launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return GTP_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// Host-buffer pipeline.  The scans are cut into chunks; chunk k runs H2D -> kernel ->
+// D2H in order on stream k % kStreams, so the copy engines and the SMs overlap across
+// chunks.  Device scratch comes from the stream-ordered pool (cudaMallocAsync), which
+// the driver keeps warm between calls.
+// ---------------------------------------------------------------------------------
+constexpr int kStreams = 3;
+constexpr int64_t kChunkOutBytes = 48ll << 20;   // per output array and chunk
+
+#define GTP_CUDA_TRY(expr, where)                                  \
+    do {                                                           \
+        cudaError_t _e = (expr);                                   \
+        if (_e != cudaSuccess) { status = cuda_fail(_e, where); goto done; } \
+    } while (0)
+
+template <typename T, int N_IN, typename Launch>
+int host_pipeline(const T* const (&in)[N_IN], T* out_lon, T* out_lat, int64_t n_scans,
+                  int64_t in_elems_per_scan, int64_t out_elems_per_scan, int device, Launch launch)
+{
+    if (n_scans == 0) return GTP_OK;
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) { cudaGetLastError(); return fail(GTP_E_NO_DEVICE, "no usable CUDA device: %s", cudaGetErrorString(guard.err)); }
+    int status = GTP_OK;
+    int64_t chunk = std::max<int64_t>(1, kChunkOutBytes / (int64_t)(out_elems_per_scan * sizeof(T)));
+    chunk = std::min(chunk, n_scans);
+    const int64_t n_chunks = (n_scans + chunk - 1) / chunk;
+    const int n_streams = (int)std::min<int64_t>(kStreams, n_chunks);
+    cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr};
+    T* d_in[kStreams][N_IN] = {};
+    T* d_out[kStreams][2] = {};
+    for (int s = 0; s < n_streams; ++s) {
+        GTP_CUDA_TRY(cudaStreamCreateWithFlags(&streams[s], cudaStreamNonBlocking), "stream create");
+        for (int a = 0; a < N_IN; ++a)
+            GTP_CUDA_TRY(cudaMallocAsync((void**)&d_in[s][a], chunk * in_elems_per_scan * sizeof(T), streams[s]), "scratch alloc");
+        for (int a = 0; a < 2; ++a)
+            GTP_CUDA_TRY(cudaMallocAsync((void**)&d_out[s][a], chunk * out_elems_per_scan * sizeof(T), streams[s]), "scratch alloc");
+    }
+    for (int64_t k = 0; k < n_chunks; ++k) {
+        const int s = (int)(k % n_streams);
+        const int64_t s0 = k * chunk, ns = std::min(chunk, n_scans - s0);
+        for (int a = 0; a < N_IN; ++a)
+            GTP_CUDA_TRY(cudaMemcpyAsync(d_in[s][a], in[a] + s0 * in_elems_per_scan, ns * in_elems_per_scan * sizeof(T),
+                                         cudaMemcpyHostToDevice, streams[s]), "H2D");
+        status = launch(d_in[s], d_out[s][0], d_out[s][1], ns, streams[s]);
+        if (status != GTP_OK) goto done;
+        GTP_CUDA_TRY(cudaMemcpyAsync(out_lon + s0 * out_elems_per_scan, d_out[s][0], ns * out_elems_per_scan * sizeof(T),
+                                     cudaMemcpyDeviceToHost, streams[s]), "D2H");
+        GTP_CUDA_TRY(cudaMemcpyAsync(out_lat + s0 * out_elems_per_scan, d_out[s][1], ns * out_elems_per_scan * sizeof(T),
+                                     cudaMemcpyDeviceToHost, streams[s]), "D2H");
+    }
+done:
+    for (int s = 0; s < n_streams; ++s) {
+        if (!streams[s]) continue;
+        for (int a = 0; a < N_IN; ++a) if (d_in[s][a]) cudaFreeAsync(d_in[s][a], streams[s]);
+        for (int a = 0; a < 2; ++a) if (d_out[s][a]) cudaFreeAsync(d_out[s][a], streams[s]);
+        cudaError_t e = cudaStreamSynchronize(streams[s]);
+        if (e != cudaSuccess && status == GTP_OK) status = cuda_fail(e, "pipeline sync");
+        cudaStreamDestroy(streams[s]);
+    }
+    return status;
+}
+
+template <typename T>
+int cviirs_host(const T* lon, const T* lat, const T* satz, int64_t n_scans, int coarse_res, int fine_res,
+                int coarse_width, T* out_lon, T* out_lat, int device)
+{
+    CviirsCfg cfg;
+    int rc = gtp_make_cfg(coarse_res, fine_res, coarse_width, &cfg);
+    if (rc) return cfg_error(rc);
+    if (n_scans < 0) return fail(GTP_E_SHAPE, "n_scans must be >= 0%s");
+    if (n_scans == 0) return GTP_OK;
+    if (!lon || !lat || !satz || !out_lon || !out_lat) return fail(GTP_E_NULL, "null buffer%s");
+    const T* const in[3] = {lon, lat, satz};
+    return host_pipeline<T, 3>(in, out_lon, out_lat, n_scans, (int64_t)cfg.L * cfg.W, (int64_t)cfg.n * cfg.Wf, device,
+        [&](T* const* d_in, T* d_lon, T* d_lat, int64_t ns, cudaStream_t st) {
+            return cviirs_device<T>(d_in[0], d_in[1], d_in[2], ns, coarse_res, fine_res, coarse_width,
+                                    d_lon, d_lat, -1, (void*)st, true);
+        });
+}
+
+template <typename T>
+int simple_host(const T* lon, const T* lat, int64_t n_scans, int64_t width, int res, T* out_lon, T* out_lat, int device)
+{
+    if (res != 2 && res != 4) return fail(GTP_E_RESOLUTION, "simple interpolator: res_factor must be 2 or 4%s");
+    if (n_scans < 0) return fail(GTP_E_SHAPE, "n_scans must be >= 0%s");
+    if (width < 4 || width > (1 << 24)) return fail(GTP_E_SHAPE, "simple interpolator: width must be in [4, 2^24]%s");
+    if (n_scans == 0) return GTP_OK;
+    if (!lon || !lat || !out_lon || !out_lat) return fail(GTP_E_NULL, "null buffer%s");
+    const T* const in[2] = {lon, lat};
+    return host_pipeline<T, 2>(in, out_lon, out_lat, n_scans, 10 * width, 10 * res * width * res, device,
+        [&](T* const* d_in, T* d_lon, T* d_lat, int64_t ns, cudaStream_t st) {
+            return simple_device<T>(d_in[0], d_in[1], ns, width, res, d_lon, d_lat, -1, (void*)st);
+        });
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* gtp_version(void) { return "gtp_b200 0.1.0 (sm_100a; restates python-geotiepoints 1.9.0 MODIS interpolators)"; }
+const char* gtp_last_error(void) { return g_err; }
+uint64_t gtp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int gtp_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int gtp_cviirs_geometry(int coarse_res, int fine_res, int coarse_width,
+                        int* rows_per_scan_in, int* cols_in, int* rows_per_scan_out, int* cols_out)
+{
+    CviirsCfg cfg;
+    int rc = gtp_make_cfg(coarse_res, fine_res, coarse_width, &cfg);
+    if (rc) return cfg_error(rc);
+    if (rows_per_scan_in) *rows_per_scan_in = cfg.L;
+    if (cols_in) *cols_in = cfg.W;
+    if (rows_per_scan_out) *rows_per_scan_out = cfg.n;
+    if (cols_out) *cols_out = cfg.Wf;
+    return GTP_OK;
+}
+
+int gtp_cviirs_interp_f32(const float* lon, const float* lat, const float* satz, int64_t n_scans,
+                          int coarse_res, int fine_res, int coarse_width,
+                          float* out_lon, float* out_lat, int device, void* stream)
+{ return cviirs_device<float>(lon, lat, satz, n_scans, coarse_res, fine_res, coarse_width, out_lon, out_lat, device, stream, true); }
+
+int gtp_cviirs_interp_f64(const double* lon, const double* lat, const double* satz, int64_t n_scans,
+                          int coarse_res, int fine_res, int coarse_width,
+                          double* out_lon, double* out_lat, int device, void* stream)
+{ return cviirs_device<double>(lon, lat, satz, n_scans, coarse_res, fine_res, coarse_width, out_lon, out_lat, device, stream, true); }
+
+int gtp_cviirs_interp_generic_f64(const double* lon, const double* lat, const double* satz, int64_t n_scans,
+                                  int coarse_res, int fine_res, int coarse_width,
+                                  double* out_lon, double* out_lat, int device, void* stream)
+{ return cviirs_device<double>(lon, lat, satz, n_scans, coarse_res, fine_res, coarse_width, out_lon, out_lat, device, stream, false); }
+
+int gtp_simple_interp_f32(const float* lon, const float* lat, int64_t n_scans, int64_t width, int res_factor,
+                          float* out_lon, float* out_lat, int device, void* stream)
+{ return simple_device<float>(lon, lat, n_scans, width, res_factor, out_lon, out_lat, device, stream); }
+
+int gtp_simple_interp_f64(const double* lon, const double* lat, int64_t n_scans, int64_t width, int res_factor,
+                          double* out_lon, double* out_lat, int device, void* stream)
+{ return simple_device<double>(lon, lat, n_scans, width, res_factor, out_lon, out_lat, device, stream); }
+
+int gtp_cviirs_interp_host_f32(const float* lon, const float* lat, const float* satz, int64_t n_scans,
+                               int coarse_res, int fine_res, int coarse_width, float* out_lon, float* out_lat, int device)
+{ return cviirs_host<float>(lon, lat, satz, n_scans, coarse_res, fine_res, coarse_width, out_lon, out_lat, device); }
+
+int gtp_cviirs_interp_host_f64(const double* lon, const double* lat, const double* satz, int64_t n_scans,
+                               int coarse_res, int fine_res, int coarse_width, double* out_lon, double* out_lat, int device)
+{ return cviirs_host<double>(lon, lat, satz, n_scans, coarse_res, fine_res, coarse_width, out_lon, out_lat, device); }
+
+int gtp_simple_interp_host_f32(const float* lon, const float* lat, int64_t n_scans, int64_t width, int res_factor,
+                               float* out_lon, float* out_lat, int device)
+{ return simple_host<float>(lon, lat, n_scans, width, res_factor, out_lon, out_lat, device); }
+
+int gtp_simple_interp_host_f64(const double* lon, const double* lat, int64_t n_scans, int64_t width, int res_factor,
+                               double* out_lon, double* out_lat, int device)
+{ return simple_host<double>(lon, lat, n_scans, width, res_factor, out_lon, out_lat, device); }
+
+int gtp_host_alloc(void** ptr, uint64_t bytes)
+{
+    if (!ptr) return fail(GTP_E_NULL, "null pointer%s");
+    cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaHostAlloc");
+    return GTP_OK;
+}
+
+int gtp_host_free(void* ptr)
+{
+    if (!ptr) return GTP_OK;
+    cudaError_t e = cudaFreeHost(ptr);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFreeHost");
+    return GTP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,18 @@
+// gtp_kernels.h - internal launcher declarations shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include "gtp_common.cuh"
+
+// gtp_generic.cu: rounding-faithful kernels (all configurations, float32/float64)
+template <typename T>
+cudaError_t gtp_launch_cviirs_generic(const T* lon, const T* lat, const T* satz, T* out_lon, T* out_lat,
+                                      long long n_scans, const CviirsCfg& cfg, cudaStream_t stream);
+template <typename T>
+cudaError_t gtp_launch_simple_generic(const T* lon, const T* lat, T* out_lon, T* out_lat,
+                                      long long n_scans, int width, int res, cudaStream_t stream);
+
+// gtp_fast.cu: float64 anchor-relative fast paths
+cudaError_t gtp_launch_cviirs_fast_f64(const double* lon, const double* lat, const double* satz,
+                                       double* out_lon, double* out_lat,
+                                       long long n_scans, const CviirsCfg& cfg, cudaStream_t stream);
+bool gtp_cviirs_fast_f64_supported(const CviirsCfg& cfg);

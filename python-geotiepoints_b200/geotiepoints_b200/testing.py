@@ -23,7 +23,7 @@ EARTH_ROT_DEG_PER_S = 360.0 / 86164.1
 
 
 def modis_granule(granule=0, n_scans=SCANS_PER_GRANULE, dtype=np.float64, jitter_deg=1e-4,
-                  quantize_satz=False, node_lon_deg=0.0, arg_lat0_deg=None):
+                  quantize_satz=False, node_lon_deg=0.0, arg_lat0_deg=None, inclination_deg=INCLINATION_DEG):
     """Return ``(lon, lat, satz)`` of shape ``(10 * n_scans, 1354)`` in degrees.
 
     ``granule`` selects the 5-minute slot of the day (0..287): the argument of latitude
@@ -35,7 +35,7 @@ def modis_granule(granule=0, n_scans=SCANS_PER_GRANULE, dtype=np.float64, jitter
     rng = np.random.default_rng(int(granule))
     u0 = np.deg2rad(granule * GRANULE_ARG_LAT_STEP_DEG if arg_lat0_deg is None else arg_lat0_deg)
     node0 = np.deg2rad(node_lon_deg + granule * GRANULE_NODE_SHIFT_DEG)
-    inc = np.deg2rad(INCLINATION_DEG)
+    inc = np.deg2rad(inclination_deg)
 
     frame = np.arange(FRAMES, dtype=np.float64)
     theta = np.deg2rad((frame - 676.5) * (110.0 / FRAMES))           # scan angle at the satellite
@@ -89,13 +89,14 @@ def stress_granule(kind, n_scans=4, dtype=np.float64):
     if kind == "antimeridian":
         lon, lat, satz = modis_granule(0, n_scans, np.float64, node_lon_deg=172.0, arg_lat0_deg=20.0)
     elif kind == "pole":
-        lon, lat, satz = modis_granule(0, n_scans, np.float64, arg_lat0_deg=88.0)
+        # a polar orbit whose ground track crosses the pole inside the first scan
+        lon, lat, satz = modis_granule(0, n_scans, np.float64, arg_lat0_deg=89.97, inclination_deg=90.0)
     elif kind == "south_pole":
-        lon, lat, satz = modis_granule(0, n_scans, np.float64, arg_lat0_deg=268.0)
+        lon, lat, satz = modis_granule(0, n_scans, np.float64, arg_lat0_deg=269.97, inclination_deg=90.0)
     elif kind == "prime_meridian":
         lon, lat, satz = modis_granule(0, n_scans, np.float64, node_lon_deg=-1.0, arg_lat0_deg=1.0)
     elif kind == "lat_switch":           # straddles |lat| = 53.13 deg (z = 0.8 R), _modis_utils.pyx:62
-        lon, lat, satz = modis_granule(0, n_scans, np.float64, arg_lat0_deg=52.6)
+        lon, lat, satz = modis_granule(0, n_scans, np.float64, arg_lat0_deg=54.4)
     elif kind == "symmetric_satz":       # GH #19, tests/test_modisinterpolator.py:143-149
         lon, lat, _ = modis_granule(0, n_scans, np.float64)
         satz = np.abs(np.linspace(-65.4, 65.4, FRAMES, dtype=np.float32)).astype(np.float64)

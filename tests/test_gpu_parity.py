@@ -1,0 +1,150 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle.
+
+Every case runs the same inputs through ``libgtp_b200.so`` (host entry points for numpy,
+device entry points for torch CUDA tensors) and through ``oracle/libgtp_oracle.so`` and
+compares with the tolerances of BASELINE.json (tests/parity.py: 1e-10 deg float64,
+1e-5 deg / 1 ulp float32, conditioning band reported separately).
+"""
+import numpy as np
+import pytest
+
+import gtp_oracle
+from cases import CVIIRS_CONFIGS, DTYPES, INPUT_NAMES, SIMPLE_CONFIGS, cviirs_inputs
+from geotiepoints_b200 import _capi, modisinterpolator, simple_modis_interpolator, testing
+from geotiepoints_b200._modis_interpolator import interpolate
+from parity import assert_parity, compare
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_cviirs(a, coarse, fine, width):
+    with np.errstate(all="ignore"):
+        return gtp_oracle.cviirs(*a, coarse, fine, width, n_threads=8)
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("name", INPUT_NAMES)
+def test_cviirs_golden_inputs_all_configs(name, dtype, golden_inputs):
+    for coarse, fine, width in CVIIRS_CONFIGS:
+        a = cviirs_inputs(golden_inputs[name], coarse, width, dtype)
+        got = interpolate(*a, coarse_resolution=coarse, fine_resolution=fine, coarse_scan_width=width)
+        exp = _oracle_cviirs(a, coarse, fine, width)
+        assert got[0].dtype == dtype and got[0].shape == exp[0].shape
+        assert_parity(*got, *exp, what=f"{name} cviirs {coarse}->{fine} w{width} {np.dtype(dtype).name}")
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("name", INPUT_NAMES)
+def test_simple_golden_inputs(name, dtype, golden_inputs):
+    lon1, lat1, _ = (a.astype(dtype) for a in golden_inputs[name])
+    for coarse, fine in SIMPLE_CONFIGS:
+        got = simple_modis_interpolator.interpolate_geolocation_cartesian(
+            lon1, lat1, coarse_resolution=coarse, fine_resolution=fine)
+        with np.errstate(all="ignore"):
+            exp = gtp_oracle.simple(lon1, lat1, coarse, fine, n_threads=8)
+        assert_parity(*got, *exp, what=f"{name} simple {coarse}->{fine} {np.dtype(dtype).name}")
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("granule", [0, 5, 9, 14, 100, 287])
+def test_cviirs_synthetic_granules_1km(granule, dtype):
+    """Orbit-synthetic granules over the whole day: equator, both polar caps, antimeridian."""
+    lon, lat, satz = testing.modis_granule(granule, n_scans=12, dtype=dtype, quantize_satz=(granule % 2 == 1))
+    for fine in (250, 500):
+        got = interpolate(lon, lat, satz, coarse_resolution=1000, fine_resolution=fine)
+        exp = _oracle_cviirs((lon, lat, satz), 1000, fine, 0)
+        assert_parity(*got, *exp, what=f"granule {granule} 1km->{fine} {np.dtype(dtype).name}")
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=lambda d: np.dtype(d).name)
+def test_cviirs_full_granule_5km(dtype):
+    """BASELINE config 3: 406 x 271|270 tie points -> 2030 x 1354."""
+    lon, lat, satz = testing.modis_granule(33, dtype=dtype)
+    for width in (271, 270):
+        a = testing.subsample_5km(lon, lat, satz, width)
+        assert a[0].shape == (406, width)
+        got = modisinterpolator.modis_5km_to_1km(*a)
+        exp = _oracle_cviirs(a, 5000, 1000, width)
+        assert got[0].shape == (2030, 1354)
+        assert_parity(*got, *exp, what=f"5km({width})->1km {np.dtype(dtype).name}")
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=lambda d: np.dtype(d).name)
+def test_cviirs_full_granule_1km_to_250m(dtype):
+    """BASELINE config 2 at full size (oracle on 8 threads finishes in a few seconds)."""
+    lon, lat, satz = testing.modis_granule(141, dtype=dtype)
+    got = modisinterpolator.modis_1km_to_250m(lon, lat, satz)
+    exp = _oracle_cviirs((lon, lat, satz), 1000, 250, 0)
+    assert got[0].shape == (8120, 5416)
+    s = assert_parity(*got, *exp, what=f"full granule 1km->250m {np.dtype(dtype).name}")
+    print("\nparity full granule", np.dtype(dtype).name, s)
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=lambda d: np.dtype(d).name)
+def test_simple_full_granule_and_odd_width(dtype):
+    lon, lat, _ = testing.modis_granule(77, n_scans=40, dtype=dtype)
+    for fine in (250, 500):
+        got = simple_modis_interpolator.modis_1km_to_250m(lon, lat) if fine == 250 else \
+            simple_modis_interpolator.modis_1km_to_500m(lon, lat)
+        exp = gtp_oracle.simple(lon, lat, 1000, fine, n_threads=8)
+        assert_parity(*got, *exp, what=f"simple 1km->{fine} {np.dtype(dtype).name}")
+    a = np.ascontiguousarray(lon[:20, :131]), np.ascontiguousarray(lat[:20, :131])
+    got = simple_modis_interpolator.interpolate_geolocation_cartesian(*a, coarse_resolution=1000, fine_resolution=250)
+    exp = gtp_oracle.simple(*a, 1000, 250)
+    assert_parity(*got, *exp, what="simple width 131")
+
+
+def test_generic_f64_kernel_matches_oracle_tightly():
+    """The rounding-faithful float64 kernel differs from the reference only through CUDA's
+    libm (<= 2 ulp) - checked at a tolerance 100x tighter than the contract, outside the band."""
+    import ctypes
+    import torch
+    lon, lat, satz = testing.modis_granule(20, n_scans=6)
+    exp = _oracle_cviirs((lon, lat, satz), 1000, 250, 0)
+    d = [torch.from_numpy(a).cuda() for a in (lon, lat, satz)]
+    out_lon = torch.empty(exp[0].shape, dtype=torch.float64, device="cuda")
+    out_lat = torch.empty_like(out_lon)
+    rc = _capi.lib().gtp_cviirs_interp_generic_f64(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), 6, 1000, 250, 0,
+                                                    out_lon.data_ptr(), out_lat.data_ptr(), 0,
+                                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _capi.check(rc)
+    torch.cuda.synchronize()
+    s = compare(out_lon.cpu().numpy(), out_lat.cpu().numpy(), *exp)
+    assert s["max_dlat"] < 1e-12 and s["max_dlon_outside_band"] < 1e-12, s
+
+
+def test_torch_device_path_matches_host_path():
+    import torch
+    lon, lat, satz = testing.modis_granule(3, n_scans=5)
+    host = modisinterpolator.modis_1km_to_250m(lon, lat, satz)
+    dev = modisinterpolator.modis_1km_to_250m(*[torch.from_numpy(a).cuda() for a in (lon, lat, satz)])
+    assert dev[0].is_cuda and dev[0].dtype == torch.float64
+    np.testing.assert_array_equal(dev[0].cpu().numpy(), host[0])
+    np.testing.assert_array_equal(dev[1].cpu().numpy(), host[1])
+    host = simple_modis_interpolator.modis_1km_to_500m(lon.astype(np.float32), lat.astype(np.float32))
+    dev = simple_modis_interpolator.modis_1km_to_500m(*[torch.from_numpy(a.astype(np.float32)).cuda() for a in (lon, lat)])
+    np.testing.assert_array_equal(dev[0].cpu().numpy(), host[0])
+    np.testing.assert_array_equal(dev[1].cpu().numpy(), host[1])
+
+
+def test_empty_and_strided_inputs():
+    lon, lat, satz = testing.modis_granule(3, n_scans=2, dtype=np.float32)
+    got = modisinterpolator.modis_1km_to_500m(lon[:0], lat[:0], satz[:0])
+    assert got[0].shape == (0, 2708) and got[1].shape == (0, 2708)
+    # non-contiguous views are made contiguous, as the reference does (:136-138)
+    big = np.zeros((20, 2708), np.float32)
+    big[:, ::2] = lon
+    ref = modisinterpolator.modis_1km_to_500m(lon, lat, satz)
+    got = modisinterpolator.modis_1km_to_500m(big[:, ::2], lat, satz)
+    np.testing.assert_array_equal(got[0], ref[0])
+    # inputs are never modified
+    lon2 = lon.copy()
+    modisinterpolator.modis_1km_to_250m(lon, lat, satz)
+    np.testing.assert_array_equal(lon, lon2)
+
+
+def test_launch_counter_moves():
+    lon, lat, satz = testing.modis_granule(3, n_scans=1, dtype=np.float32)
+    before = _capi.launch_count()
+    modisinterpolator.modis_1km_to_250m(lon, lat, satz)
+    assert _capi.launch_count() == before + 1

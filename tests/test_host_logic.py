@@ -1,0 +1,177 @@
+"""Host-side logic that needs no GPU: the array-container adapter, argument validation
+with the reference's error types and messages, the C-ABI export list, scan sharding."""
+import ctypes
+import os
+import re
+import types
+import warnings
+
+import numpy as np
+import pytest
+
+import fake_dask
+from conftest import ROOT
+from geotiepoints_b200 import _capi, _modis_utils, modisinterpolator, sharding, simple_modis_interpolator
+from geotiepoints_b200._modis_interpolator import MODISInterpolator, interpolate
+from geotiepoints_b200._modis_utils import rows_per_scan_for_resolution, scanline_mapblocks
+
+
+# ---- C ABI ---------------------------------------------------------------------------
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "gtp_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gtp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _header_functions()
+    assert len(names) >= 16
+    handle = ctypes.CDLL(_capi.LIB_PATH)
+    for name in names:
+        assert hasattr(handle, name), f"{name} declared in include/gtp_b200.h but not exported"
+    assert set(names) == set(_capi.SIGNATURES), "ctypes binding and header disagree"
+
+
+def test_version_and_geometry_without_gpu():
+    lib = _capi.lib()
+    assert b"gtp_b200" in lib.gtp_version()
+    vals = [ctypes.c_int() for _ in range(4)]
+    for (coarse, fine, width), want in {
+        (1000, 250, 0): (10, 1354, 40, 5416), (1000, 500, 0): (10, 1354, 20, 2708),
+        (5000, 1000, 271): (2, 271, 10, 1354), (5000, 1000, 270): (2, 270, 10, 1354),
+        (5000, 500, 0): (2, 271, 20, 2708), (5000, 250, 270): (2, 270, 40, 5416),
+    }.items():
+        assert lib.gtp_cviirs_geometry(coarse, fine, width, *[ctypes.byref(v) for v in vals]) == 0
+        assert tuple(v.value for v in vals) == want
+    assert lib.gtp_cviirs_geometry(5000, 1000, 100, *[ctypes.byref(v) for v in vals]) == _capi.GTP_E_WIDTH_5KM
+    assert b"less than 270 columns" in lib.gtp_last_error()
+    assert lib.gtp_cviirs_geometry(2000, 250, 0, *[ctypes.byref(v) for v in vals]) == 1
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_capi, "_lib", None)
+    monkeypatch.setattr(_capi, "LIB_PATH", "/nonexistent/libgtp_b200.so")
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        _capi.lib()
+
+
+# ---- argument validation (reference error types / messages) -----------
+def test_required_keyword_arguments():
+    a = np.zeros((10, 1354), np.float32)
+    with pytest.raises(ValueError, match="'coarse_resolution' and 'fine_resolution' are required keyword arguments."):
+        interpolate(a, a, a)
+
+
+def test_expected_2d():
+    a = np.zeros((10,), np.float32)
+    with pytest.raises(ValueError, match="Expected 2D input arrays."):
+        interpolate(a, a, a, coarse_resolution=1000, fine_resolution=250)
+
+
+def test_5km_width_guard():
+    a = np.zeros((2, 100), np.float32)
+    with pytest.raises(NotImplementedError, match="Can't interpolate if 5km tiepoints have less than 270 columns."):
+        modisinterpolator.modis_5km_to_1km(a, a, a)
+
+
+def test_integer_dtype_is_a_type_error():
+    a = np.zeros((10, 1354), np.int32)
+    with pytest.raises(TypeError, match="No matching signature found"):
+        modisinterpolator.modis_1km_to_250m(a, a, a)
+
+
+def test_mixed_dtypes_is_a_value_error():
+    a = np.zeros((10, 1354), np.float32)
+    with pytest.raises(ValueError, match="Buffer dtype mismatch"):
+        modisinterpolator.modis_1km_to_250m(a, a.astype(np.float64), a)
+
+
+def test_partial_scan_and_wrong_width_are_refused():
+    a = np.zeros((15, 1354), np.float32)
+    with pytest.raises(ValueError, match="whole scans"):
+        modisinterpolator.modis_1km_to_250m(a, a, a)
+    b = np.zeros((10, 1000), np.float32)
+    with pytest.raises(ValueError, match="1354"):
+        modisinterpolator.modis_1km_to_500m(b, b, b)
+    with pytest.raises(ValueError, match="whole scans"):
+        simple_modis_interpolator.modis_1km_to_250m(a, a)
+
+
+def test_5km_poor_quality_warnings(monkeypatch):
+    """modisinterpolator.py:45-47, :56-58 (tested in tests/test_modisinterpolator.py:130-134)."""
+    import geotiepoints_b200.modisinterpolator as mi
+    monkeypatch.setattr(mi, "interpolate", lambda *a, **k: ("lon", "lat"))
+    a = np.zeros((2, 271), np.float32)
+    for fn, expect in ((mi.modis_5km_to_500m, True), (mi.modis_5km_to_250m, True), (mi.modis_5km_to_1km, False),
+                       (mi.modis_1km_to_250m, False)):
+        with warnings.catch_warnings(record=True) as warns:
+            warnings.simplefilter("always")
+            fn(a, a, a)
+        assert any("may result in poor quality" in str(w.message) for w in warns) == expect
+
+
+def test_interpolator_geometry():
+    m = MODISInterpolator(5000, 250, 270)
+    assert (m._coarse_scan_length, m._coarse_scan_width, m._fine_pixels_per_coarse_pixel, m._fine_scan_width) == (2, 270, 20, 5416)
+    m = MODISInterpolator(1000, 500)
+    assert (m._coarse_scan_length, m._coarse_scan_width, m._fine_pixels_per_coarse_pixel, m._fine_scan_width) == (10, 1354, 2, 2708)
+    assert [rows_per_scan_for_resolution(r) for r in (5000, 1000, 500, 250)] == [2, 10, 20, 40]
+
+
+# ---- the dask adapter, against a fake dask ------------------------------------------
+@pytest.fixture
+def fake_da(monkeypatch):
+    mod = types.SimpleNamespace(map_blocks=fake_dask.map_blocks, Array=fake_dask.Array)
+    monkeypatch.setattr(_modis_utils, "da", mod)
+    fake_dask.COMPUTES["n"] = 0
+    fake_dask.BLOCK_SHAPES.clear()
+    return mod
+
+
+def _dummy_operator(factor):
+    @scanline_mapblocks
+    def op(lon, lat, coarse_resolution=0, fine_resolution=0):
+        assert isinstance(lon, np.ndarray)
+        out = np.repeat(np.repeat(lon, factor, axis=0), factor, axis=1)
+        return out, out + 1
+    return op
+
+
+def test_dask_blocks_are_whole_scans_and_lazy(fake_da):
+    lon = np.arange(60 * 1354, dtype=np.float32).reshape(60, 1354)
+    d = fake_dask.from_array(lon, chunks=(25, 700))      # neither whole scans nor full width
+    op = _dummy_operator(4)
+    lons, lats = op(d, d, coarse_resolution=1000, fine_resolution=250)
+    assert fake_dask.COMPUTES["n"] == 0                  # building the graph computes nothing
+    assert lons.shape == (240, 5416) and lons.chunks == ((80, 80, 80), (5416,))
+    out = lons.compute()
+    assert fake_dask.BLOCK_SHAPES == [(20, 1354)] * 3     # 25 -> 20 rows = 2 whole scans
+    np.testing.assert_array_equal(out, np.repeat(np.repeat(lon, 4, axis=0), 4, axis=1))
+    np.testing.assert_array_equal(lats.compute(), out + 1)
+
+
+def test_dask_partial_scan_is_refused(fake_da):
+    lon = np.zeros((19, 1354), np.float32)
+    d = fake_dask.from_array(lon, chunks=4096)
+    with pytest.raises(ValueError, match=r"does not consist of whole scans \(10 rows per scan\)"):
+        simple_modis_interpolator.modis_1km_to_250m(d, d)
+
+
+def test_numpy_passthrough_does_not_touch_dask(fake_da):
+    op = _dummy_operator(2)
+    a = np.ones((10, 4), np.float32)
+    lons, lats = op(a, a, coarse_resolution=1000, fine_resolution=500)
+    assert isinstance(lons, np.ndarray) and lons.shape == (20, 8)
+
+
+# ---- scan sharding ---------------------------------------------------------------------
+@pytest.mark.parametrize("n_scans,world", [(288 * 203, 8), (203, 3), (7, 8), (0, 4), (58464, 1)])
+def test_scan_ranges_partition(n_scans, world):
+    ranges = [sharding.scan_range(r, world, n_scans) for r in range(world)]
+    assert ranges[0][0] == 0 and ranges[-1][1] == n_scans
+    for (a0, a1), (b0, b1) in zip(ranges, ranges[1:]):
+        assert a1 == b0 and a0 <= a1
+    sizes = [hi - lo for lo, hi in ranges]
+    assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sharding.scan_range(world, world, n_scans)
