@@ -1,10 +1,179 @@
-// gtp_fast.cu - float64 anchor-relative fast path (placeholder: not enabled yet).
+// gtp_fast.cu - float64 CVIIRS 1 km -> 250 m / 500 m fast path for sm_100a.
+//
+// One THREAD owns one tie-point quad column of one scan and walks down the ten tie
+// rows of the scan; the neighbouring column's tie-point data comes from the next lane
+// by warp shuffle, so nothing is staged in shared memory and there is no barrier.
+// For every quad the thread projects the quad on the local frame of its corner A once
+// (gtp_fast_math.cuh) and then produces the quad's P x (P | P + P/2) fine pixels with
+// ~25 FP64 FMAs each; a warp therefore writes 31 x 32 B = 992 contiguous bytes per
+// fine row and output array with one 256-bit store per lane (st.global.v4.f64).
+//
+// HBM traffic per output pixel (1 km -> 250 m): 16 B written + 3 x 8 B / 16 read =
+// 17.5 B, the algorithmic minimum; the halo column a warp shares with its neighbour
+// is an L2 hit.  Warps cover 31 quad columns (lane 31 only provides the right
+// neighbour's tie points), 44 warps per scan; the thread of tie column 1353 produces
+// the P extra pixels right of the last quad (x = P .. 2P-1, extrapolation).
+#include <cuda_runtime.h>
 #include "gtp_kernels.h"
+#include "gtp_fast_math.cuh"
 
-bool gtp_cviirs_fast_f64_supported(const CviirsCfg&) { return false; }
+namespace {
 
-cudaError_t gtp_launch_cviirs_fast_f64(const double*, const double*, const double*, double*, double*,
-                                       long long, const CviirsCfg&, cudaStream_t)
+using namespace gtpfast;
+
+constexpr int kW = 1354;            // tie columns at 1 km
+constexpr int kL = 10;              // tie rows per scan
+constexpr int kQuadColsPerWarp = 31;
+constexpr int kWarpsPerScan = (kW + kQuadColsPerWarp - 1) / kQuadColsPerWarp;   // 44
+constexpr int kThreads = 128;
+constexpr unsigned kFull = 0xffffffffu;
+
+template <int P>
+__device__ __forceinline__ void store_px(double* p, const double (&v)[P]);
+
+template <>
+__device__ __forceinline__ void store_px<4>(double* p, const double (&v)[4])
 {
-    return cudaErrorNotSupported;
+    asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+}
+
+template <>
+__device__ __forceinline__ void store_px<2>(double* p, const double (&v)[2])
+{
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v[0]), "d"(v[1]) : "memory");
+}
+
+__device__ __forceinline__ double ldg(const double* p)
+{
+    return __ldg(p);
+}
+
+template <int P>
+__global__ void __launch_bounds__(kThreads)
+cviirs_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restrict__ lat,
+                           const double* __restrict__ satz, double* __restrict__ out_lon,
+                           double* __restrict__ out_lat, long long n_scans)
+{
+    constexpr int kWf = kW * P;          // fine columns
+    constexpr int kN = kL * P;           // fine rows per scan
+    constexpr int kHalf = P / 2;
+
+    const long long warp_global = (blockIdx.x * (long long)kThreads + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long scan = warp_global / kWarpsPerScan;
+    if (scan >= n_scans) return;
+    const int w = (int)(warp_global - scan * kWarpsPerScan);
+    const int c = w * kQuadColsPerWarp + lane;          // tie column this lane computes
+    const int tc = min(c, kW - 1);
+    const bool last_warp = (w == kWarpsPerScan - 1);
+    const bool extra = (c == kW - 1);                   // also owns the pixels right of the last quad
+    const bool quad_lane = (lane < kQuadColsPerWarp) && (c <= kW - 2);
+    const bool active = quad_lane || extra;
+    const int quad_col = extra ? kW - 2 : c;
+    const int xoff = extra ? P : 0;
+
+    const long long in_base = scan * (long long)(kL * kW) + tc;
+    double* olon = out_lon + scan * (long long)kN * kWf + (long long)quad_col * P + xoff;
+    double* olat = out_lat + scan * (long long)kN * kWf + (long long)quad_col * P + xoff;
+
+    // sub-pixel fractions of this lane's P pixels along the scan (:341) and s_s (1 - s_s)
+    double s_s[P], k1[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+        s_s[k] = (double)(xoff + k) / (double)P;
+        k1[k] = s_s[k] * (1.0 - s_s[k]);
+    }
+
+    Tie topA;            // upper-left corner of the quad being formed
+    TieB topB;           // upper-right corner
+    double nlon = ldg(lon + in_base), nlat = ldg(lat + in_base), nsatz = ldg(satz + in_base);
+
+#pragma unroll 1
+    for (int r = 0; r < kL; ++r) {
+        const double clon = nlon, clat = nlat, csatz = nsatz;
+        if (r + 1 < kL) {            // prefetch the next tie row while this one is worked on
+            const long long o = in_base + (long long)(r + 1) * kW;
+            nlon = ldg(lon + o); nlat = ldg(lat + o); nsatz = ldg(satz + o);
+        }
+        const Tie own = tie_setup(clon, clat, csatz);
+        Tie curA = own;
+        TieB curB;
+        curB.x = __shfl_down_sync(kFull, own.x, 1);
+        curB.y = __shfl_down_sync(kFull, own.y, 1);
+        curB.z = __shfl_down_sync(kFull, own.z, 1);
+        curB.phi = __shfl_down_sync(kFull, own.phi, 1);
+        curB.theta = __shfl_down_sync(kFull, own.theta, 1);
+        if (last_warp) {             // warp-uniform: the lane of tie column 1353 takes A from its left neighbour
+            Tie up;
+            up.x = __shfl_up_sync(kFull, own.x, 1); up.y = __shfl_up_sync(kFull, own.y, 1);
+            up.z = __shfl_up_sync(kFull, own.z, 1);
+            up.sl = __shfl_up_sync(kFull, own.sl, 1); up.cl = __shfl_up_sync(kFull, own.cl, 1);
+            up.sp = __shfl_up_sync(kFull, own.sp, 1); up.cp = __shfl_up_sync(kFull, own.cp, 1);
+            up.lon = __shfl_up_sync(kFull, own.lon, 1); up.lat = __shfl_up_sync(kFull, own.lat, 1);
+            up.phi = __shfl_up_sync(kFull, own.phi, 1); up.theta = __shfl_up_sync(kFull, own.theta, 1);
+            if (extra) {
+                curA = up;
+                curB.x = own.x; curB.y = own.y; curB.z = own.z; curB.phi = own.phi; curB.theta = own.theta;
+            }
+        }
+
+        if (r > 0 && active) {
+            const int qr = r - 1;    // quad row; its fine rows (a6): [j0, j1)
+            const int j0 = (qr == 0) ? 0 : qr * P + kHalf;
+            const int j1 = (qr == kL - 2) ? kN : (qr + 1) * P + kHalf;
+            const Quad q = quad_setup(topA, topB, curB.x, curB.y, curB.z, curA.x, curA.y, curA.z, 1);
+            if (q.mode != kSlow) {
+#pragma unroll 1
+                for (int j = j0; j < j1; ++j) {
+                    const double y = fine_row_y<P>(j);
+                    const RowCoef rc = row_setup(q, y / (double)P);
+                    double vlon[P], vlat[P];
+#pragma unroll
+                    for (int k = 0; k < P; ++k) pixel_eval(q, rc, s_s[k], k1[k], vlon[k], vlat[k]);
+                    store_px<P>(olon + (long long)j * kWf, vlon);
+                    store_px<P>(olat + (long long)j * kWf, vlat);
+                }
+            } else {
+#pragma unroll 1
+                for (int j = j0; j < j1; ++j) {
+                    const double y = fine_row_y<P>(j);
+                    double vlon[P], vlat[P];
+#pragma unroll 1
+                    for (int k = 0; k < P; ++k)
+                        pixel_eval_slow(topA, topB, curB.x, curB.y, curB.z, curA.x, curA.y, curA.z, q.ce, q.ca,
+                                        s_s[k], y / (double)P, vlon[k], vlat[k]);
+                    store_px<P>(olon + (long long)j * kWf, vlon);
+                    store_px<P>(olat + (long long)j * kWf, vlat);
+                }
+            }
+        }
+        topA = curA;
+        topB = curB;
+    }
+}
+
+}  // namespace
+
+bool gtp_cviirs_fast_f64_supported(const CviirsCfg& cfg)
+{
+    return cfg.km == 1 && (cfg.p == 4 || cfg.p == 2);
+}
+
+cudaError_t gtp_launch_cviirs_fast_f64(const double* lon, const double* lat, const double* satz,
+                                       double* out_lon, double* out_lat,
+                                       long long n_scans, const CviirsCfg& cfg, cudaStream_t stream)
+{
+    if (n_scans <= 0) return cudaSuccess;
+    // 256-bit (P = 4) / 128-bit (P = 2) stores need aligned outputs; the row pitch already is
+    const uintptr_t align = (cfg.p == 4) ? 32 : 16;
+    if (((uintptr_t)out_lon | (uintptr_t)out_lat) & (align - 1))
+        return gtp_launch_cviirs_generic<double>(lon, lat, satz, out_lon, out_lat, n_scans, cfg, stream);
+    const long long warps = n_scans * kWarpsPerScan;
+    const long long blocks = (warps * 32 + kThreads - 1) / kThreads;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    if (cfg.p == 4)
+        cviirs_fast_1km_f64_kernel<4><<<(unsigned)blocks, kThreads, 0, stream>>>(lon, lat, satz, out_lon, out_lat, n_scans);
+    else
+        cviirs_fast_1km_f64_kernel<2><<<(unsigned)blocks, kThreads, 0, stream>>>(lon, lat, satz, out_lon, out_lat, n_scans);
+    return cudaGetLastError();
 }

@@ -1,0 +1,255 @@
+// gtp_fast_math.cuh - anchor-relative float64 math of the CVIIRS 1 km fast path.
+//
+// Same algorithm as the reference (/root/reference/geotiepoints/_modis_interpolator.pyx
+// :41-82 expansion/alignment, :328-344 a_track/a_scan, :379-398 bilinear blend of the
+// Cartesian tie points; _modis_utils.pyx:26-65 transforms), re-formulated so that the
+// per-pixel work is ~25 FP64 FMAs instead of two inverse-trig calls, a sqrt and two
+// divisions (SURVEY.md 7 "hard part 1"):
+//
+//   * every fine pixel of a tie-point quad lies within a few km of the quad's corner A,
+//     whose lon/lat are INPUTS.  With the quad written as  v = A + a P + t Q + a t S
+//     (P = B-A, Q = D-A, S = C-D-B+A;  a = a_scan, t = a_track), the displacement
+//     d = v - A is projected once per quad on the local frame at A
+//     (east e, horizontal-radial h, polar axis z) and pre-scaled by 1/rho_A and 1/R;
+//   * lon = lon_A + atan(e' / (1 + h'))        - one Newton-refined reciprocal and a
+//                                                3-term series (|e'|,|h'| <= 0.01);
+//   * lat = lat_A + Taylor series of asin((z_A + d_z)/R) around z_A/R  (|z| < 0.8 R,
+//     the reference's low-latitude branch, _modis_utils.pyx:62-63), or of
+//     sign(z) acos(rho/R) around rho_A/R (high-latitude branch, :65), 5 terms.
+//
+// The reformulation is exact up to the truncation of the series; a quad is accepted
+// (`Quad::mode`) only when its size guarantees a truncation error below 2e-13 deg, else
+// the caller falls back to the rounding-faithful per-pixel evaluation.  The functions
+// are __host__ __device__ so that tests/host_emulation.cpp can run exactly this math
+// on the CPU against the oracle.
+#pragma once
+#include <math.h>
+#include "gtp_common.cuh"
+
+namespace gtpfast {
+
+enum QuadMode { kSlow = 0, kLow = 1, kHigh = 2, kBoth = 3 };
+
+// The reference's latitude switch: z < thr*R and z > -thr*R with thr = 0.8
+#define GTP_LAT_SWITCH 0.8
+// acceptance limits of the series (see header)
+#define GTP_MAX_REL_HORIZ 0.01   // bound on |d_horizontal| / rho_A
+#define GTP_MAX_REL_Z 2.0e-3     // bound on |d_z| / R
+// bounds on |a_scan|, |a_track|, |a_scan * a_track| used to bound |d|
+#define GTP_A_BOUND 2.3
+#define GTP_T_BOUND 1.4
+#define GTP_AT_BOUND 3.3
+
+struct Tie {               // one tie point, everything a quad may need from it
+    double x, y, z;        // Cartesian, metres (lonlat2xyz)
+    double sl, cl;         // sin / cos of the longitude
+    double sp, cp;         // sin / cos of the latitude
+    double lon, lat;       // the inputs, degrees
+    double phi, theta;     // _compute_phi(zeta), _compute_theta(zeta, phi) of its satz
+};
+
+struct TieB {              // what a quad needs from its corner B (upper right)
+    double x, y, z, phi, theta;
+};
+
+struct Quad {
+    int mode;
+    double ce, ca;                       // c_expansion, c_alignment
+    double Pe, Ph, Pw, Qe, Qh, Qw, Se, Sh, Sw;   // scaled frame components of P, Q, S
+    double lon0, lat0;                   // anchor, degrees
+    double s0;                           // z_A / R
+    double a1, a2, a3, a4, a5;           // low-latitude series (degrees per w^k)
+    double b1, b2, b3, b4, b5;           // high-latitude series (degrees per v^k), v = (rho-rho_A)/rho_A
+    bool wrap;                           // lon may cross +-180
+};
+
+GTP_HD Tie tie_setup(double lon, double lat, double satz)
+{
+    Tie t;
+    t.lon = lon; t.lat = lat;
+    sincos(lon * GTP_DEG2RAD, &t.sl, &t.cl);
+    sincos(lat * GTP_DEG2RAD, &t.sp, &t.cp);
+    const double rc = GTP_EARTH_RADIUS * t.cp;
+    t.x = rc * t.cl; t.y = rc * t.sl; t.z = GTP_EARTH_RADIUS * t.sp;
+    const double za = satz * GTP_DEG2RAD;
+    t.phi = asin((GTP_RK * sin(za)) / (GTP_RK + GTP_H));
+    t.theta = za - t.phi;
+    return t;
+}
+
+// expansion / alignment of the quad whose upper corners are a (left) and b (right)
+GTP_HD void quad_exp_ali(double phi_a, double theta_a, double phi_b, double theta_b, int km,
+                         double& ce, double& ca)
+{
+    const double phi = (phi_a + phi_b) * 0.5;
+    double sphi, cphi;
+    sincos(phi, &sphi, &cphi);
+    const double szeta = ((GTP_RK + GTP_H) * sphi) / GTP_RK;      // = sin(asin(.)) of :82
+    const double zeta = asin(szeta);
+    const double theta = zeta - phi;
+    const double czeta = sqrt(fma(-szeta, szeta, 1.0));
+    const double den = (theta_a == theta_b) ? theta_a * 2.0 : theta_a - theta_b;   // :61-62
+    const double inv_den = 4.0 / den;
+    ce = ((theta_a + theta_b) * 0.5 - theta) * inv_den;
+    const double d = (((GTP_RK + GTP_H) / GTP_RK) * cphi - czeta) * ((double)km / (2.0 * GTP_H));
+    const double e = czeta - sqrt(czeta * czeta - d * d);
+    ca = (e * szeta) * inv_den;
+}
+
+GTP_HD double absd(double x) { return fabs(x); }
+
+// A, B = upper left / right, D, C = lower left / right corner of the quad
+GTP_HD Quad quad_setup(const Tie& A, const TieB& B, double Cx, double Cy, double Cz,
+                       double Dx, double Dy, double Dz, int km)
+{
+    Quad q;
+    quad_exp_ali(A.phi, A.theta, B.phi, B.theta, km, q.ce, q.ca);
+
+    const double inv_c = 1.0 / A.cp;
+    const double inv_rho = inv_c * (1.0 / GTP_EARTH_RADIUS);
+    const double inv_R = 1.0 / GTP_EARTH_RADIUS;
+    const double Px = B.x - A.x, Py = B.y - A.y, Pz = B.z - A.z;
+    const double Qx = Dx - A.x, Qy = Dy - A.y, Qz = Dz - A.z;
+    const double Sx = (Cx - Dx) - Px, Sy = (Cy - Dy) - Py, Sz = (Cz - Dz) - Pz;
+    q.Pe = fma(-A.sl, Px, A.cl * Py) * inv_rho; q.Ph = fma(A.cl, Px, A.sl * Py) * inv_rho; q.Pw = Pz * inv_R;
+    q.Qe = fma(-A.sl, Qx, A.cl * Qy) * inv_rho; q.Qh = fma(A.cl, Qx, A.sl * Qy) * inv_rho; q.Qw = Qz * inv_R;
+    q.Se = fma(-A.sl, Sx, A.cl * Sy) * inv_rho; q.Sh = fma(A.cl, Sx, A.sl * Sy) * inv_rho; q.Sw = Sz * inv_R;
+    q.lon0 = A.lon; q.lat0 = A.lat; q.s0 = A.sp;
+
+    // size of the displacement over the whole quad (incl. the extrapolated edge pixels)
+    const double horiz = GTP_A_BOUND * (absd(q.Pe) + absd(q.Ph)) + GTP_T_BOUND * (absd(q.Qe) + absd(q.Qh))
+                         + GTP_AT_BOUND * (absd(q.Se) + absd(q.Sh));
+    const double wmax = GTP_A_BOUND * absd(q.Pw) + GTP_T_BOUND * absd(q.Qw) + GTP_AT_BOUND * absd(q.Sw);
+    // written so that any NaN (lon/lat/satz) fails the test and takes the slow path
+    const bool ok = (horiz <= GTP_MAX_REL_HORIZ) && (wmax <= GTP_MAX_REL_Z)
+                    && (absd(q.ce) <= 1.0) && (absd(q.ca) <= 0.5) && (A.cp > 1e-6);
+    if (!ok) { q.mode = kSlow; return q; }
+
+    const double zr_lo = q.s0 - wmax, zr_hi = q.s0 + wmax;
+    const double margin = 1e-9;
+    if (zr_hi < GTP_LAT_SWITCH - margin && zr_lo > -GTP_LAT_SWITCH + margin) q.mode = kLow;
+    else if (zr_lo > GTP_LAT_SWITCH + margin || zr_hi < -GTP_LAT_SWITCH - margin) q.mode = kHigh;
+    else q.mode = kBoth;
+    q.wrap = (absd(q.lon0) + 1.05 * horiz * GTP_RAD2DEG) >= 180.0;
+
+    if (q.mode & kLow) {
+        // d/dw^k of asin(s + w) at w = 0, over k!  (s = sin lat_A, c = cos lat_A)
+        const double s = A.sp, s2 = s * s, u = inv_c * inv_c;
+        double m = inv_c * GTP_RAD2DEG;
+        q.a1 = m;
+        m *= u; q.a2 = 0.5 * s * m;
+        m *= u; q.a3 = fma(2.0, s2, 1.0) * (1.0 / 6.0) * m;
+        m *= u; q.a4 = s * fma(2.0, s2, 3.0) * 0.125 * m;
+        m *= u; q.a5 = fma(s2, fma(8.0, s2, 24.0), 3.0) * (1.0 / 40.0) * m;
+    }
+    if (q.mode & kHigh) {
+        // lat = sign(z) * acos(rho / R);  rho / R = c * (1 + v),  v = (rho - rho_A) / rho_A.
+        // acos(c + c v) = |lat_A| - sum_k asinser_k(s -> c, c -> |s|) (c v)^k
+        const double c = A.cp, c2 = c * c, sa = absd(A.sp);
+        const double inv_s = 1.0 / sa, u = inv_s * inv_s;
+        const double sgn = (A.sp < 0.0) ? GTP_RAD2DEG : -GTP_RAD2DEG;   // -sign(z) * rad2deg
+        double m = inv_s * c * sgn;
+        q.b1 = m;
+        m *= u * c; q.b2 = 0.5 * c * m;
+        m *= u * c; q.b3 = fma(2.0, c2, 1.0) * (1.0 / 6.0) * m;
+        m *= u * c; q.b4 = c * fma(2.0, c2, 3.0) * 0.125 * m;
+        m *= u * c; q.b5 = fma(c2, fma(8.0, c2, 24.0), 3.0) * (1.0 / 40.0) * m;
+    }
+    return q;
+}
+
+struct RowCoef {           // per (quad, fine row): the a_track-dependent half of the bilinear form
+    double Ue, Uh, Uw, Ve, Vh, Vw;
+    double a_base;         // s_t (1 - s_t) c_ali
+};
+
+GTP_HD RowCoef row_setup(const Quad& q, double s_t)
+{
+    RowCoef r;
+    r.Ue = fma(s_t, q.Se, q.Pe); r.Uh = fma(s_t, q.Sh, q.Ph); r.Uw = fma(s_t, q.Sw, q.Pw);
+    r.Ve = s_t * q.Qe; r.Vh = s_t * q.Qh; r.Vw = s_t * q.Qw;
+    r.a_base = (s_t * (1.0 - s_t)) * q.ca;
+    return r;
+}
+
+// one fine pixel at along-scan fraction s_s (k1 = s_s (1 - s_s))
+GTP_HD void pixel_eval(const Quad& q, const RowCoef& r, double s_s, double k1, double& lon, double& lat)
+{
+    const double a = fma(k1, q.ce, s_s) + r.a_base;                 // :344
+    const double e = fma(a, r.Ue, r.Ve);
+    const double h = fma(a, r.Uh, r.Vh);
+    const double w = fma(a, r.Uw, r.Vw);
+    // t = e / (1 + h): 1/(1+h) ~ 1 - h + h^2, one Newton step (|h| <= 0.01 -> rel. error 1e-12)
+    const double g = 1.0 + h;
+    double rcp = fma(h, h - 1.0, 1.0);
+    rcp = fma(rcp, fma(-g, rcp, 1.0), rcp);
+    const double t = e * rcp;
+    const double t2 = t * t;
+    // atan(t) = t - t^3/3 + t^5/5 - t^7/7   (|t| <= 0.011 -> next term 3e-19)
+    const double at = fma(t * t2, fma(t2, fma(t2, -1.0 / 7.0, 0.2), -1.0 / 3.0), t);
+    double lo = fma(at, GTP_RAD2DEG, q.lon0);
+    if (q.wrap) {
+        if (lo > 180.0) lo -= 360.0;
+        else if (lo < -180.0) lo += 360.0;
+    }
+    lon = lo;
+
+    double la_low = 0.0, la_high = 0.0;
+    if (q.mode & kLow)
+        la_low = fma(w, fma(w, fma(w, fma(w, fma(w, q.a5, q.a4), q.a3), q.a2), q.a1), q.lat0);
+    if (q.mode & kHigh) {
+        // rho / rho_A = (1 + h) sqrt(1 + t^2);  v = h + g (t^2/2 - t^4/8 + t^6/16)
+        const double v = fma(g, t2 * fma(t2, fma(t2, 0.0625, -0.125), 0.5), h);
+        la_high = fma(v, fma(v, fma(v, fma(v, fma(v, q.b5, q.b4), q.b3), q.b2), q.b1), q.lat0);
+    }
+    if (q.mode == kLow) lat = la_low;
+    else if (q.mode == kHigh) lat = la_high;
+    else {
+        const double zr = q.s0 + w;
+        lat = (zr < GTP_LAT_SWITCH && zr > -GTP_LAT_SWITCH) ? la_low : la_high;
+    }
+}
+
+// ---- rounding-faithful per-pixel evaluation (fallback for quads the series cannot take) ----
+GTP_HD int sign_of(double x) { return x > 0.0 ? 1 : (x < 0.0 ? -1 : 0); }
+
+GTP_HD void xyz_to_lonlat(double x, double y, double z, double& lon, double& lat)
+{
+    const double rho = sqrt(x * x + y * y);
+    lon = (acos(x / rho) * GTP_RAD2DEG) * (double)sign_of(y);
+    if ((z < (GTP_LAT_SWITCH * GTP_EARTH_RADIUS)) && (z > ((-1.0 * GTP_LAT_SWITCH) * GTP_EARTH_RADIUS)))
+        lat = 90.0 - acos(z / GTP_EARTH_RADIUS) * GTP_RAD2DEG;
+    else
+        lat = (double)sign_of(z) * (90.0 - asin(rho / GTP_EARTH_RADIUS) * GTP_RAD2DEG);
+}
+
+GTP_HD double blend(double a_scan, double a_track, double A, double B, double C, double D)
+{
+    const double scan1 = (1.0 - a_scan) * A + a_scan * B;
+    const double scan2 = (1.0 - a_scan) * D + a_scan * C;
+    return (1.0 - a_track) * scan1 + a_track * scan2;
+}
+
+GTP_HD void pixel_eval_slow(const Tie& A, const TieB& B, double Cx, double Cy, double Cz,
+                            double Dx, double Dy, double Dz, double ce, double ca,
+                            double s_s, double s_t, double& lon, double& lat)
+{
+    const double a_scan = (s_s + (s_s * (1.0 - s_s)) * ce) + (s_t * (1.0 - s_t)) * ca;
+    const double x = blend(a_scan, s_t, A.x, B.x, Cx, Dx);
+    const double y = blend(a_scan, s_t, A.y, B.y, Cy, Dy);
+    const double z = blend(a_scan, s_t, A.z, B.z, Cz, Dz);
+    xyz_to_lonlat(x, y, z, lon, lat);
+}
+
+// y[j] of _get_coords_1km (a4): 0.5 + j - h on the first h rows of the scan, continuing
+// past f on the last h rows, ((j + h) mod f) + 0.5 in between (f = P, h = P / 2, n = 10 P)
+template <int P>
+GTP_HD double fine_row_y(int j)
+{
+    constexpr int kHalf = P / 2, kN = 10 * P;
+    return (j < kHalf) ? (0.5 + j - kHalf)
+         : (j >= kN - kHalf) ? ((P + 0.5) + (kHalf - (kN - j)))
+         : (((j + kHalf) % P) + 0.5);
+}
+
+}  // namespace gtpfast

@@ -1,0 +1,55 @@
+// host_emulation.cpp - runs the float64 fast-path MATH of the CUDA kernel on the CPU.
+//
+// TEST INFRASTRUCTURE (tests/test_fast_math_host.py).  It includes the very header the
+// kernel is built from (csrc/gtp_fast_math.cuh, __host__ __device__ functions) and replaces
+// only the warp orchestration of gtp_fast.cu by plain loops, so the series, the acceptance
+// test and the fallback can be checked against the oracle without a GPU.  It is not part of
+// the product and is never loaded by geotiepoints_b200.
+#include <cstdint>
+#include "../python-geotiepoints_b200/geotiepoints_b200/csrc/gtp_fast_math.cuh"
+
+using namespace gtpfast;
+
+template <int P>
+static void run(const double* lon, const double* lat, const double* satz, long n_scans,
+                double* out_lon, double* out_lat, long* mode_counts)
+{
+    const int W = 1354, L = 10, Wf = W * P, N = L * P, H = P / 2;
+    for (long s = 0; s < n_scans; ++s) {
+        for (int qc = 0; qc <= W - 1; ++qc) {            // qc == W-1: the "extra" pixels of the last quad
+            const bool extra = (qc == W - 1);
+            const int ca = extra ? W - 2 : qc, cb = ca + 1, xoff = extra ? P : 0;
+            for (int qr = 0; qr < L - 1; ++qr) {
+                auto at = [&](int r, int c) { long o = (s * L + r) * W + c; return tie_setup(lon[o], lat[o], satz[o]); };
+                const Tie A = at(qr, ca), Bf = at(qr, cb), D = at(qr + 1, ca), C = at(qr + 1, cb);
+                TieB B; B.x = Bf.x; B.y = Bf.y; B.z = Bf.z; B.phi = Bf.phi; B.theta = Bf.theta;
+                const Quad q = quad_setup(A, B, C.x, C.y, C.z, D.x, D.y, D.z, 1);
+                mode_counts[q.mode]++;
+                const int j0 = (qr == 0) ? 0 : qr * P + H;
+                const int j1 = (qr == L - 2) ? N : (qr + 1) * P + H;
+                for (int j = j0; j < j1; ++j) {
+                    const double s_t = fine_row_y<P>(j) / (double)P;
+                    const RowCoef rc = row_setup(q, s_t);
+                    for (int k = 0; k < P; ++k) {
+                        const double s_s = (double)(xoff + k) / (double)P;
+                        double lo, la;
+                        if (q.mode != kSlow) pixel_eval(q, rc, s_s, s_s * (1.0 - s_s), lo, la);
+                        else pixel_eval_slow(A, B, C.x, C.y, C.z, D.x, D.y, D.z, q.ce, q.ca, s_s, s_t, lo, la);
+                        const long o = (s * N + j) * (long)Wf + (long)ca * P + xoff + k;
+                        out_lon[o] = lo; out_lat[o] = la;
+                    }
+                }
+            }
+        }
+    }
+}
+
+extern "C" int gtp_emul_cviirs_fast_f64(const double* lon, const double* lat, const double* satz, long n_scans,
+                                        int fine_res, double* out_lon, double* out_lat, long* mode_counts)
+{
+    for (int k = 0; k < 4; ++k) mode_counts[k] = 0;
+    if (fine_res == 250) run<4>(lon, lat, satz, n_scans, out_lon, out_lat, mode_counts);
+    else if (fine_res == 500) run<2>(lon, lat, satz, n_scans, out_lon, out_lat, mode_counts);
+    else return 1;
+    return 0;
+}
