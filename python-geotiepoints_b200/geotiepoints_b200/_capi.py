@@ -12,7 +12,8 @@ import weakref
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgtp_b200.so")
+# GTP_B200_LIB lets a developer point at an experimental build of the same ABI
+LIB_PATH = os.environ.get("GTP_B200_LIB") or os.path.join(_HERE, "libgtp_b200.so")
 
 GTP_E_WIDTH_5KM = 2
 GTP_E_NO_DEVICE = 5

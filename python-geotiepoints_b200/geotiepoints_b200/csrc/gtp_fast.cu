@@ -27,6 +27,9 @@ constexpr int kQuadColsPerWarp = 31;
 constexpr int kWarpsPerScan = (kW + kQuadColsPerWarp - 1) / kQuadColsPerWarp;   // 44
 constexpr int kThreads = 128;
 constexpr unsigned kFull = 0xffffffffu;
+#ifndef GTP_FAST_MIN_BLOCKS
+#define GTP_FAST_MIN_BLOCKS 4     // resident CTAs per SM the register allocation is tuned for
+#endif
 
 template <int P>
 __device__ __forceinline__ void store_px(double* p, const double (&v)[P]);
@@ -48,8 +51,28 @@ __device__ __forceinline__ double ldg(const double* p)
     return __ldg(p);
 }
 
+// the fine rows [0, nrows) of one quad, first row at a_track = s_t0, branch-free per pixel
+template <int P, int MODE, bool WRAP>
+__device__ __forceinline__ void quad_rows(const Quad& q, const double (&a_col)[P], double s_t0, int nrows,
+                                          double* olon, double* olat)
+{
+    constexpr long long kPitch = (long long)kW * P;
+    double s_t = s_t0;
+#pragma unroll 1
+    for (int m = 0; m < nrows; ++m) {
+        const RowCoef rc = row_setup(q, s_t);
+        double vlon[P], vlat[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) pixel_eval<MODE, WRAP>(q, rc, a_col[k], vlon[k], vlat[k]);
+        store_px<P>(olon, vlon);
+        store_px<P>(olat, vlat);
+        olon += kPitch; olat += kPitch;
+        s_t += 1.0 / P;              // exact: multiples of 1/8
+    }
+}
+
 template <int P>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, GTP_FAST_MIN_BLOCKS)
 cviirs_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restrict__ lat,
                            const double* __restrict__ satz, double* __restrict__ out_lon,
                            double* __restrict__ out_lat, long long n_scans)
@@ -72,28 +95,22 @@ cviirs_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restr
     const int quad_col = extra ? kW - 2 : c;
     const int xoff = extra ? P : 0;
 
-    const long long in_base = scan * (long long)(kL * kW) + tc;
+    const double* plon = lon + scan * (long long)(kL * kW) + tc;
+    const double* plat = lat + scan * (long long)(kL * kW) + tc;
+    const double* psatz = satz + scan * (long long)(kL * kW) + tc;
     double* olon = out_lon + scan * (long long)kN * kWf + (long long)quad_col * P + xoff;
     double* olat = out_lat + scan * (long long)kN * kWf + (long long)quad_col * P + xoff;
 
-    // sub-pixel fractions of this lane's P pixels along the scan (:341) and s_s (1 - s_s)
-    double s_s[P], k1[P];
-#pragma unroll
-    for (int k = 0; k < P; ++k) {
-        s_s[k] = (double)(xoff + k) / (double)P;
-        k1[k] = s_s[k] * (1.0 - s_s[k]);
-    }
-
     Tie topA;            // upper-left corner of the quad being formed
     TieB topB;           // upper-right corner
-    double nlon = ldg(lon + in_base), nlat = ldg(lat + in_base), nsatz = ldg(satz + in_base);
+    double nlon = ldg(plon), nlat = ldg(plat), nsatz = ldg(psatz);
 
 #pragma unroll 1
     for (int r = 0; r < kL; ++r) {
         const double clon = nlon, clat = nlat, csatz = nsatz;
         if (r + 1 < kL) {            // prefetch the next tie row while this one is worked on
-            const long long o = in_base + (long long)(r + 1) * kW;
-            nlon = ldg(lon + o); nlat = ldg(lat + o); nsatz = ldg(satz + o);
+            plon += kW; plat += kW; psatz += kW;
+            nlon = ldg(plon); nlat = ldg(plat); nsatz = ldg(psatz);
         }
         const Tie own = tie_setup(clon, clat, csatz);
         Tie curA = own;
@@ -118,34 +135,41 @@ cviirs_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restr
         }
 
         if (r > 0 && active) {
-            const int qr = r - 1;    // quad row; its fine rows (a6): [j0, j1)
-            const int j0 = (qr == 0) ? 0 : qr * P + kHalf;
-            const int j1 = (qr == kL - 2) ? kN : (qr + 1) * P + kHalf;
+            // quad row qr = r - 1 covers the fine rows [j0, j0 + nrows) of the scan (a6); its first
+            // row sits at y = 0.5 (a4), except for the top quad row whose first h rows extrapolate
+            const int qr = r - 1;
+            const int nrows = P + ((qr == 0 || qr == kL - 2) ? kHalf : 0);
+            const double s_t0 = ((qr == 0) ? (0.5 - kHalf) : 0.5) / P;
             const Quad q = quad_setup(topA, topB, curB.x, curB.y, curB.z, curA.x, curA.y, curA.z, 1);
             if (q.mode != kSlow) {
-#pragma unroll 1
-                for (int j = j0; j < j1; ++j) {
-                    const double y = fine_row_y<P>(j);
-                    const RowCoef rc = row_setup(q, y / (double)P);
-                    double vlon[P], vlat[P];
+                double a_col[P];     // s_s + s_s (1 - s_s) c_exp  (:341, :344)
 #pragma unroll
-                    for (int k = 0; k < P; ++k) pixel_eval(q, rc, s_s[k], k1[k], vlon[k], vlat[k]);
-                    store_px<P>(olon + (long long)j * kWf, vlon);
-                    store_px<P>(olat + (long long)j * kWf, vlat);
+                for (int k = 0; k < P; ++k) {
+                    const double s_s = (double)(xoff + k) / (double)P;
+                    a_col[k] = fma(s_s * (1.0 - s_s), q.ce, s_s);
+                }
+                if (!q.wrap) {
+                    if (q.mode == kLow) quad_rows<P, kLow, false>(q, a_col, s_t0, nrows, olon, olat);
+                    else if (q.mode == kHigh) quad_rows<P, kHigh, false>(q, a_col, s_t0, nrows, olon, olat);
+                    else quad_rows<P, kBoth, false>(q, a_col, s_t0, nrows, olon, olat);
+                } else {
+                    quad_rows<P, kBoth, true>(q, a_col, s_t0, nrows, olon, olat);
                 }
             } else {
 #pragma unroll 1
-                for (int j = j0; j < j1; ++j) {
-                    const double y = fine_row_y<P>(j);
+                for (int m = 0; m < nrows; ++m) {
+                    const double s_t = s_t0 + m * (1.0 / P);
                     double vlon[P], vlat[P];
 #pragma unroll 1
                     for (int k = 0; k < P; ++k)
                         pixel_eval_slow(topA, topB, curB.x, curB.y, curB.z, curA.x, curA.y, curA.z, q.ce, q.ca,
-                                        s_s[k], y / (double)P, vlon[k], vlat[k]);
-                    store_px<P>(olon + (long long)j * kWf, vlon);
-                    store_px<P>(olat + (long long)j * kWf, vlat);
+                                        (double)(xoff + k) / (double)P, s_t, vlon[k], vlat[k]);
+                    store_px<P>(olon + (long long)m * kWf, vlon);
+                    store_px<P>(olat + (long long)m * kWf, vlat);
                 }
             }
+            olon += (long long)nrows * kWf;
+            olat += (long long)nrows * kWf;
         }
         topA = curA;
         topB = curB;

@@ -103,6 +103,9 @@ GTP_HD Quad quad_setup(const Tie& A, const TieB& B, double Cx, double Cy, double
                        double Dx, double Dy, double Dz, int km)
 {
     Quad q;
+    q.a1 = q.a2 = q.a3 = q.a4 = q.a5 = 0.0;
+    q.b1 = q.b2 = q.b3 = q.b4 = q.b5 = 0.0;
+    q.wrap = false;
     quad_exp_ali(A.phi, A.theta, B.phi, B.theta, km, q.ce, q.ca);
 
     const double inv_c = 1.0 / A.cp;
@@ -172,10 +175,13 @@ GTP_HD RowCoef row_setup(const Quad& q, double s_t)
     return r;
 }
 
-// one fine pixel at along-scan fraction s_s (k1 = s_s (1 - s_s))
-GTP_HD void pixel_eval(const Quad& q, const RowCoef& r, double s_s, double k1, double& lon, double& lat)
+// One fine pixel.  `a_col` = s_s + s_s (1 - s_s) c_exp is the per-(quad, column) part of
+// a_scan (:344), r.a_base the per-(quad, row) part.  MODE and WRAP are compile-time so that
+// the row loops of the kernel are branch-free; they are quad properties (Quad::mode, ::wrap).
+template <int MODE, bool WRAP>
+GTP_HD void pixel_eval(const Quad& q, const RowCoef& r, double a_col, double& lon, double& lat)
 {
-    const double a = fma(k1, q.ce, s_s) + r.a_base;                 // :344
+    const double a = a_col + r.a_base;
     const double e = fma(a, r.Ue, r.Ve);
     const double h = fma(a, r.Uh, r.Vh);
     const double w = fma(a, r.Uw, r.Vw);
@@ -185,25 +191,25 @@ GTP_HD void pixel_eval(const Quad& q, const RowCoef& r, double s_s, double k1, d
     rcp = fma(rcp, fma(-g, rcp, 1.0), rcp);
     const double t = e * rcp;
     const double t2 = t * t;
-    // atan(t) = t - t^3/3 + t^5/5 - t^7/7   (|t| <= 0.011 -> next term 3e-19)
-    const double at = fma(t * t2, fma(t2, fma(t2, -1.0 / 7.0, 0.2), -1.0 / 3.0), t);
+    // atan(t) = t - t^3/3 + t^5/5   (|t| <= 0.011 -> next term 3e-15 rad)
+    const double at = fma(t * t2, fma(t2, 0.2, -1.0 / 3.0), t);
     double lo = fma(at, GTP_RAD2DEG, q.lon0);
-    if (q.wrap) {
+    if (WRAP) {
         if (lo > 180.0) lo -= 360.0;
         else if (lo < -180.0) lo += 360.0;
     }
     lon = lo;
 
     double la_low = 0.0, la_high = 0.0;
-    if (q.mode & kLow)
+    if (MODE & kLow)
         la_low = fma(w, fma(w, fma(w, fma(w, fma(w, q.a5, q.a4), q.a3), q.a2), q.a1), q.lat0);
-    if (q.mode & kHigh) {
+    if (MODE & kHigh) {
         // rho / rho_A = (1 + h) sqrt(1 + t^2);  v = h + g (t^2/2 - t^4/8 + t^6/16)
         const double v = fma(g, t2 * fma(t2, fma(t2, 0.0625, -0.125), 0.5), h);
         la_high = fma(v, fma(v, fma(v, fma(v, fma(v, q.b5, q.b4), q.b3), q.b2), q.b1), q.lat0);
     }
-    if (q.mode == kLow) lat = la_low;
-    else if (q.mode == kHigh) lat = la_high;
+    if (MODE == kLow) lat = la_low;
+    else if (MODE == kHigh) lat = la_high;
     else {
         const double zr = q.s0 + w;
         lat = (zr < GTP_LAT_SWITCH && zr > -GTP_LAT_SWITCH) ? la_low : la_high;

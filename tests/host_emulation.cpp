@@ -33,8 +33,12 @@ static void run(const double* lon, const double* lat, const double* satz, long n
                     for (int k = 0; k < P; ++k) {
                         const double s_s = (double)(xoff + k) / (double)P;
                         double lo, la;
-                        if (q.mode != kSlow) pixel_eval(q, rc, s_s, s_s * (1.0 - s_s), lo, la);
-                        else pixel_eval_slow(A, B, C.x, C.y, C.z, D.x, D.y, D.z, q.ce, q.ca, s_s, s_t, lo, la);
+                        const double a_col = fma(s_s * (1.0 - s_s), q.ce, s_s);
+                        if (q.mode == kSlow) pixel_eval_slow(A, B, C.x, C.y, C.z, D.x, D.y, D.z, q.ce, q.ca, s_s, s_t, lo, la);
+                        else if (q.wrap) pixel_eval<kBoth, true>(q, rc, a_col, lo, la);
+                        else if (q.mode == kLow) pixel_eval<kLow, false>(q, rc, a_col, lo, la);
+                        else if (q.mode == kHigh) pixel_eval<kHigh, false>(q, rc, a_col, lo, la);
+                        else pixel_eval<kBoth, false>(q, rc, a_col, lo, la);
                         const long o = (s * N + j) * (long)Wf + (long)ca * P + xoff + k;
                         out_lon[o] = lo; out_lat[o] = la;
                     }

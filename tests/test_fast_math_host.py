@@ -1,0 +1,91 @@
+"""The float64 fast-path math of the CUDA kernel, run on the CPU (tests/host_emulation.cpp
+includes csrc/gtp_fast_math.cuh) and checked against the oracle.  This pins the series, the
+acceptance test (`Quad::mode`) and the fallback without a GPU; the GPU tests then only have to
+show that the kernel's warp orchestration feeds the same math."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import gtp_oracle
+from conftest import ROOT
+from geotiepoints_b200 import testing
+from parity import assert_parity
+
+SRC = os.path.join(ROOT, "tests", "host_emulation.cpp")
+LIB = os.path.join(ROOT, "tests", "libgtp_host_emulation.so")
+HDRS = [os.path.join(ROOT, "python-geotiepoints_b200", "geotiepoints_b200", "csrc", n)
+        for n in ("gtp_fast_math.cuh", "gtp_common.cuh")]
+
+
+@pytest.fixture(scope="module")
+def emul():
+    if not os.path.exists(LIB) or any(os.path.getmtime(LIB) < os.path.getmtime(f) for f in [SRC] + HDRS):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=fast", "-mfma",
+                               SRC, "-o", LIB])
+    lib = ctypes.CDLL(LIB)
+    dp = ctypes.POINTER(ctypes.c_double)
+
+    def run(lon, lat, satz, fine):
+        ns, p = lon.shape[0] // 10, 1000 // fine
+        out_lon = np.full((ns * 10 * p, 1354 * p), np.nan)
+        out_lat = np.full_like(out_lon, np.nan)
+        modes = (ctypes.c_long * 4)()
+        rc = lib.gtp_emul_cviirs_fast_f64(lon.ctypes.data_as(dp), lat.ctypes.data_as(dp), satz.ctypes.data_as(dp),
+                                          ctypes.c_long(ns), fine, out_lon.ctypes.data_as(dp),
+                                          out_lat.ctypes.data_as(dp), modes)
+        assert rc == 0
+        return out_lon, out_lat, dict(zip(("slow", "low", "high", "both"), modes))
+    return run
+
+
+@pytest.mark.parametrize("fine", [250, 500])
+@pytest.mark.parametrize("granule", [0, 3, 5, 14, 287])
+def test_fast_math_matches_oracle(emul, granule, fine):
+    lon, lat, satz = testing.modis_granule(granule, n_scans=3)
+    got_lon, got_lat, modes = emul(lon, lat, satz, fine)
+    exp = gtp_oracle.cviirs(lon, lat, satz, 1000, fine, n_threads=4)
+    assert_parity(got_lon, got_lat, *exp, what=f"host emulation granule {granule} -> {fine} m, modes {modes}")
+
+
+def test_every_mode_is_exercised(emul):
+    seen = {"slow": 0, "low": 0, "high": 0, "both": 0}
+    for granule in (0, 3, 5):
+        lon, lat, satz = testing.modis_granule(granule, n_scans=2)
+        for k, v in emul(lon, lat, satz, 250)[2].items():
+            seen[k] += v
+    assert all(v > 0 for v in seen.values()), seen
+
+
+@pytest.mark.parametrize("name", ["antimeridian", "pole", "south_pole", "prime_meridian", "lat_switch",
+                                  "symmetric_satz", "zeros", "nan_holes"])
+def test_fast_math_stress_inputs(emul, golden_inputs, name):
+    lon, lat, satz = (a.astype(np.float64) for a in golden_inputs[name])
+    for fine in (250, 500):
+        got_lon, got_lat, modes = emul(lon, lat, satz, fine)
+        with np.errstate(all="ignore"):
+            exp = gtp_oracle.cviirs(lon, lat, satz, 1000, fine)
+        assert_parity(got_lon, got_lat, *exp, what=f"host emulation {name} -> {fine} m, modes {modes}")
+
+
+def test_unphysical_inputs_fall_back(emul):
+    """Tie points that are not MODIS-like spaced (random lon/lat) must take the slow path and
+    still agree with the oracle."""
+    rng = np.random.default_rng(5)
+    lon = rng.uniform(-180, 180, (10, 1354))
+    lat = rng.uniform(-89, 89, (10, 1354))
+    satz = rng.uniform(0, 65, (10, 1354))
+    got_lon, got_lat, modes = emul(lon, lat, satz, 250)
+    assert modes["slow"] > 0.99 * sum(modes.values())
+    with np.errstate(all="ignore"):
+        exp = gtp_oracle.cviirs(lon, lat, satz, 1000, 250)
+    # Chords between random points run deep inside the sphere, where the reference's formulas are
+    # ill-conditioned in ways that never occur for real geolocation (rho -> 0 away from the poles,
+    # rho / R -> 1 in the asin branch): an FMA contraction already moves the result by ~1e-9 deg.
+    # This test is about the fallback being taken and being the right formula, so 1e-7 deg.
+    from parity import compare
+    s = compare(got_lon, got_lat, *exp)
+    assert s["nan_pattern_equal"], s
+    assert s["max_dlat"] < 1e-7 and max(s["max_dlon_outside_band"], s["max_dlon_in_band"]) < 1e-7, s
