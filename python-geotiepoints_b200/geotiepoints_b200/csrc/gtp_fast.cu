@@ -28,7 +28,7 @@ constexpr int kWarpsPerScan = (kW + kQuadColsPerWarp - 1) / kQuadColsPerWarp;   
 constexpr int kThreads = 128;
 constexpr unsigned kFull = 0xffffffffu;
 #ifndef GTP_FAST_MIN_BLOCKS
-#define GTP_FAST_MIN_BLOCKS 4     // resident CTAs per SM the register allocation is tuned for
+#define GTP_FAST_MIN_BLOCKS 3     // resident CTAs per SM the register allocation is tuned for
 #endif
 
 template <int P>
@@ -118,8 +118,9 @@ cviirs_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restr
         curB.x = __shfl_down_sync(kFull, own.x, 1);
         curB.y = __shfl_down_sync(kFull, own.y, 1);
         curB.z = __shfl_down_sync(kFull, own.z, 1);
-        curB.phi = __shfl_down_sync(kFull, own.phi, 1);
-        curB.theta = __shfl_down_sync(kFull, own.theta, 1);
+        curB.za = __shfl_down_sync(kFull, own.za, 1);
+        curB.sphi = __shfl_down_sync(kFull, own.sphi, 1);
+        curB.cphi = __shfl_down_sync(kFull, own.cphi, 1);
         if (last_warp) {             // warp-uniform: the lane of tie column 1353 takes A from its left neighbour
             Tie up;
             up.x = __shfl_up_sync(kFull, own.x, 1); up.y = __shfl_up_sync(kFull, own.y, 1);
@@ -127,10 +128,13 @@ cviirs_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restr
             up.sl = __shfl_up_sync(kFull, own.sl, 1); up.cl = __shfl_up_sync(kFull, own.cl, 1);
             up.sp = __shfl_up_sync(kFull, own.sp, 1); up.cp = __shfl_up_sync(kFull, own.cp, 1);
             up.lon = __shfl_up_sync(kFull, own.lon, 1); up.lat = __shfl_up_sync(kFull, own.lat, 1);
-            up.phi = __shfl_up_sync(kFull, own.phi, 1); up.theta = __shfl_up_sync(kFull, own.theta, 1);
+            up.za = __shfl_up_sync(kFull, own.za, 1);
+            up.sz = __shfl_up_sync(kFull, own.sz, 1); up.cz = __shfl_up_sync(kFull, own.cz, 1);
+            up.sphi = __shfl_up_sync(kFull, own.sphi, 1); up.cphi = __shfl_up_sync(kFull, own.cphi, 1);
             if (extra) {
                 curA = up;
-                curB.x = own.x; curB.y = own.y; curB.z = own.z; curB.phi = own.phi; curB.theta = own.theta;
+                curB.x = own.x; curB.y = own.y; curB.z = own.z;
+                curB.za = own.za; curB.sphi = own.sphi; curB.cphi = own.cphi;
             }
         }
 

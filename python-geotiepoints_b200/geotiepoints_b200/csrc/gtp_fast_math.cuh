@@ -45,11 +45,14 @@ struct Tie {               // one tie point, everything a quad may need from it
     double sl, cl;         // sin / cos of the longitude
     double sp, cp;         // sin / cos of the latitude
     double lon, lat;       // the inputs, degrees
-    double phi, theta;     // _compute_phi(zeta), _compute_theta(zeta, phi) of its satz
+    // satellite-zenith chain (:52-57, :73-78), kept as sines/cosines instead of angles:
+    double za;             // zeta = deg2rad(satz)
+    double sz, cz;         // sin / cos zeta
+    double sphi, cphi;     // sin / cos of phi = asin(R sin(zeta) / (R + H))
 };
 
 struct TieB {              // what a quad needs from its corner B (upper right)
-    double x, y, z, phi, theta;
+    double x, y, z, za, sphi, cphi;
 };
 
 struct Quad {
@@ -63,37 +66,147 @@ struct Quad {
     bool wrap;                           // lon may cross +-180
 };
 
+// ---- lean elementary functions ------------------------------------------------------------
+// The tie-point / quad set-up runs once per 16 output pixels but CUDA's general-purpose
+// sincos / asin / sqrt / division carry argument-reduction slow paths, special-case fix-ups
+// and dozens of 64-bit immediates; measured (profiles/r01_fast_v2_ncu.txt) they made the
+// set-up two thirds of all issued instructions.  The inputs here are bounded angles and the
+// contract is 1e-10 deg (1.7e-12 relative on the Cartesian tie points), so: Cody-Waite
+// reduction by pi/2 with a two-part constant, the fdlibm minimax kernels on [-pi/4, pi/4]
+// (error < 2^-57), and MUFU-seeded Newton iterations for 1/x and sqrt(x).
+
+// 1/x to ~1 ulp (no special cases: 0 and inf give NaN, which routes the quad to the slow path)
+GTP_HD double fast_rcp(double x)
+{
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+#else
+    return 1.0 / x;
+#endif
+}
+
+// sqrt(x) to ~1 ulp for x > 0 (0 gives NaN -> slow path)
+GTP_HD double fast_sqrt(double x)
+{
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    y = y * fma(-hx * y, y, 1.5);
+    y = y * fma(-hx * y, y, 1.5);
+    const double sq = x * y;
+    return fma(fma(-sq, sq, x), 0.5 * y, sq);
+#else
+    return sqrt(x);
+#endif
+}
+
+// sin and cos of |x| <= 8 (longitudes, latitudes, zenith angles in radians)
+GTP_HD void fast_sincos(double x, double& sn, double& cs)
+{
+    if (!(fabs(x) <= 8.0)) { sincos(x, &sn, &cs); return; }    // out-of-range or NaN input: library path
+    const double kf = rint(x * 0.63661977236758138243);          // 2 / pi
+    double r = fma(-kf, 1.57079632679489655800e+00, x);           // pi/2 high part
+    r = fma(-kf, 6.12323399573676603587e-17, r);                  // pi/2 low part
+    const int quad = (int)kf;
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double sr = fma(r * z, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+    const double s0 = (quad & 1) ? cr : sr;
+    const double c0 = (quad & 1) ? sr : cr;
+    sn = (quad & 2) ? -s0 : s0;
+    cs = ((quad + 1) & 2) ? -c0 : c0;
+}
+
 GTP_HD Tie tie_setup(double lon, double lat, double satz)
 {
     Tie t;
     t.lon = lon; t.lat = lat;
-    sincos(lon * GTP_DEG2RAD, &t.sl, &t.cl);
-    sincos(lat * GTP_DEG2RAD, &t.sp, &t.cp);
+    fast_sincos(lon * GTP_DEG2RAD, t.sl, t.cl);
+    fast_sincos(lat * GTP_DEG2RAD, t.sp, t.cp);
     const double rc = GTP_EARTH_RADIUS * t.cp;
     t.x = rc * t.cl; t.y = rc * t.sl; t.z = GTP_EARTH_RADIUS * t.sp;
-    const double za = satz * GTP_DEG2RAD;
-    t.phi = asin((GTP_RK * sin(za)) / (GTP_RK + GTP_H));
-    t.theta = za - t.phi;
+    t.za = satz * GTP_DEG2RAD;
+    fast_sincos(t.za, t.sz, t.cz);
+    t.sphi = t.sz * (GTP_RK / (GTP_RK + GTP_H));                   // :74
+    t.cphi = fast_sqrt(fma(-t.sphi, t.sphi, 1.0));
     return t;
 }
 
-// expansion / alignment of the quad whose upper corners are a (left) and b (right)
-GTP_HD void quad_exp_ali(double phi_a, double theta_a, double phi_b, double theta_b, int km,
-                         double& ce, double& ca)
+// Expansion / alignment of the quad whose upper corners are a (left) and b (right),
+// _modis_interpolator.pyx:41-70, without inverse trigonometry.  With zm = (za + zb)/2:
+//   phi_a, phi_b are known through their sines/cosines; dphi = phi_b - phi_a and the mean
+//   phi follow from angle-difference identities with small-argument series;
+//   (theta_a + theta_b)/2 - theta  =  zm - zeta   (phi is the exact mean of phi_a, phi_b), and
+//   zeta - zm = asin(sin(zeta) cos(zm) - cos(zeta) sin(zm)) is a tiny angle;
+//   theta_a - theta_b = dphi - dz.
+// Returns false (ce, ca untouched) when the two zenith angles are too far apart for the
+// small-argument series; the caller then uses quad_exp_ali_exact.
+GTP_HD bool quad_exp_ali(double za, double sza, double cza, double sphi_a, double cphi_a,
+                         double zb, double sphi_b, double cphi_b, int km, double& ce, double& ca)
 {
-    const double phi = (phi_a + phi_b) * 0.5;
-    double sphi, cphi;
-    sincos(phi, &sphi, &cphi);
-    const double szeta = ((GTP_RK + GTP_H) * sphi) / GTP_RK;      // = sin(asin(.)) of :82
-    const double zeta = asin(szeta);
-    const double theta = zeta - phi;
-    const double czeta = sqrt(fma(-szeta, szeta, 1.0));
-    const double den = (theta_a == theta_b) ? theta_a * 2.0 : theta_a - theta_b;   // :61-62
-    const double inv_den = 4.0 / den;
-    ce = ((theta_a + theta_b) * 0.5 - theta) * inv_den;
-    const double d = (((GTP_RK + GTP_H) / GTP_RK) * cphi - czeta) * ((double)km / (2.0 * GTP_H));
-    const double e = czeta - sqrt(czeta * czeta - d * d);
+    const double K = (GTP_RK + GTP_H) / GTP_RK;
+    // dphi = asin(sin(phi_b - phi_a))
+    const double sd = fma(sphi_b, cphi_a, -(sphi_a * cphi_b));
+    const double dz = zb - za;
+    if (!(fabs(sd) <= 0.01 && fabs(dz) <= 0.02)) return false;      // also catches NaN
+    const double sd2 = sd * sd;
+    const double dphi = fma(sd * sd2, fma(sd2, 0.075, 1.0 / 6.0), sd);
+    // mean phi = phi_a + dphi / 2
+    const double hp = 0.5 * dphi, hp2 = hp * hp;
+    const double sh = fma(hp * hp2, fma(hp2, 1.0 / 120.0, -1.0 / 6.0), hp);
+    const double ch = fma(hp2, fma(hp2, 1.0 / 24.0, -0.5), 1.0);
+    const double sphi = fma(sphi_a, ch, cphi_a * sh);
+    const double cphi = fma(cphi_a, ch, -(sphi_a * sh));
+    const double szeta = K * sphi;                                   // sin(zeta) of :82
+    const double czeta = fast_sqrt(fma(-szeta, szeta, 1.0));
+    // zm = za + dz / 2
+    const double hz = 0.5 * dz, hz2 = hz * hz;
+    const double shz = fma(hz * hz2, fma(hz2, fma(hz2, -1.0 / 5040.0, 1.0 / 120.0), -1.0 / 6.0), hz);
+    const double chz = fma(hz2, fma(hz2, fma(hz2, -1.0 / 720.0, 1.0 / 24.0), -0.5), 1.0);
+    const double szm = fma(sza, chz, cza * shz);
+    const double czm = fma(cza, chz, -(sza * shz));
+    // delta = zeta - zm
+    const double sdel = fma(szeta, czm, -(czeta * szm));
+    const double delta = fma(sdel * (sdel * sdel), 1.0 / 6.0, sdel);
+    double den = dphi - dz;                                          // theta_a - theta_b
+    if (dz == 0.0) den = 2.0 * (za - asin(sphi_a));                  // :61-62, symmetric tie points
+    const double inv_den = 4.0 * fast_rcp(den);
+    ce = -delta * inv_den;
+    const double d = (K * cphi - czeta) * ((double)km / (2.0 * GTP_H));
+    const double e = czeta - fast_sqrt(fma(czeta, czeta, -(d * d)));
     ca = (e * szeta) * inv_den;
+    return true;
+}
+
+// the same coefficients, written exactly like the reference (:52-70), library functions
+GTP_HD void quad_exp_ali_exact(double za, double zb, int km, double& ce, double& ca)
+{
+    const double phi_a = asin((GTP_RK * sin(za)) / (GTP_RK + GTP_H));
+    const double phi_b = asin((GTP_RK * sin(zb)) / (GTP_RK + GTP_H));
+    const double theta_a = za - phi_a, theta_b = zb - phi_b;
+    const double phi = (phi_a + phi_b) / 2.0;
+    const double zeta = asin(((GTP_RK + GTP_H) * sin(phi)) / GTP_RK);
+    const double theta = zeta - phi;
+    const double den = (theta_a == theta_b) ? theta_a * 2.0 : theta_a - theta_b;
+    ce = 4.0 * ((((theta_a + theta_b) / 2.0) - theta) / den);
+    const double d = ((((GTP_RK + GTP_H) / GTP_RK) * cos(phi)) - cos(zeta)) * ((double)km / (2.0 * GTP_H));
+    const double e = cos(zeta) - sqrt((cos(zeta) * cos(zeta)) - (d * d));
+    ca = ((4.0 * e) * sin(zeta)) / den;
 }
 
 GTP_HD double absd(double x) { return fabs(x); }
@@ -106,9 +219,10 @@ GTP_HD Quad quad_setup(const Tie& A, const TieB& B, double Cx, double Cy, double
     q.a1 = q.a2 = q.a3 = q.a4 = q.a5 = 0.0;
     q.b1 = q.b2 = q.b3 = q.b4 = q.b5 = 0.0;
     q.wrap = false;
-    quad_exp_ali(A.phi, A.theta, B.phi, B.theta, km, q.ce, q.ca);
+    if (!quad_exp_ali(A.za, A.sz, A.cz, A.sphi, A.cphi, B.za, B.sphi, B.cphi, km, q.ce, q.ca))
+        quad_exp_ali_exact(A.za, B.za, km, q.ce, q.ca);
 
-    const double inv_c = 1.0 / A.cp;
+    const double inv_c = fast_rcp(A.cp);
     const double inv_rho = inv_c * (1.0 / GTP_EARTH_RADIUS);
     const double inv_R = 1.0 / GTP_EARTH_RADIUS;
     const double Px = B.x - A.x, Py = B.y - A.y, Pz = B.z - A.z;
@@ -149,7 +263,7 @@ GTP_HD Quad quad_setup(const Tie& A, const TieB& B, double Cx, double Cy, double
         // lat = sign(z) * acos(rho / R);  rho / R = c * (1 + v),  v = (rho - rho_A) / rho_A.
         // acos(c + c v) = |lat_A| - sum_k asinser_k(s -> c, c -> |s|) (c v)^k
         const double c = A.cp, c2 = c * c, sa = absd(A.sp);
-        const double inv_s = 1.0 / sa, u = inv_s * inv_s;
+        const double inv_s = fast_rcp(sa), u = inv_s * inv_s;
         const double sgn = (A.sp < 0.0) ? GTP_RAD2DEG : -GTP_RAD2DEG;   // -sign(z) * rad2deg
         double m = inv_s * c * sgn;
         q.b1 = m;

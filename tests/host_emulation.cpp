@@ -22,7 +22,7 @@ static void run(const double* lon, const double* lat, const double* satz, long n
             for (int qr = 0; qr < L - 1; ++qr) {
                 auto at = [&](int r, int c) { long o = (s * L + r) * W + c; return tie_setup(lon[o], lat[o], satz[o]); };
                 const Tie A = at(qr, ca), Bf = at(qr, cb), D = at(qr + 1, ca), C = at(qr + 1, cb);
-                TieB B; B.x = Bf.x; B.y = Bf.y; B.z = Bf.z; B.phi = Bf.phi; B.theta = Bf.theta;
+                TieB B; B.x = Bf.x; B.y = Bf.y; B.z = Bf.z; B.za = Bf.za; B.sphi = Bf.sphi; B.cphi = Bf.cphi;
                 const Quad q = quad_setup(A, B, C.x, C.y, C.z, D.x, D.y, D.z, 1);
                 mode_counts[q.mode]++;
                 const int j0 = (qr == 0) ? 0 : qr * P + H;
