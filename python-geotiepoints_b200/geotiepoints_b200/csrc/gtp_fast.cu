@@ -46,10 +46,16 @@ __device__ __forceinline__ void store_px<2>(double* p, const double (&v)[2])
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v[0]), "d"(v[1]) : "memory");
 }
 
-__device__ __forceinline__ double ldg(const double* p)
+// 8-byte asynchronous global -> shared copy (LDGSTS): the next tie row is fetched while the
+// current quad row is computed without holding the values in registers (with ~165 live
+// registers ptxas otherwise parks a register prefetch in local memory and stalls on it).
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src)
 {
-    return __ldg(p);
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // the fine rows [0, nrows) of one quad, first row at a_track = s_t0, branch-free per pixel
 template <int P, int MODE, bool WRAP>
@@ -103,14 +109,23 @@ cviirs_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restr
 
     Tie topA;            // upper-left corner of the quad being formed
     TieB topB;           // upper-right corner
-    double nlon = ldg(plon), nlat = ldg(plat), nsatz = ldg(psatz);
+    __shared__ double stage[2][3][kThreads];     // double-buffered next-row inputs, one slot per thread
+    cp_async8(&stage[0][0][threadIdx.x], plon);
+    cp_async8(&stage[0][1][threadIdx.x], plat);
+    cp_async8(&stage[0][2][threadIdx.x], psatz);
+    cp_async_commit();
 
 #pragma unroll 1
     for (int r = 0; r < kL; ++r) {
-        const double clon = nlon, clat = nlat, csatz = nsatz;
-        if (r + 1 < kL) {            // prefetch the next tie row while this one is worked on
+        cp_async_wait_all();
+        const double clon = stage[r & 1][0][threadIdx.x], clat = stage[r & 1][1][threadIdx.x],
+                     csatz = stage[r & 1][2][threadIdx.x];
+        if (r + 1 < kL) {            // fetch the next tie row while this one is worked on
             plon += kW; plat += kW; psatz += kW;
-            nlon = ldg(plon); nlat = ldg(plat); nsatz = ldg(psatz);
+            cp_async8(&stage[(r + 1) & 1][0][threadIdx.x], plon);
+            cp_async8(&stage[(r + 1) & 1][1][threadIdx.x], plat);
+            cp_async8(&stage[(r + 1) & 1][2][threadIdx.x], psatz);
+            cp_async_commit();
         }
         const Tie own = tie_setup(clon, clat, csatz);
         Tie curA = own;
