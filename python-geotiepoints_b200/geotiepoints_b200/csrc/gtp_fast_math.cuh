@@ -26,19 +26,64 @@
 #include <math.h>
 #include "gtp_common.cuh"
 
+// Under nvcc these functions are device-only so that they may read __constant__ data: a
+// double literal costs two UMOV issue slots per use (measured: 126 UMOV per tie row), a
+// constant-bank operand costs none.  g++ (tests/host_emulation.cpp) sees plain inline
+// functions and static const doubles.
+#ifdef __CUDACC__
+#define GTP_FD __device__ __forceinline__
+#define GTP_DCONST(name, value) static __constant__ double name = value
+#else
+#define GTP_FD inline
+#define GTP_DCONST(name, value) static const double name = value
+#endif
+
 namespace gtpfast {
+
+GTP_DCONST(kDeg2Rad, GTP_DEG2RAD);
+GTP_DCONST(kRad2Deg, GTP_RAD2DEG);
+GTP_DCONST(kEarthR, GTP_EARTH_RADIUS);
+GTP_DCONST(kInvEarthR, 1.0 / GTP_EARTH_RADIUS);
+GTP_DCONST(kSinPhiScale, GTP_RK / (GTP_RK + GTP_H));           // R / (R + H)
+GTP_DCONST(kK, (GTP_RK + GTP_H) / GTP_RK);                     // (R + H) / R
+GTP_DCONST(kInv2H, 1.0 / (2.0 * GTP_H));
+GTP_DCONST(kTwoOverPi, 0.63661977236758138243);
+GTP_DCONST(kPio2Hi, 1.57079632679489655800e+00);
+GTP_DCONST(kPio2Lo, 6.12323399573676603587e-17);
+GTP_DCONST(kS1, -1.66666666666666324348e-01);
+GTP_DCONST(kS2, 8.33333333332248946124e-03);
+GTP_DCONST(kS3, -1.98412698298579493134e-04);
+GTP_DCONST(kS4, 2.75573137070700676789e-06);
+GTP_DCONST(kS5, -2.50507602534068634195e-08);
+GTP_DCONST(kS6, 1.58969099521155010221e-10);
+GTP_DCONST(kC1, 4.16666666666666019037e-02);
+GTP_DCONST(kC2, -1.38888888888741095749e-03);
+GTP_DCONST(kC3, 2.48015872894767294178e-05);
+GTP_DCONST(kC4, -2.75573143513906633035e-07);
+GTP_DCONST(kC5, 2.08757232129817482790e-09);
+GTP_DCONST(kC6, -1.13596475577881948265e-11);
+GTP_DCONST(kThird, 1.0 / 3.0);
+GTP_DCONST(kSixth, 1.0 / 6.0);
+GTP_DCONST(k1_24, 1.0 / 24.0);
+GTP_DCONST(k1_40, 1.0 / 40.0);
+GTP_DCONST(k1_120, 1.0 / 120.0);
+GTP_DCONST(k1_720, 1.0 / 720.0);
+GTP_DCONST(k1_5040, 1.0 / 5040.0);
+GTP_DCONST(k3_40, 0.075);
+GTP_DCONST(kABound, 2.3);
+GTP_DCONST(kTBound, 1.4);
+GTP_DCONST(kATBound, 3.3);
+GTP_DCONST(kMaxRelHoriz, 0.01);
+GTP_DCONST(kMaxRelZ, 2.0e-3);
+GTP_DCONST(kLatSwitch, 0.8);
 
 enum QuadMode { kSlow = 0, kLow = 1, kHigh = 2, kBoth = 3 };
 
 // The reference's latitude switch: z < thr*R and z > -thr*R with thr = 0.8
 #define GTP_LAT_SWITCH 0.8
-// acceptance limits of the series (see header)
-#define GTP_MAX_REL_HORIZ 0.01   // bound on |d_horizontal| / rho_A
-#define GTP_MAX_REL_Z 2.0e-3     // bound on |d_z| / R
-// bounds on |a_scan|, |a_track|, |a_scan * a_track| used to bound |d|
-#define GTP_A_BOUND 2.3
-#define GTP_T_BOUND 1.4
-#define GTP_AT_BOUND 3.3
+// Acceptance limits of the series (see header), in the constant table above:
+//   kMaxRelHoriz  bound on |d_horizontal| / rho_A;  kMaxRelZ  bound on |d_z| / R;
+//   kABound, kTBound, kATBound  bounds on |a_scan|, |a_track|, |a_scan a_track| used to bound |d|
 
 struct Tie {               // one tie point, everything a quad may need from it
     double x, y, z;        // Cartesian, metres (lonlat2xyz)
@@ -76,7 +121,7 @@ struct Quad {
 // (error < 2^-57), and MUFU-seeded Newton iterations for 1/x and sqrt(x).
 
 // 1/x to ~1 ulp (no special cases: 0 and inf give NaN, which routes the quad to the slow path)
-GTP_HD double fast_rcp(double x)
+GTP_FD double fast_rcp(double x)
 {
 #ifdef __CUDA_ARCH__
     double r;
@@ -90,7 +135,7 @@ GTP_HD double fast_rcp(double x)
 }
 
 // sqrt(x) to ~1 ulp for x > 0 (0 gives NaN -> slow path)
-GTP_HD double fast_sqrt(double x)
+GTP_FD double fast_sqrt(double x)
 {
 #ifdef __CUDA_ARCH__
     double y;
@@ -106,25 +151,25 @@ GTP_HD double fast_sqrt(double x)
 }
 
 // sin and cos of |x| <= 8 (longitudes, latitudes, zenith angles in radians)
-GTP_HD void fast_sincos(double x, double& sn, double& cs)
+GTP_FD void fast_sincos(double x, double& sn, double& cs)
 {
     if (!(fabs(x) <= 8.0)) { sincos(x, &sn, &cs); return; }    // out-of-range or NaN input: library path
-    const double kf = rint(x * 0.63661977236758138243);          // 2 / pi
-    double r = fma(-kf, 1.57079632679489655800e+00, x);           // pi/2 high part
-    r = fma(-kf, 6.12323399573676603587e-17, r);                  // pi/2 low part
+    const double kf = rint(x * kTwoOverPi);
+    double r = fma(-kf, kPio2Hi, x);
+    r = fma(-kf, kPio2Lo, r);
     const int quad = (int)kf;
     const double z = r * r;
-    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    ps = fma(z, ps, 2.75573137070700676789e-06);
-    ps = fma(z, ps, -1.98412698298579493134e-04);
-    ps = fma(z, ps, 8.33333333332248946124e-03);
-    ps = fma(z, ps, -1.66666666666666324348e-01);
+    double ps = fma(z, kS6, kS5);
+    ps = fma(z, ps, kS4);
+    ps = fma(z, ps, kS3);
+    ps = fma(z, ps, kS2);
+    ps = fma(z, ps, kS1);
     const double sr = fma(r * z, ps, r);
-    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    pc = fma(z, pc, -2.75573143513906633035e-07);
-    pc = fma(z, pc, 2.48015872894767294178e-05);
-    pc = fma(z, pc, -1.38888888888741095749e-03);
-    pc = fma(z, pc, 4.16666666666666019037e-02);
+    double pc = fma(z, kC6, kC5);
+    pc = fma(z, pc, kC4);
+    pc = fma(z, pc, kC3);
+    pc = fma(z, pc, kC2);
+    pc = fma(z, pc, kC1);
     const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
     const double s0 = (quad & 1) ? cr : sr;
     const double c0 = (quad & 1) ? sr : cr;
@@ -132,17 +177,17 @@ GTP_HD void fast_sincos(double x, double& sn, double& cs)
     cs = ((quad + 1) & 2) ? -c0 : c0;
 }
 
-GTP_HD Tie tie_setup(double lon, double lat, double satz)
+GTP_FD Tie tie_setup(double lon, double lat, double satz)
 {
     Tie t;
     t.lon = lon; t.lat = lat;
-    fast_sincos(lon * GTP_DEG2RAD, t.sl, t.cl);
-    fast_sincos(lat * GTP_DEG2RAD, t.sp, t.cp);
-    const double rc = GTP_EARTH_RADIUS * t.cp;
-    t.x = rc * t.cl; t.y = rc * t.sl; t.z = GTP_EARTH_RADIUS * t.sp;
-    t.za = satz * GTP_DEG2RAD;
+    fast_sincos(lon * kDeg2Rad, t.sl, t.cl);
+    fast_sincos(lat * kDeg2Rad, t.sp, t.cp);
+    const double rc = kEarthR * t.cp;
+    t.x = rc * t.cl; t.y = rc * t.sl; t.z = kEarthR * t.sp;
+    t.za = satz * kDeg2Rad;
     fast_sincos(t.za, t.sz, t.cz);
-    t.sphi = t.sz * (GTP_RK / (GTP_RK + GTP_H));                   // :74
+    t.sphi = t.sz * kSinPhiScale;                                  // :74
     t.cphi = fast_sqrt(fma(-t.sphi, t.sphi, 1.0));
     return t;
 }
@@ -156,45 +201,45 @@ GTP_HD Tie tie_setup(double lon, double lat, double satz)
 //   theta_a - theta_b = dphi - dz.
 // Returns false (ce, ca untouched) when the two zenith angles are too far apart for the
 // small-argument series; the caller then uses quad_exp_ali_exact.
-GTP_HD bool quad_exp_ali(double za, double sza, double cza, double sphi_a, double cphi_a,
+GTP_FD bool quad_exp_ali(double za, double sza, double cza, double sphi_a, double cphi_a,
                          double zb, double sphi_b, double cphi_b, int km, double& ce, double& ca)
 {
-    const double K = (GTP_RK + GTP_H) / GTP_RK;
+    const double K = kK;
     // dphi = asin(sin(phi_b - phi_a))
     const double sd = fma(sphi_b, cphi_a, -(sphi_a * cphi_b));
     const double dz = zb - za;
     if (!(fabs(sd) <= 0.01 && fabs(dz) <= 0.02)) return false;      // also catches NaN
     const double sd2 = sd * sd;
-    const double dphi = fma(sd * sd2, fma(sd2, 0.075, 1.0 / 6.0), sd);
+    const double dphi = fma(sd * sd2, fma(sd2, k3_40, kSixth), sd);
     // mean phi = phi_a + dphi / 2
     const double hp = 0.5 * dphi, hp2 = hp * hp;
-    const double sh = fma(hp * hp2, fma(hp2, 1.0 / 120.0, -1.0 / 6.0), hp);
-    const double ch = fma(hp2, fma(hp2, 1.0 / 24.0, -0.5), 1.0);
+    const double sh = fma(hp * hp2, fma(hp2, k1_120, -kSixth), hp);
+    const double ch = fma(hp2, fma(hp2, k1_24, -0.5), 1.0);
     const double sphi = fma(sphi_a, ch, cphi_a * sh);
     const double cphi = fma(cphi_a, ch, -(sphi_a * sh));
     const double szeta = K * sphi;                                   // sin(zeta) of :82
     const double czeta = fast_sqrt(fma(-szeta, szeta, 1.0));
     // zm = za + dz / 2
     const double hz = 0.5 * dz, hz2 = hz * hz;
-    const double shz = fma(hz * hz2, fma(hz2, fma(hz2, -1.0 / 5040.0, 1.0 / 120.0), -1.0 / 6.0), hz);
-    const double chz = fma(hz2, fma(hz2, fma(hz2, -1.0 / 720.0, 1.0 / 24.0), -0.5), 1.0);
+    const double shz = fma(hz * hz2, fma(hz2, fma(hz2, -k1_5040, k1_120), -kSixth), hz);
+    const double chz = fma(hz2, fma(hz2, fma(hz2, -k1_720, k1_24), -0.5), 1.0);
     const double szm = fma(sza, chz, cza * shz);
     const double czm = fma(cza, chz, -(sza * shz));
     // delta = zeta - zm
     const double sdel = fma(szeta, czm, -(czeta * szm));
-    const double delta = fma(sdel * (sdel * sdel), 1.0 / 6.0, sdel);
+    const double delta = fma(sdel * (sdel * sdel), kSixth, sdel);
     double den = dphi - dz;                                          // theta_a - theta_b
     if (dz == 0.0) den = 2.0 * (za - asin(sphi_a));                  // :61-62, symmetric tie points
     const double inv_den = 4.0 * fast_rcp(den);
     ce = -delta * inv_den;
-    const double d = (K * cphi - czeta) * ((double)km / (2.0 * GTP_H));
+    const double d = (K * cphi - czeta) * ((double)km * kInv2H);
     const double e = czeta - fast_sqrt(fma(czeta, czeta, -(d * d)));
     ca = (e * szeta) * inv_den;
     return true;
 }
 
 // the same coefficients, written exactly like the reference (:52-70), library functions
-GTP_HD void quad_exp_ali_exact(double za, double zb, int km, double& ce, double& ca)
+GTP_FD void quad_exp_ali_exact(double za, double zb, int km, double& ce, double& ca)
 {
     const double phi_a = asin((GTP_RK * sin(za)) / (GTP_RK + GTP_H));
     const double phi_b = asin((GTP_RK * sin(zb)) / (GTP_RK + GTP_H));
@@ -209,10 +254,10 @@ GTP_HD void quad_exp_ali_exact(double za, double zb, int km, double& ce, double&
     ca = ((4.0 * e) * sin(zeta)) / den;
 }
 
-GTP_HD double absd(double x) { return fabs(x); }
+GTP_FD double absd(double x) { return fabs(x); }
 
 // A, B = upper left / right, D, C = lower left / right corner of the quad
-GTP_HD Quad quad_setup(const Tie& A, const TieB& B, double Cx, double Cy, double Cz,
+GTP_FD Quad quad_setup(const Tie& A, const TieB& B, double Cx, double Cy, double Cz,
                        double Dx, double Dy, double Dz, int km)
 {
     Quad q;
@@ -223,8 +268,8 @@ GTP_HD Quad quad_setup(const Tie& A, const TieB& B, double Cx, double Cy, double
         quad_exp_ali_exact(A.za, B.za, km, q.ce, q.ca);
 
     const double inv_c = fast_rcp(A.cp);
-    const double inv_rho = inv_c * (1.0 / GTP_EARTH_RADIUS);
-    const double inv_R = 1.0 / GTP_EARTH_RADIUS;
+    const double inv_rho = inv_c * kInvEarthR;
+    const double inv_R = kInvEarthR;
     const double Px = B.x - A.x, Py = B.y - A.y, Pz = B.z - A.z;
     const double Qx = Dx - A.x, Qy = Dy - A.y, Qz = Dz - A.z;
     const double Sx = (Cx - Dx) - Px, Sy = (Cy - Dy) - Py, Sz = (Cz - Dz) - Pz;
@@ -234,43 +279,43 @@ GTP_HD Quad quad_setup(const Tie& A, const TieB& B, double Cx, double Cy, double
     q.lon0 = A.lon; q.lat0 = A.lat; q.s0 = A.sp;
 
     // size of the displacement over the whole quad (incl. the extrapolated edge pixels)
-    const double horiz = GTP_A_BOUND * (absd(q.Pe) + absd(q.Ph)) + GTP_T_BOUND * (absd(q.Qe) + absd(q.Qh))
-                         + GTP_AT_BOUND * (absd(q.Se) + absd(q.Sh));
-    const double wmax = GTP_A_BOUND * absd(q.Pw) + GTP_T_BOUND * absd(q.Qw) + GTP_AT_BOUND * absd(q.Sw);
+    const double horiz = kABound * (absd(q.Pe) + absd(q.Ph)) + kTBound * (absd(q.Qe) + absd(q.Qh))
+                         + kATBound * (absd(q.Se) + absd(q.Sh));
+    const double wmax = kABound * absd(q.Pw) + kTBound * absd(q.Qw) + kATBound * absd(q.Sw);
     // written so that any NaN (lon/lat/satz) fails the test and takes the slow path
-    const bool ok = (horiz <= GTP_MAX_REL_HORIZ) && (wmax <= GTP_MAX_REL_Z)
+    const bool ok = (horiz <= kMaxRelHoriz) && (wmax <= kMaxRelZ)
                     && (absd(q.ce) <= 1.0) && (absd(q.ca) <= 0.5) && (A.cp > 1e-6);
     if (!ok) { q.mode = kSlow; return q; }
 
     const double zr_lo = q.s0 - wmax, zr_hi = q.s0 + wmax;
     const double margin = 1e-9;
-    if (zr_hi < GTP_LAT_SWITCH - margin && zr_lo > -GTP_LAT_SWITCH + margin) q.mode = kLow;
-    else if (zr_lo > GTP_LAT_SWITCH + margin || zr_hi < -GTP_LAT_SWITCH - margin) q.mode = kHigh;
+    if (zr_hi < kLatSwitch - margin && zr_lo > -kLatSwitch + margin) q.mode = kLow;
+    else if (zr_lo > kLatSwitch + margin || zr_hi < -kLatSwitch - margin) q.mode = kHigh;
     else q.mode = kBoth;
-    q.wrap = (absd(q.lon0) + 1.05 * horiz * GTP_RAD2DEG) >= 180.0;
+    q.wrap = (absd(q.lon0) + 1.05 * horiz * kRad2Deg) >= 180.0;
 
     if (q.mode & kLow) {
         // d/dw^k of asin(s + w) at w = 0, over k!  (s = sin lat_A, c = cos lat_A)
         const double s = A.sp, s2 = s * s, u = inv_c * inv_c;
-        double m = inv_c * GTP_RAD2DEG;
+        double m = inv_c * kRad2Deg;
         q.a1 = m;
         m *= u; q.a2 = 0.5 * s * m;
-        m *= u; q.a3 = fma(2.0, s2, 1.0) * (1.0 / 6.0) * m;
+        m *= u; q.a3 = fma(2.0, s2, 1.0) * kSixth * m;
         m *= u; q.a4 = s * fma(2.0, s2, 3.0) * 0.125 * m;
-        m *= u; q.a5 = fma(s2, fma(8.0, s2, 24.0), 3.0) * (1.0 / 40.0) * m;
+        m *= u; q.a5 = fma(s2, fma(8.0, s2, 24.0), 3.0) * k1_40 * m;
     }
     if (q.mode & kHigh) {
         // lat = sign(z) * acos(rho / R);  rho / R = c * (1 + v),  v = (rho - rho_A) / rho_A.
         // acos(c + c v) = |lat_A| - sum_k asinser_k(s -> c, c -> |s|) (c v)^k
         const double c = A.cp, c2 = c * c, sa = absd(A.sp);
         const double inv_s = fast_rcp(sa), u = inv_s * inv_s;
-        const double sgn = (A.sp < 0.0) ? GTP_RAD2DEG : -GTP_RAD2DEG;   // -sign(z) * rad2deg
+        const double sgn = (A.sp < 0.0) ? kRad2Deg : -kRad2Deg;   // -sign(z) * rad2deg
         double m = inv_s * c * sgn;
         q.b1 = m;
         m *= u * c; q.b2 = 0.5 * c * m;
-        m *= u * c; q.b3 = fma(2.0, c2, 1.0) * (1.0 / 6.0) * m;
+        m *= u * c; q.b3 = fma(2.0, c2, 1.0) * kSixth * m;
         m *= u * c; q.b4 = c * fma(2.0, c2, 3.0) * 0.125 * m;
-        m *= u * c; q.b5 = fma(c2, fma(8.0, c2, 24.0), 3.0) * (1.0 / 40.0) * m;
+        m *= u * c; q.b5 = fma(c2, fma(8.0, c2, 24.0), 3.0) * k1_40 * m;
     }
     return q;
 }
@@ -280,7 +325,7 @@ struct RowCoef {           // per (quad, fine row): the a_track-dependent half o
     double a_base;         // s_t (1 - s_t) c_ali
 };
 
-GTP_HD RowCoef row_setup(const Quad& q, double s_t)
+GTP_FD RowCoef row_setup(const Quad& q, double s_t)
 {
     RowCoef r;
     r.Ue = fma(s_t, q.Se, q.Pe); r.Uh = fma(s_t, q.Sh, q.Ph); r.Uw = fma(s_t, q.Sw, q.Pw);
@@ -293,7 +338,7 @@ GTP_HD RowCoef row_setup(const Quad& q, double s_t)
 // a_scan (:344), r.a_base the per-(quad, row) part.  MODE and WRAP are compile-time so that
 // the row loops of the kernel are branch-free; they are quad properties (Quad::mode, ::wrap).
 template <int MODE, bool WRAP>
-GTP_HD void pixel_eval(const Quad& q, const RowCoef& r, double a_col, double& lon, double& lat)
+GTP_FD void pixel_eval(const Quad& q, const RowCoef& r, double a_col, double& lon, double& lat)
 {
     const double a = a_col + r.a_base;
     const double e = fma(a, r.Ue, r.Ve);
@@ -306,8 +351,8 @@ GTP_HD void pixel_eval(const Quad& q, const RowCoef& r, double a_col, double& lo
     const double t = e * rcp;
     const double t2 = t * t;
     // atan(t) = t - t^3/3 + t^5/5   (|t| <= 0.011 -> next term 3e-15 rad)
-    const double at = fma(t * t2, fma(t2, 0.2, -1.0 / 3.0), t);
-    double lo = fma(at, GTP_RAD2DEG, q.lon0);
+    const double at = fma(t * t2, fma(t2, 0.2, -kThird), t);
+    double lo = fma(at, kRad2Deg, q.lon0);
     if (WRAP) {
         if (lo > 180.0) lo -= 360.0;
         else if (lo < -180.0) lo += 360.0;
@@ -326,14 +371,14 @@ GTP_HD void pixel_eval(const Quad& q, const RowCoef& r, double a_col, double& lo
     else if (MODE == kHigh) lat = la_high;
     else {
         const double zr = q.s0 + w;
-        lat = (zr < GTP_LAT_SWITCH && zr > -GTP_LAT_SWITCH) ? la_low : la_high;
+        lat = (zr < kLatSwitch && zr > -kLatSwitch) ? la_low : la_high;
     }
 }
 
 // ---- rounding-faithful per-pixel evaluation (fallback for quads the series cannot take) ----
-GTP_HD int sign_of(double x) { return x > 0.0 ? 1 : (x < 0.0 ? -1 : 0); }
+GTP_FD int sign_of(double x) { return x > 0.0 ? 1 : (x < 0.0 ? -1 : 0); }
 
-GTP_HD void xyz_to_lonlat(double x, double y, double z, double& lon, double& lat)
+GTP_FD void xyz_to_lonlat(double x, double y, double z, double& lon, double& lat)
 {
     const double rho = sqrt(x * x + y * y);
     lon = (acos(x / rho) * GTP_RAD2DEG) * (double)sign_of(y);
@@ -343,14 +388,14 @@ GTP_HD void xyz_to_lonlat(double x, double y, double z, double& lon, double& lat
         lat = (double)sign_of(z) * (90.0 - asin(rho / GTP_EARTH_RADIUS) * GTP_RAD2DEG);
 }
 
-GTP_HD double blend(double a_scan, double a_track, double A, double B, double C, double D)
+GTP_FD double blend(double a_scan, double a_track, double A, double B, double C, double D)
 {
     const double scan1 = (1.0 - a_scan) * A + a_scan * B;
     const double scan2 = (1.0 - a_scan) * D + a_scan * C;
     return (1.0 - a_track) * scan1 + a_track * scan2;
 }
 
-GTP_HD void pixel_eval_slow(const Tie& A, const TieB& B, double Cx, double Cy, double Cz,
+GTP_FD void pixel_eval_slow(const Tie& A, const TieB& B, double Cx, double Cy, double Cz,
                             double Dx, double Dy, double Dz, double ce, double ca,
                             double s_s, double s_t, double& lon, double& lat)
 {
@@ -364,7 +409,7 @@ GTP_HD void pixel_eval_slow(const Tie& A, const TieB& B, double Cx, double Cy, d
 // y[j] of _get_coords_1km (a4): 0.5 + j - h on the first h rows of the scan, continuing
 // past f on the last h rows, ((j + h) mod f) + 0.5 in between (f = P, h = P / 2, n = 10 P)
 template <int P>
-GTP_HD double fine_row_y(int j)
+GTP_FD double fine_row_y(int j)
 {
     constexpr int kHalf = P / 2, kN = 10 * P;
     return (j < kHalf) ? (0.5 + j - kHalf)
