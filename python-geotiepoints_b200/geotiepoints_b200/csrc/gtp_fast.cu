@@ -25,10 +25,13 @@ constexpr int kW = 1354;            // tie columns at 1 km
 constexpr int kL = 10;              // tie rows per scan
 constexpr int kQuadColsPerWarp = 31;
 constexpr int kWarpsPerScan = (kW + kQuadColsPerWarp - 1) / kQuadColsPerWarp;   // 44
-constexpr int kThreads = 128;
+#ifndef GTP_FAST_THREADS
+#define GTP_FAST_THREADS 128
+#endif
+constexpr int kThreads = GTP_FAST_THREADS;
 constexpr unsigned kFull = 0xffffffffu;
 #ifndef GTP_FAST_MIN_BLOCKS
-#define GTP_FAST_MIN_BLOCKS 3     // resident CTAs per SM the register allocation is tuned for
+#define GTP_FAST_MIN_BLOCKS 4     // resident CTAs per SM the register allocation is tuned for
 #endif
 
 template <int P>
@@ -107,8 +110,11 @@ cviirs_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restr
     double* olon = out_lon + scan * (long long)kN * kWf + (long long)quad_col * P + xoff;
     double* olat = out_lat + scan * (long long)kN * kWf + (long long)quad_col * P + xoff;
 
-    Tie topA;            // upper-left corner of the quad being formed
-    TieB topB;           // upper-right corner
+    // carried from the tie row above: corner A (frame + anchor), corner B, and the quad row's
+    // expansion / alignment coefficients (they depend on the upper corners only, :307-308)
+    TieGeo topA;
+    Vec3 topB;
+    double top_ce = 0.0, top_ca = 0.0;
     __shared__ double stage[2][3][kThreads];     // double-buffered next-row inputs, one slot per thread
     cp_async8(&stage[0][0][threadIdx.x], plon);
     cp_async8(&stage[0][1][threadIdx.x], plat);
@@ -127,30 +133,20 @@ cviirs_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restr
             cp_async8(&stage[(r + 1) & 1][2][threadIdx.x], psatz);
             cp_async_commit();
         }
-        const Tie own = tie_setup(clon, clat, csatz);
-        Tie curA = own;
-        TieB curB;
-        curB.x = __shfl_down_sync(kFull, own.x, 1);
-        curB.y = __shfl_down_sync(kFull, own.y, 1);
-        curB.z = __shfl_down_sync(kFull, own.z, 1);
-        curB.za = __shfl_down_sync(kFull, own.za, 1);
-        curB.sphi = __shfl_down_sync(kFull, own.sphi, 1);
-        curB.cphi = __shfl_down_sync(kFull, own.cphi, 1);
+        // this lane's tie point of row r; corner B of the lane's quad column comes from lane + 1
+        const TieGeo own = tie_geo(clon, clat);
+        const Vec3 own_xyz = tie_xyz(own);
+        TieGeo curA = own;
+        Vec3 curA_xyz = own_xyz, curB;
+        curB.x = __shfl_down_sync(kFull, own_xyz.x, 1);
+        curB.y = __shfl_down_sync(kFull, own_xyz.y, 1);
+        curB.z = __shfl_down_sync(kFull, own_xyz.z, 1);
         if (last_warp) {             // warp-uniform: the lane of tie column 1353 takes A from its left neighbour
-            Tie up;
-            up.x = __shfl_up_sync(kFull, own.x, 1); up.y = __shfl_up_sync(kFull, own.y, 1);
-            up.z = __shfl_up_sync(kFull, own.z, 1);
+            TieGeo up;
             up.sl = __shfl_up_sync(kFull, own.sl, 1); up.cl = __shfl_up_sync(kFull, own.cl, 1);
             up.sp = __shfl_up_sync(kFull, own.sp, 1); up.cp = __shfl_up_sync(kFull, own.cp, 1);
             up.lon = __shfl_up_sync(kFull, own.lon, 1); up.lat = __shfl_up_sync(kFull, own.lat, 1);
-            up.za = __shfl_up_sync(kFull, own.za, 1);
-            up.sz = __shfl_up_sync(kFull, own.sz, 1); up.cz = __shfl_up_sync(kFull, own.cz, 1);
-            up.sphi = __shfl_up_sync(kFull, own.sphi, 1); up.cphi = __shfl_up_sync(kFull, own.cphi, 1);
-            if (extra) {
-                curA = up;
-                curB.x = own.x; curB.y = own.y; curB.z = own.z;
-                curB.za = own.za; curB.sphi = own.sphi; curB.cphi = own.cphi;
-            }
+            if (extra) { curA = up; curA_xyz = tie_xyz(up); curB = own_xyz; }
         }
 
         if (r > 0 && active) {
@@ -159,7 +155,8 @@ cviirs_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restr
             const int qr = r - 1;
             const int nrows = P + ((qr == 0 || qr == kL - 2) ? kHalf : 0);
             const double s_t0 = ((qr == 0) ? (0.5 - kHalf) : 0.5) / P;
-            const Quad q = quad_setup(topA, topB, curB.x, curB.y, curB.z, curA.x, curA.y, curA.z, 1);
+            const Vec3 topA_xyz = tie_xyz(topA);
+            const Quad q = quad_setup(topA, topA_xyz, topB, curB, curA_xyz, top_ce, top_ca);
             if (q.mode != kSlow) {
                 double a_col[P];     // s_s + s_s (1 - s_s) c_exp  (:341, :344)
 #pragma unroll
@@ -181,7 +178,7 @@ cviirs_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restr
                     double vlon[P], vlat[P];
 #pragma unroll 1
                     for (int k = 0; k < P; ++k)
-                        pixel_eval_slow(topA, topB, curB.x, curB.y, curB.z, curA.x, curA.y, curA.z, q.ce, q.ca,
+                        pixel_eval_slow(topA_xyz, topB, curB, curA_xyz, q.ce, q.ca,
                                         (double)(xoff + k) / (double)P, s_t, vlon[k], vlat[k]);
                     store_px<P>(olon + (long long)m * kWf, vlon);
                     store_px<P>(olat + (long long)m * kWf, vlat);
@@ -192,6 +189,23 @@ cviirs_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restr
         }
         topA = curA;
         topB = curB;
+
+        if (r + 1 < kL) {
+            // expansion / alignment of the quad row BELOW this tie row, from this row's zenith angles
+            const TieZen zen = tie_zen(csatz);
+            double zb = __shfl_down_sync(kFull, zen.za, 1);
+            double sphi_b = __shfl_down_sync(kFull, zen.sphi, 1);
+            double cphi_b = __shfl_down_sync(kFull, zen.cphi, 1);
+            TieZen za = zen;
+            if (last_warp) {
+                TieZen up;
+                up.za = __shfl_up_sync(kFull, zen.za, 1);
+                up.sz = __shfl_up_sync(kFull, zen.sz, 1); up.cz = __shfl_up_sync(kFull, zen.cz, 1);
+                up.sphi = __shfl_up_sync(kFull, zen.sphi, 1); up.cphi = __shfl_up_sync(kFull, zen.cphi, 1);
+                if (extra) { za = up; zb = zen.za; sphi_b = zen.sphi; cphi_b = zen.cphi; }
+            }
+            quad_coefficients(za, zb, sphi_b, cphi_b, 1, top_ce, top_ca);
+        }
     }
 }
 

@@ -85,19 +85,18 @@ enum QuadMode { kSlow = 0, kLow = 1, kHigh = 2, kBoth = 3 };
 //   kMaxRelHoriz  bound on |d_horizontal| / rho_A;  kMaxRelZ  bound on |d_z| / R;
 //   kABound, kTBound, kATBound  bounds on |a_scan|, |a_track|, |a_scan a_track| used to bound |d|
 
-struct Tie {               // one tie point, everything a quad may need from it
-    double x, y, z;        // Cartesian, metres (lonlat2xyz)
+struct TieGeo {            // geometry of one tie point (lonlat2xyz and the local frame)
     double sl, cl;         // sin / cos of the longitude
     double sp, cp;         // sin / cos of the latitude
     double lon, lat;       // the inputs, degrees
-    // satellite-zenith chain (:52-57, :73-78), kept as sines/cosines instead of angles:
-    double za;             // zeta = deg2rad(satz)
-    double sz, cz;         // sin / cos zeta
-    double sphi, cphi;     // sin / cos of phi = asin(R sin(zeta) / (R + H))
 };
 
-struct TieB {              // what a quad needs from its corner B (upper right)
-    double x, y, z, za, sphi, cphi;
+struct Vec3 { double x, y, z; };
+
+struct TieZen {            // satellite-zenith chain of one tie point (:52-57, :73-78),
+    double za;             // kept as sines/cosines instead of angles: zeta = deg2rad(satz)
+    double sz, cz;         // sin / cos zeta
+    double sphi, cphi;     // sin / cos of phi = asin(R sin(zeta) / (R + H))
 };
 
 struct Quad {
@@ -177,14 +176,26 @@ GTP_FD void fast_sincos(double x, double& sn, double& cs)
     cs = ((quad + 1) & 2) ? -c0 : c0;
 }
 
-GTP_FD Tie tie_setup(double lon, double lat, double satz)
+GTP_FD TieGeo tie_geo(double lon, double lat)
 {
-    Tie t;
+    TieGeo t;
     t.lon = lon; t.lat = lat;
     fast_sincos(lon * kDeg2Rad, t.sl, t.cl);
     fast_sincos(lat * kDeg2Rad, t.sp, t.cp);
+    return t;
+}
+
+GTP_FD Vec3 tie_xyz(const TieGeo& t)             // _modis_utils.pyx:38-40
+{
+    Vec3 v;
     const double rc = kEarthR * t.cp;
-    t.x = rc * t.cl; t.y = rc * t.sl; t.z = kEarthR * t.sp;
+    v.x = rc * t.cl; v.y = rc * t.sl; v.z = kEarthR * t.sp;
+    return v;
+}
+
+GTP_FD TieZen tie_zen(double satz)
+{
+    TieZen t;
     t.za = satz * kDeg2Rad;
     fast_sincos(t.za, t.sz, t.cz);
     t.sphi = t.sz * kSinPhiScale;                                  // :74
@@ -254,25 +265,32 @@ GTP_FD void quad_exp_ali_exact(double za, double zb, int km, double& ce, double&
     ca = ((4.0 * e) * sin(zeta)) / den;
 }
 
+GTP_FD void quad_coefficients(const TieZen& a, double zb, double sphi_b, double cphi_b, int km,
+                              double& ce, double& ca)
+{
+    if (!quad_exp_ali(a.za, a.sz, a.cz, a.sphi, a.cphi, zb, sphi_b, cphi_b, km, ce, ca))
+        quad_exp_ali_exact(a.za, zb, km, ce, ca);
+}
+
 GTP_FD double absd(double x) { return fabs(x); }
 
-// A, B = upper left / right, D, C = lower left / right corner of the quad
-GTP_FD Quad quad_setup(const Tie& A, const TieB& B, double Cx, double Cy, double Cz,
-                       double Dx, double Dy, double Dz, int km)
+// A, B = upper left / right, D, C = lower left / right corner of the quad; ce, ca from
+// quad_exp_ali (they only depend on the zenith angles of A and B)
+GTP_FD Quad quad_setup(const TieGeo& A, const Vec3& Axyz, const Vec3& B, const Vec3& C, const Vec3& D,
+                       double ce, double ca)
 {
     Quad q;
     q.a1 = q.a2 = q.a3 = q.a4 = q.a5 = 0.0;
     q.b1 = q.b2 = q.b3 = q.b4 = q.b5 = 0.0;
     q.wrap = false;
-    if (!quad_exp_ali(A.za, A.sz, A.cz, A.sphi, A.cphi, B.za, B.sphi, B.cphi, km, q.ce, q.ca))
-        quad_exp_ali_exact(A.za, B.za, km, q.ce, q.ca);
+    q.ce = ce; q.ca = ca;
 
     const double inv_c = fast_rcp(A.cp);
     const double inv_rho = inv_c * kInvEarthR;
     const double inv_R = kInvEarthR;
-    const double Px = B.x - A.x, Py = B.y - A.y, Pz = B.z - A.z;
-    const double Qx = Dx - A.x, Qy = Dy - A.y, Qz = Dz - A.z;
-    const double Sx = (Cx - Dx) - Px, Sy = (Cy - Dy) - Py, Sz = (Cz - Dz) - Pz;
+    const double Px = B.x - Axyz.x, Py = B.y - Axyz.y, Pz = B.z - Axyz.z;
+    const double Qx = D.x - Axyz.x, Qy = D.y - Axyz.y, Qz = D.z - Axyz.z;
+    const double Sx = (C.x - D.x) - Px, Sy = (C.y - D.y) - Py, Sz = (C.z - D.z) - Pz;
     q.Pe = fma(-A.sl, Px, A.cl * Py) * inv_rho; q.Ph = fma(A.cl, Px, A.sl * Py) * inv_rho; q.Pw = Pz * inv_R;
     q.Qe = fma(-A.sl, Qx, A.cl * Qy) * inv_rho; q.Qh = fma(A.cl, Qx, A.sl * Qy) * inv_rho; q.Qw = Qz * inv_R;
     q.Se = fma(-A.sl, Sx, A.cl * Sy) * inv_rho; q.Sh = fma(A.cl, Sx, A.sl * Sy) * inv_rho; q.Sw = Sz * inv_R;
@@ -395,14 +413,13 @@ GTP_FD double blend(double a_scan, double a_track, double A, double B, double C,
     return (1.0 - a_track) * scan1 + a_track * scan2;
 }
 
-GTP_FD void pixel_eval_slow(const Tie& A, const TieB& B, double Cx, double Cy, double Cz,
-                            double Dx, double Dy, double Dz, double ce, double ca,
+GTP_FD void pixel_eval_slow(const Vec3& A, const Vec3& B, const Vec3& C, const Vec3& D, double ce, double ca,
                             double s_s, double s_t, double& lon, double& lat)
 {
     const double a_scan = (s_s + (s_s * (1.0 - s_s)) * ce) + (s_t * (1.0 - s_t)) * ca;
-    const double x = blend(a_scan, s_t, A.x, B.x, Cx, Dx);
-    const double y = blend(a_scan, s_t, A.y, B.y, Cy, Dy);
-    const double z = blend(a_scan, s_t, A.z, B.z, Cz, Dz);
+    const double x = blend(a_scan, s_t, A.x, B.x, C.x, D.x);
+    const double y = blend(a_scan, s_t, A.y, B.y, C.y, D.y);
+    const double z = blend(a_scan, s_t, A.z, B.z, C.z, D.z);
     xyz_to_lonlat(x, y, z, lon, lat);
 }
 

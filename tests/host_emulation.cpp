@@ -20,10 +20,14 @@ static void run(const double* lon, const double* lat, const double* satz, long n
             const bool extra = (qc == W - 1);
             const int ca = extra ? W - 2 : qc, cb = ca + 1, xoff = extra ? P : 0;
             for (int qr = 0; qr < L - 1; ++qr) {
-                auto at = [&](int r, int c) { long o = (s * L + r) * W + c; return tie_setup(lon[o], lat[o], satz[o]); };
-                const Tie A = at(qr, ca), Bf = at(qr, cb), D = at(qr + 1, ca), C = at(qr + 1, cb);
-                TieB B; B.x = Bf.x; B.y = Bf.y; B.z = Bf.z; B.za = Bf.za; B.sphi = Bf.sphi; B.cphi = Bf.cphi;
-                const Quad q = quad_setup(A, B, C.x, C.y, C.z, D.x, D.y, D.z, 1);
+                auto geo = [&](int r, int c) { long o = (s * L + r) * W + c; return tie_geo(lon[o], lat[o]); };
+                auto zen = [&](int r, int c) { long o = (s * L + r) * W + c; return tie_zen(satz[o]); };
+                const TieGeo A = geo(qr, ca);
+                const Vec3 Ax = tie_xyz(A), B = tie_xyz(geo(qr, cb)), D = tie_xyz(geo(qr + 1, ca)), C = tie_xyz(geo(qr + 1, cb));
+                const TieZen za = zen(qr, ca), zb = zen(qr, cb);
+                double ce, cal;
+                quad_coefficients(za, zb.za, zb.sphi, zb.cphi, 1, ce, cal);
+                const Quad q = quad_setup(A, Ax, B, C, D, ce, cal);
                 mode_counts[q.mode]++;
                 const int j0 = (qr == 0) ? 0 : qr * P + H;
                 const int j1 = (qr == L - 2) ? N : (qr + 1) * P + H;
@@ -34,7 +38,7 @@ static void run(const double* lon, const double* lat, const double* satz, long n
                         const double s_s = (double)(xoff + k) / (double)P;
                         double lo, la;
                         const double a_col = fma(s_s * (1.0 - s_s), q.ce, s_s);
-                        if (q.mode == kSlow) pixel_eval_slow(A, B, C.x, C.y, C.z, D.x, D.y, D.z, q.ce, q.ca, s_s, s_t, lo, la);
+                        if (q.mode == kSlow) pixel_eval_slow(Ax, B, C, D, q.ce, q.ca, s_s, s_t, lo, la);
                         else if (q.wrap) pixel_eval<kBoth, true>(q, rc, a_col, lo, la);
                         else if (q.mode == kLow) pixel_eval<kLow, false>(q, rc, a_col, lo, la);
                         else if (q.mode == kHigh) pixel_eval<kHigh, false>(q, rc, a_col, lo, la);
