@@ -80,6 +80,27 @@ __device__ __forceinline__ void quad_rows(const Quad& q, const double (&a_col)[P
     }
 }
 
+// same loop for low-latitude quads, small correction terms in float32 (pixel_eval_low_mixed)
+template <int P, bool WRAP>
+__device__ __forceinline__ void quad_rows_low_mixed(const Quad& q, const double (&a_col)[P], double s_t0, int nrows,
+                                                    double* olon, double* olat)
+{
+    constexpr long long kPitch = (long long)kW * P;
+    const QuadF qf = quad_float_terms(q);
+    double s_t = s_t0;
+#pragma unroll 1
+    for (int m = 0; m < nrows; ++m) {
+        const RowCoef rc = row_setup(q, s_t);
+        double vlon[P], vlat[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) pixel_eval_low_mixed<WRAP>(q, qf, rc, a_col[k], vlon[k], vlat[k]);
+        store_px<P>(olon, vlon);
+        store_px<P>(olat, vlat);
+        olon += kPitch; olat += kPitch;
+        s_t += 1.0 / P;
+    }
+}
+
 template <int P>
 __global__ void __launch_bounds__(kThreads, GTP_FAST_MIN_BLOCKS)
 cviirs_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restrict__ lat,
@@ -165,7 +186,11 @@ cviirs_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restr
                     a_col[k] = fma(s_s * (1.0 - s_s), q.ce, s_s);
                 }
                 if (!q.wrap) {
+#ifdef GTP_FAST_MIXED
+                    if (q.mode == kLow) quad_rows_low_mixed<P, false>(q, a_col, s_t0, nrows, olon, olat);
+#else
                     if (q.mode == kLow) quad_rows<P, kLow, false>(q, a_col, s_t0, nrows, olon, olat);
+#endif
                     else if (q.mode == kHigh) quad_rows<P, kHigh, false>(q, a_col, s_t0, nrows, olon, olat);
                     else quad_rows<P, kBoth, false>(q, a_col, s_t0, nrows, olon, olat);
                 } else {

@@ -393,6 +393,47 @@ GTP_FD void pixel_eval(const Quad& q, const RowCoef& r, double a_col, double& lo
     }
 }
 
+// Low-latitude pixel with the small correction terms in float32.  Everything that is added to
+// a large term is still float64; only terms that are themselves < 2e-6 rad / 1e-6 deg are
+// evaluated in float (relative error 2e-7 -> below 3e-13 rad / 2e-13 deg):
+//   1/(1+h) = (1 - h) + rb,          rb = h^2 - h^3 + h^4 - h^5          (|h| <= 0.01)
+//   atan(e/(1+h)) = e (1 - h) + [e rb - t^3/3 + t^5/5]                    (|t| <= 0.011)
+//   lat = lat_A + w (a1 + a2 w) + [w^3 (a3 + a4 w + a5 w^2)]
+// 11 FP64 instructions and 5 conversions per pixel instead of 20 FP64 instructions.
+struct QuadF { float a3, a4, a5; };
+
+GTP_FD QuadF quad_float_terms(const Quad& q)
+{
+    QuadF f;
+    f.a3 = (float)q.a3; f.a4 = (float)q.a4; f.a5 = (float)q.a5;
+    return f;
+}
+
+template <bool WRAP>
+GTP_FD void pixel_eval_low_mixed(const Quad& q, const QuadF& qf, const RowCoef& r, double a_col,
+                                 double& lon, double& lat)
+{
+    const double a = a_col + r.a_base;
+    const double e = fma(a, r.Ue, r.Ve);
+    const double h = fma(a, r.Uh, r.Vh);
+    const double w = fma(a, r.Uw, r.Vw);
+    const float ef = (float)e, hf = (float)h, wf = (float)w;
+    const float omhf = 1.0f - hf;
+    const float rb = (hf * hf) * fmaf(hf * hf, omhf, omhf);          // (h^2)(1 - h)(1 + h^2)
+    const float tf = ef * (omhf + rb);
+    const float t2f = tf * tf;
+    const float corr = fmaf(tf * t2f, fmaf(t2f, 0.2f, -0.33333334f), ef * rb);
+    const double omh = 1.0 - h;
+    double lo = fma(e * omh, kRad2Deg, q.lon0 + (double)(corr * 57.29578f));
+    if (WRAP) {
+        if (lo > 180.0) lo -= 360.0;
+        else if (lo < -180.0) lo += 360.0;
+    }
+    lon = lo;
+    const float br = (wf * wf) * wf * fmaf(wf, fmaf(wf, qf.a5, qf.a4), qf.a3);
+    lat = fma(w, fma(w, q.a2, q.a1), q.lat0 + (double)br);
+}
+
 // ---- rounding-faithful per-pixel evaluation (fallback for quads the series cannot take) ----
 GTP_FD int sign_of(double x) { return x > 0.0 ? 1 : (x < 0.0 ? -1 : 0); }
 

@@ -40,7 +40,11 @@ static void run(const double* lon, const double* lat, const double* satz, long n
                         const double a_col = fma(s_s * (1.0 - s_s), q.ce, s_s);
                         if (q.mode == kSlow) pixel_eval_slow(Ax, B, C, D, q.ce, q.ca, s_s, s_t, lo, la);
                         else if (q.wrap) pixel_eval<kBoth, true>(q, rc, a_col, lo, la);
+#ifdef GTP_FAST_MIXED
+                        else if (q.mode == kLow) pixel_eval_low_mixed<false>(q, quad_float_terms(q), rc, a_col, lo, la);
+#else
                         else if (q.mode == kLow) pixel_eval<kLow, false>(q, rc, a_col, lo, la);
+#endif
                         else if (q.mode == kHigh) pixel_eval<kHigh, false>(q, rc, a_col, lo, la);
                         else pixel_eval<kBoth, false>(q, rc, a_col, lo, la);
                         const long o = (s * N + j) * (long)Wf + (long)ca * P + xoff + k;

@@ -10,8 +10,8 @@
 template <int OP>
 __global__ void pipe_kernel(double* out, double seed)
 {
-    double a[ILP]; float f[ILP];
-    for (int k = 0; k < ILP; ++k) { a[k] = seed + threadIdx.x * 1e-9 + k; f[k] = (float)a[k]; }
+    double a[ILP], g[ILP]; float f[ILP];
+    for (int k = 0; k < ILP; ++k) { a[k] = seed + threadIdx.x * 1e-9 + k; f[k] = (float)a[k]; g[k] = a[k] * 0.5; }
     double b = 1.0000001, c = 1e-9; float fb = 1.0000001f, fc = 1e-9f;
     for (int i = 0; i < ITERS; ++i) {
 #pragma unroll
@@ -24,9 +24,16 @@ __global__ void pipe_kernel(double* out, double seed)
             if (OP == 5) a[k] = a[k] * b;                              // DMUL
             if (OP == 6) a[k] = sqrt(a[k]) + b;                        // DSQRT sequence
             if (OP == 7) a[k] = b / a[k] + c;                          // DDIV sequence
+            if (OP == 8) { a[k] = fma(a[k], b, c); a[k] = fma(a[k], b, c); a[k] = fma(a[k], b, c); a[k] = fma(a[k], b, c); }  // 4 DFMA
+            if (OP == 9) { f[k] = (float)a[k]; a[k] = (double)(f[k] * fb); }   // F2F pair + FMUL (dependent)
+            if (OP == 10) {                                            // 4 DFMA on a[] + independent F2F pair on g
+                a[k] = fma(a[k], b, c); a[k] = fma(a[k], b, c); a[k] = fma(a[k], b, c); a[k] = fma(a[k], b, c);
+                f[k] = (float)g[k]; g[k] = (double)(f[k] * fb);
+            }
+            if (OP == 11) { g[k] = (double)(float)g[k] * b; }          // F2F pair + DMUL
         }
     }
-    double s = 0; for (int k = 0; k < ILP; ++k) s += a[k] + f[k];
+    double s = 0; for (int k = 0; k < ILP; ++k) s += a[k] + f[k] + g[k];
     if (s == 12345.678) out[0] = s;
 }
 
@@ -81,6 +88,10 @@ int main()
     run_pipe<4>("SHFL.64 + DADD", p.multiProcessorCount, ghz, 1);
     run_pipe<6>("sqrt(double)+DADD", p.multiProcessorCount, ghz, 1);
     run_pipe<7>("div(double)+DADD", p.multiProcessorCount, ghz, 1);
+    run_pipe<8>("4x DFMA", p.multiProcessorCount, ghz, 1);
+    run_pipe<9>("F2F d->f, FMUL, F2F f->d", p.multiProcessorCount, ghz, 1);
+    run_pipe<10>("4x DFMA + independent F2F pair", p.multiProcessorCount, ghz, 1);
+    run_pipe<11>("F2F pair + DMUL", p.multiProcessorCount, ghz, 1);
 
     size_t bytes = 4ull << 30;
     void *a, *b; cudaMalloc(&a, bytes); cudaMalloc(&b, bytes);
