@@ -33,15 +33,32 @@ import numpy as np  # noqa: E402
 METRIC = "interpolated lon/lat pixels/sec (1km->250m)"
 UNIT = "px/s"
 SCANS_PER_GRANULE = 203
+FALLBACK_HBM_GBS = 6650.0            # /opt/skills/guides/B200_PROFILING.md fallback
+
+# The headline workload (default) and the secondary configurations of SURVEY.md 8(d).  The
+# driver only runs the default; the others are for `python bench.py --config ...`.
+CONFIGS = {
+    "cviirs_1km_250m": dict(kind="cviirs", coarse=1000, fine=250, width=0, n_in=3, tie_rows=2030, tie_cols=1354, f=4, out_cols=5416),
+    "cviirs_1km_500m": dict(kind="cviirs", coarse=1000, fine=500, width=0, n_in=3, tie_rows=2030, tie_cols=1354, f=2, out_cols=2708),
+    "cviirs_5km_1km": dict(kind="cviirs", coarse=5000, fine=1000, width=271, n_in=3, tie_rows=406, tie_cols=271, f=5, out_cols=1354),
+    "cviirs_5km_1km_270": dict(kind="cviirs", coarse=5000, fine=1000, width=270, n_in=3, tie_rows=406, tie_cols=270, f=5, out_cols=1354),
+    "simple_1km_250m": dict(kind="simple", coarse=1000, fine=250, width=0, n_in=2, tie_rows=2030, tie_cols=1354, f=4, out_cols=5416),
+    "simple_1km_500m": dict(kind="simple", coarse=1000, fine=500, width=0, n_in=2, tie_rows=2030, tie_cols=1354, f=2, out_cols=2708),
+}
 TIE_ROWS, TIE_COLS = 2030, 1354
 OUT_ROWS, OUT_COLS = 8120, 5416
 PX_PER_GRANULE = OUT_ROWS * OUT_COLS
-FALLBACK_HBM_GBS = 6650.0            # /opt/skills/guides/B200_PROFILING.md fallback
 
 
-def algorithmic_bytes_per_px(itemsize, n_in=3, ratio=16):
-    """Each input element read once, each output written once: 17.5 B f64."""
-    return 2 * itemsize + n_in * itemsize / ratio
+def px_per_granule(cfg):
+    return cfg["tie_rows"] * cfg["f"] * cfg["out_cols"]
+
+
+def algorithmic_bytes_per_px(itemsize, cfg=None):
+    """Each input element read once, each output written once: 17.5 B/px for
+    CVIIRS 1 km -> 250 m float64."""
+    cfg = cfg or CONFIGS["cviirs_1km_250m"]
+    return 2 * itemsize + cfg["n_in"] * itemsize * (cfg["tie_rows"] * cfg["tie_cols"]) / px_per_granule(cfg)
 
 
 def parse_args():
@@ -53,6 +70,8 @@ def parse_args():
     ap.add_argument("--dtype", choices=["f64", "f32"], default="f64")
     ap.add_argument("--granules-per-gpu", type=int, default=36)
     ap.add_argument("--e2e-granules", type=int, default=4)
+    ap.add_argument("--config", choices=sorted(CONFIGS), default="cviirs_1km_250m",
+                    help="workload; the default is the headline metric, the others are SURVEY 8(d) secondary configs")
     ap.add_argument("--kernel", choices=["auto", "generic"], default="auto",
                     help="auto = what the public API runs; generic = force the rounding-faithful kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -63,13 +82,20 @@ def parse_args():
 # ------------------------------------------------------------------------------------
 # synthetic inputs
 # ------------------------------------------------------------------------------------
-def make_granules(first, count, dtype):
+def make_granules(first, count, dtype, cfg=None):
     """`count` consecutive synthetic granules of the day, stacked along the scan axis."""
     from concurrent.futures import ThreadPoolExecutor
     from geotiepoints_b200 import testing
+    cfg = cfg or CONFIGS["cviirs_1km_250m"]
+
+    def one(g):
+        arrs = testing.modis_granule(g % 288, dtype=dtype)
+        if cfg["coarse"] == 5000:
+            arrs = testing.subsample_5km(*arrs, width=cfg["width"])
+        return arrs
     with ThreadPoolExecutor(min(8, max(1, count))) as pool:
-        parts = list(pool.map(lambda g: testing.modis_granule(g % 288, dtype=dtype), range(first, first + count)))
-    return tuple(np.concatenate([p[k] for p in parts]) for k in range(3))
+        parts = list(pool.map(one, range(first, first + count)))
+    return tuple(np.concatenate([p[k] for p in parts]) for k in range(cfg["n_in"]))
 
 
 # ------------------------------------------------------------------------------------
@@ -235,24 +261,33 @@ def run_b200_arm(args, dtype):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
+    cfg = CONFIGS[args.config]
+    headline = args.config == "cviirs_1km_250m"
     tdtype = torch.float64 if dtype == np.float64 else torch.float32
     itemsize = np.dtype(dtype).itemsize
     G = args.granules_per_gpu
     # rank r owns the contiguous scan range of granules [r*G, (r+1)*G) of the day
     g_lo, g_hi = sharding.granule_range(rank, world, G * world)
-    lon, lat, satz = make_granules(g_lo, g_hi - g_lo, dtype)
-    n_scans = lon.shape[0] // 10
-    d_in = [torch.from_numpy(a).to(device) for a in (lon, lat, satz)]
-    out_lon = torch.empty((n_scans * 40, OUT_COLS), dtype=tdtype, device=device)
+    host_in = make_granules(g_lo, g_hi - g_lo, dtype, cfg)
+    lon, lat = host_in[0], host_in[1]
+    rows_per_scan = 10 if cfg["coarse"] == 1000 else 2
+    n_scans = lon.shape[0] // rows_per_scan
+    out_rows_per_scan = rows_per_scan * cfg["f"]
+    d_in = [torch.from_numpy(a).to(device) for a in host_in]
+    out_lon = torch.empty((n_scans * out_rows_per_scan, cfg["out_cols"]), dtype=tdtype, device=device)
     out_lat = torch.empty_like(out_lon)
     lib = _capi.lib()
     suffix = "f64" if dtype == np.float64 else "f32"
-    fn = lib.gtp_cviirs_interp_generic_f64 if (args.kernel == "generic" and suffix == "f64") \
-        else getattr(lib, f"gtp_cviirs_interp_{suffix}")
+    generic = args.kernel == "generic" and suffix == "f64"
+    fn = getattr(lib, f"gtp_{cfg['kind']}_interp_" + ("generic_f64" if generic else suffix))
     stream = torch.cuda.current_stream(device)
+    if cfg["kind"] == "cviirs":
+        scalars = (cfg["coarse"], cfg["fine"], cfg["width"])
+    else:
+        scalars = (cfg["tie_cols"], cfg["coarse"] // cfg["fine"])
 
     def step():
-        rc = fn(d_in[0].data_ptr(), d_in[1].data_ptr(), d_in[2].data_ptr(), n_scans, 1000, 250, 0,
+        rc = fn(*[t.data_ptr() for t in d_in], n_scans, *scalars,
                 out_lon.data_ptr(), out_lat.data_ptr(), local_rank, ctypes.c_void_p(stream.cuda_stream))
         _capi.check(rc)
 
@@ -261,14 +296,20 @@ def run_b200_arm(args, dtype):
             dist.barrier()
         torch.cuda.synchronize(device)
 
+    # clocks are sampled from before the warm-up to the end of the timed region (the timed
+    # region alone can be shorter than one 200 ms nvidia-smi period)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    t_load = time.perf_counter()
+    while time.perf_counter() - t_load < 0.6:      # keep the GPU under the same load for >= 3 samples
         step()
     barrier()
 
     # -- timed region: exactly K steps, one kernel launch each -------------------------
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches_before = _capi.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -287,7 +328,7 @@ def run_b200_arm(args, dtype):
     elapsed_ms = sharding.max_over_ranks(elapsed_ms, dist if world > 1 else None)
     kernel_ms_max = sharding.max_over_ranks(kernel_ms, dist if world > 1 else None)
 
-    px_per_rank_step = n_scans * 40 * OUT_COLS
+    px_per_rank_step = n_scans * out_rows_per_scan * cfg["out_cols"]
     total_px = px_per_rank_step * world * args.steps
     value = total_px / (elapsed_ms * 1e-3)
 
@@ -299,40 +340,59 @@ def run_b200_arm(args, dtype):
             import gtp_oracle
             from parity import compare
             ns = 8
-            exp = gtp_oracle.cviirs(lon[:ns * 10], lat[:ns * 10], satz[:ns * 10], 1000, 250, n_threads=8)
-            parity = compare(out_lon[:ns * 40].cpu().numpy(), out_lat[:ns * 40].cpu().numpy(), *exp)
+            sub = [a[:ns * rows_per_scan] for a in host_in]
+            with np.errstate(all="ignore"):
+                if cfg["kind"] == "cviirs":
+                    exp = gtp_oracle.cviirs(*sub, cfg["coarse"], cfg["fine"], cfg["width"], n_threads=8)
+                else:
+                    exp = gtp_oracle.simple(*sub, cfg["coarse"], cfg["fine"], n_threads=8)
+            parity = compare(out_lon[:ns * out_rows_per_scan].cpu().numpy(),
+                             out_lat[:ns * out_rows_per_scan].cpu().numpy(), *exp)
         except Exception as exc:  # the checker must never take the measurement down
             parity = {"error": repr(exc)}
 
     # -- end to end through the public API: pinned host buffers, H2D + D2H inside --------
     e2e = None
     if not args.no_e2e:
+        from geotiepoints_b200 import simple_modis_interpolator
+        from geotiepoints_b200._modis_interpolator import interpolate as cviirs_interpolate
+        if cfg["kind"] == "cviirs":
+            def public_api(*arrs):
+                return cviirs_interpolate(*arrs, coarse_resolution=cfg["coarse"], fine_resolution=cfg["fine"],
+                                          coarse_scan_width=cfg["width"])
+            if headline:
+                public_api = modisinterpolator.modis_1km_to_250m
+        else:
+            def public_api(*arrs):
+                return simple_modis_interpolator.interpolate_geolocation_cartesian(
+                    *arrs, coarse_resolution=cfg["coarse"], fine_resolution=cfg["fine"])
         ge = min(args.e2e_granules, G)
-        rows = ge * TIE_ROWS
+        rows = ge * cfg["tie_rows"]
         h_in = []
-        for a in (lon, lat, satz):
-            pinned = _capi.pinned_pool.empty((rows, TIE_COLS), dtype)
+        for a in host_in:
+            pinned = _capi.pinned_pool.empty((rows, cfg["tie_cols"]), dtype)
             pinned[...] = a[:rows]
             h_in.append(pinned)
-        res = modisinterpolator.modis_1km_to_250m(*h_in)      # warm-up (pinned pool, stream pool)
+        res = public_api(*h_in)      # warm-up (pinned pool, stream pool)
         del res
         e2e_steps = max(1, min(args.steps, 5))
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            res = modisinterpolator.modis_1km_to_250m(*h_in)
+            res = public_api(*h_in)
             checksum = float(res[0][-1, -1]) + float(res[1][-1, -1])
             del res
         torch.cuda.synchronize(device)
         dt = time.perf_counter() - t0
         dt = sharding.max_over_ranks(dt, dist if world > 1 else None)
-        e2e_px = ge * PX_PER_GRANULE
+        e2e_px = ge * px_per_granule(cfg)
         e2e = {"value": e2e_px * world * e2e_steps / dt, "unit": UNIT,
-               "h2d_bytes_per_step": int(3 * rows * TIE_COLS * itemsize),
+               "h2d_bytes_per_step": int(cfg["n_in"] * rows * cfg["tie_cols"] * itemsize),
                "d2h_bytes_per_step": int(2 * e2e_px * itemsize),
                "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
-               "sample": f"{ge} granules per GPU per call through geotiepoints_b200.modisinterpolator."
-                         f"modis_1km_to_250m(numpy), pinned host inputs, pinned host outputs",
+               "sample": f"{ge} granules per GPU per call through the public numpy API "
+                         f"({'geotiepoints_b200.modisinterpolator.modis_1km_to_250m' if headline else args.config}), "
+                         f"pinned host inputs, pinned host outputs",
                "checksum": checksum}
 
     if rank == 0:
@@ -341,16 +401,22 @@ def run_b200_arm(args, dtype):
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
         else:
             peak, peak_src = FALLBACK_HBM_GBS, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
-        bpp = algorithmic_bytes_per_px(itemsize)
+        bpp = algorithmic_bytes_per_px(itemsize, cfg)
         achieved = bpp * px_per_rank_step / (kernel_ms_max * 1e-3) / 1e9
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if headline else f"interpolated lon/lat pixels/sec ({args.config})",
+            "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {
-                "workload": f"CVIIRS 1km->250m, {G} synthetic MODIS granules (2030x1354 {np.dtype(dtype).name} tie points "
-                            f"-> 8120x5416 lon+lat each) per GPU per step, one launch per step; BASELINE configs[1] "
-                            f"batched x{G}; {G * world} granules whole-job" + (" = configs[3] full day" if G * world == 288 else ""),
+                "workload": (f"CVIIRS 1km->250m, {G} synthetic MODIS granules (2030x1354 {np.dtype(dtype).name} tie points "
+                             f"-> 8120x5416 lon+lat each) per GPU per step, one launch per step; BASELINE configs[1] "
+                             f"batched x{G}; {G * world} granules whole-job" + (" = configs[3] full day" if G * world == 288 else ""))
+                if headline else
+                            (f"{args.config}, {G} synthetic MODIS granules ({cfg['tie_rows']}x{cfg['tie_cols']} "
+                             f"{np.dtype(dtype).name} tie points -> {cfg['tie_rows'] * cfg['f']}x{cfg['out_cols']} lon+lat each) "
+                             f"per GPU per step, one launch per step"),
+                "config_name": args.config,
                 "granules_per_gpu": G, "kernel": args.kernel,
                 "l2": f"working set per step {(bpp * px_per_rank_step) / 1e9:.1f} GB per GPU >> 126 MB L2 (no flush needed)",
                 "sharding": "contiguous scan ranges per rank, outputs resident per rank, no collective on the data path",
@@ -365,7 +431,7 @@ def run_b200_arm(args, dtype):
         }
         if e2e is not None:
             line["e2e"] = e2e
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and headline:
             try:
                 line["cpu_baseline"] = cpu_baseline(dtype)
             except Exception as exc:

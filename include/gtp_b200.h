@@ -79,6 +79,9 @@ int gtp_cviirs_interp_generic_f64(const double* lon, const double* lat, const do
                                   int coarse_res, int fine_res, int coarse_width,
                                   double* out_lon, double* out_lat, int device, void* stream);
 
+int gtp_simple_interp_generic_f64(const double* lon, const double* lat, int64_t n_scans, int64_t width, int res_factor,
+                                  double* out_lon, double* out_lat, int device, void* stream);
+
 /* ---- host-pointer entry points (synchronous; copies inside) -------------------- */
 /* Inputs and outputs are host buffers (pageable or pinned).  The call splits the scans
  * into chunks and overlaps H2D, kernel and D2H on three streams; it returns when the

@@ -41,6 +41,7 @@ for _suf in ("f32", "f64"):
     SIGNATURES[f"gtp_cviirs_interp_host_{_suf}"] = (_int, [_vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _int])
     SIGNATURES[f"gtp_simple_interp_host_{_suf}"] = (_int, [_vp, _vp, _i64, _i64, _int, _vp, _vp, _int])
 SIGNATURES["gtp_cviirs_interp_generic_f64"] = SIGNATURES["gtp_cviirs_interp_f64"]
+SIGNATURES["gtp_simple_interp_generic_f64"] = SIGNATURES["gtp_simple_interp_f64"]
 
 
 class GtpError(RuntimeError):

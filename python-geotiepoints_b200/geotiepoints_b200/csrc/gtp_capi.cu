@@ -79,7 +79,7 @@ int cviirs_device(const T* lon, const T* lat, const T* satz, int64_t n_scans, in
 
 template <typename T>
 int simple_device(const T* lon, const T* lat, int64_t n_scans, int64_t width, int res, T* out_lon, T* out_lat,
-                  int device, void* stream)
+                  int device, void* stream, bool allow_fast)
 {
     if (res != 2 && res != 4) return fail(GTP_E_RESOLUTION, "simple interpolator: res_factor must be 2 or 4%s");
     if (n_scans < 0) return fail(GTP_E_SHAPE, "n_scans must be >= 0%s");
@@ -88,7 +88,15 @@ int simple_device(const T* lon, const T* lat, int64_t n_scans, int64_t width, in
     if (!lon || !lat || !out_lon || !out_lat) return fail(GTP_E_NULL, "null buffer%s");
     DeviceGuard guard(device);
     if (guard.err != cudaSuccess) { cudaGetLastError(); return fail(GTP_E_NO_DEVICE, "no usable CUDA device: %s", cudaGetErrorString(guard.err)); }
-    cudaError_t e = gtp_launch_simple_generic<T>(lon, lat, out_lon, out_lat, n_scans, (int)width, res, (cudaStream_t)stream);
+    cudaError_t e;
+    if constexpr (sizeof(T) == 8) {
+        if (allow_fast && gtp_simple_fast_f64_supported((int)width, res))
+            e = gtp_launch_simple_fast_f64(lon, lat, out_lon, out_lat, n_scans, res, (cudaStream_t)stream);
+        else
+            e = gtp_launch_simple_generic<T>(lon, lat, out_lon, out_lat, n_scans, (int)width, res, (cudaStream_t)stream);
+    } else {
+        e = gtp_launch_simple_generic<T>(lon, lat, out_lon, out_lat, n_scans, (int)width, res, (cudaStream_t)stream);
+    }
     if (e != cudaSuccess) return cuda_fail(e, "simple launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return GTP_OK;
@@ -185,7 +193,7 @@ int simple_host(const T* lon, const T* lat, int64_t n_scans, int64_t width, int 
     const T* const in[2] = {lon, lat};
     return host_pipeline<T, 2>(in, out_lon, out_lat, n_scans, 10 * width, 10 * res * width * res, device,
         [&](T* const* d_in, T* d_lon, T* d_lat, int64_t ns, cudaStream_t st) {
-            return simple_device<T>(d_in[0], d_in[1], ns, width, res, d_lon, d_lat, -1, (void*)st);
+            return simple_device<T>(d_in[0], d_in[1], ns, width, res, d_lon, d_lat, -1, (void*)st, true);
         });
 }
 
@@ -234,11 +242,15 @@ int gtp_cviirs_interp_generic_f64(const double* lon, const double* lat, const do
 
 int gtp_simple_interp_f32(const float* lon, const float* lat, int64_t n_scans, int64_t width, int res_factor,
                           float* out_lon, float* out_lat, int device, void* stream)
-{ return simple_device<float>(lon, lat, n_scans, width, res_factor, out_lon, out_lat, device, stream); }
+{ return simple_device<float>(lon, lat, n_scans, width, res_factor, out_lon, out_lat, device, stream, true); }
 
 int gtp_simple_interp_f64(const double* lon, const double* lat, int64_t n_scans, int64_t width, int res_factor,
                           double* out_lon, double* out_lat, int device, void* stream)
-{ return simple_device<double>(lon, lat, n_scans, width, res_factor, out_lon, out_lat, device, stream); }
+{ return simple_device<double>(lon, lat, n_scans, width, res_factor, out_lon, out_lat, device, stream, true); }
+
+int gtp_simple_interp_generic_f64(const double* lon, const double* lat, int64_t n_scans, int64_t width, int res_factor,
+                                  double* out_lon, double* out_lat, int device, void* stream)
+{ return simple_device<double>(lon, lat, n_scans, width, res_factor, out_lon, out_lat, device, stream, false); }
 
 int gtp_cviirs_interp_host_f32(const float* lon, const float* lat, const float* satz, int64_t n_scans,
                                int coarse_res, int fine_res, int coarse_width, float* out_lon, float* out_lat, int device)

@@ -101,11 +101,17 @@ __device__ __forceinline__ void quad_rows_low_mixed(const Quad& q, const double 
     }
 }
 
-template <int P>
+// SIMPLE = true is simple_modis_interpolator: the same bilinear form with a_scan = s_s and
+// a_track = s_t, i.e. c_expansion = c_alignment = 0 and no zenith-angle input.  In exact
+// arithmetic the reference's order-1 map_coordinates + linear extrapolation of the last 3 (1)
+// columns and first/last 2 (1) rows (_simple_modis_interpolator.pyx:85-225) IS that bilinear
+// form evaluated at t_y = j/res - (res/16 + 1/8) - r, t_x = i/res - c: the
+// fine-row / column fractions coincide with the CVIIRS ones of the same resolution.
+template <int P, bool SIMPLE>
 __global__ void __launch_bounds__(kThreads, GTP_FAST_MIN_BLOCKS)
-cviirs_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restrict__ lat,
-                           const double* __restrict__ satz, double* __restrict__ out_lon,
-                           double* __restrict__ out_lat, long long n_scans)
+modis_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restrict__ lat,
+                          const double* __restrict__ satz, double* __restrict__ out_lon,
+                          double* __restrict__ out_lat, long long n_scans)
 {
     constexpr int kWf = kW * P;          // fine columns
     constexpr int kN = kL * P;           // fine rows per scan
@@ -127,7 +133,7 @@ cviirs_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restr
 
     const double* plon = lon + scan * (long long)(kL * kW) + tc;
     const double* plat = lat + scan * (long long)(kL * kW) + tc;
-    const double* psatz = satz + scan * (long long)(kL * kW) + tc;
+    const double* psatz = SIMPLE ? nullptr : satz + scan * (long long)(kL * kW) + tc;
     double* olon = out_lon + scan * (long long)kN * kWf + (long long)quad_col * P + xoff;
     double* olat = out_lat + scan * (long long)kN * kWf + (long long)quad_col * P + xoff;
 
@@ -139,19 +145,19 @@ cviirs_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restr
     __shared__ double stage[2][3][kThreads];     // double-buffered next-row inputs, one slot per thread
     cp_async8(&stage[0][0][threadIdx.x], plon);
     cp_async8(&stage[0][1][threadIdx.x], plat);
-    cp_async8(&stage[0][2][threadIdx.x], psatz);
+    if (!SIMPLE) cp_async8(&stage[0][2][threadIdx.x], psatz);
     cp_async_commit();
 
 #pragma unroll 1
     for (int r = 0; r < kL; ++r) {
         cp_async_wait_all();
-        const double clon = stage[r & 1][0][threadIdx.x], clat = stage[r & 1][1][threadIdx.x],
-                     csatz = stage[r & 1][2][threadIdx.x];
+        const double clon = stage[r & 1][0][threadIdx.x], clat = stage[r & 1][1][threadIdx.x];
+        const double csatz = SIMPLE ? 0.0 : stage[r & 1][2][threadIdx.x];
         if (r + 1 < kL) {            // fetch the next tie row while this one is worked on
-            plon += kW; plat += kW; psatz += kW;
+            plon += kW; plat += kW;
             cp_async8(&stage[(r + 1) & 1][0][threadIdx.x], plon);
             cp_async8(&stage[(r + 1) & 1][1][threadIdx.x], plat);
-            cp_async8(&stage[(r + 1) & 1][2][threadIdx.x], psatz);
+            if (!SIMPLE) { psatz += kW; cp_async8(&stage[(r + 1) & 1][2][threadIdx.x], psatz); }
             cp_async_commit();
         }
         // this lane's tie point of row r; corner B of the lane's quad column comes from lane + 1
@@ -215,7 +221,7 @@ cviirs_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restr
         topA = curA;
         topB = curB;
 
-        if (r + 1 < kL) {
+        if (!SIMPLE && r + 1 < kL) {
             // expansion / alignment of the quad row BELOW this tie row, from this row's zenith angles
             const TieZen zen = tie_zen(csatz);
             double zb = __shfl_down_sync(kFull, zen.za, 1);
@@ -241,21 +247,50 @@ bool gtp_cviirs_fast_f64_supported(const CviirsCfg& cfg)
     return cfg.km == 1 && (cfg.p == 4 || cfg.p == 2);
 }
 
+bool gtp_simple_fast_f64_supported(int width, int res)
+{
+    return width == kW && (res == 4 || res == 2);
+}
+
+namespace {
+
+// 256-bit (P = 4) / 128-bit (P = 2) stores need aligned outputs; the row pitch already is
+bool outputs_aligned(const double* out_lon, const double* out_lat, int p)
+{
+    const uintptr_t align = (p == 4) ? 32 : 16;
+    return (((uintptr_t)out_lon | (uintptr_t)out_lat) & (align - 1)) == 0;
+}
+
+template <int P, bool SIMPLE>
+cudaError_t launch_fast(const double* lon, const double* lat, const double* satz, double* out_lon, double* out_lat,
+                        long long n_scans, cudaStream_t stream)
+{
+    const long long warps = n_scans * kWarpsPerScan;
+    const long long blocks = (warps * 32 + kThreads - 1) / kThreads;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    modis_fast_1km_f64_kernel<P, SIMPLE><<<(unsigned)blocks, kThreads, 0, stream>>>(lon, lat, satz, out_lon, out_lat, n_scans);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
 cudaError_t gtp_launch_cviirs_fast_f64(const double* lon, const double* lat, const double* satz,
                                        double* out_lon, double* out_lat,
                                        long long n_scans, const CviirsCfg& cfg, cudaStream_t stream)
 {
     if (n_scans <= 0) return cudaSuccess;
-    // 256-bit (P = 4) / 128-bit (P = 2) stores need aligned outputs; the row pitch already is
-    const uintptr_t align = (cfg.p == 4) ? 32 : 16;
-    if (((uintptr_t)out_lon | (uintptr_t)out_lat) & (align - 1))
+    if (!outputs_aligned(out_lon, out_lat, cfg.p))
         return gtp_launch_cviirs_generic<double>(lon, lat, satz, out_lon, out_lat, n_scans, cfg, stream);
-    const long long warps = n_scans * kWarpsPerScan;
-    const long long blocks = (warps * 32 + kThreads - 1) / kThreads;
-    if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    if (cfg.p == 4)
-        cviirs_fast_1km_f64_kernel<4><<<(unsigned)blocks, kThreads, 0, stream>>>(lon, lat, satz, out_lon, out_lat, n_scans);
-    else
-        cviirs_fast_1km_f64_kernel<2><<<(unsigned)blocks, kThreads, 0, stream>>>(lon, lat, satz, out_lon, out_lat, n_scans);
-    return cudaGetLastError();
+    return cfg.p == 4 ? launch_fast<4, false>(lon, lat, satz, out_lon, out_lat, n_scans, stream)
+                      : launch_fast<2, false>(lon, lat, satz, out_lon, out_lat, n_scans, stream);
+}
+
+cudaError_t gtp_launch_simple_fast_f64(const double* lon, const double* lat, double* out_lon, double* out_lat,
+                                       long long n_scans, int res, cudaStream_t stream)
+{
+    if (n_scans <= 0) return cudaSuccess;
+    if (!outputs_aligned(out_lon, out_lat, res))
+        return gtp_launch_simple_generic<double>(lon, lat, out_lon, out_lat, n_scans, kW, res, stream);
+    return res == 4 ? launch_fast<4, true>(lon, lat, nullptr, out_lon, out_lat, n_scans, stream)
+                    : launch_fast<2, true>(lon, lat, nullptr, out_lon, out_lat, n_scans, stream);
 }

@@ -16,3 +16,6 @@ cudaError_t gtp_launch_cviirs_fast_f64(const double* lon, const double* lat, con
                                        double* out_lon, double* out_lat,
                                        long long n_scans, const CviirsCfg& cfg, cudaStream_t stream);
 bool gtp_cviirs_fast_f64_supported(const CviirsCfg& cfg);
+cudaError_t gtp_launch_simple_fast_f64(const double* lon, const double* lat, double* out_lon, double* out_lat,
+                                       long long n_scans, int res, cudaStream_t stream);
+bool gtp_simple_fast_f64_supported(int width, int res);

@@ -10,9 +10,10 @@
 
 using namespace gtpfast;
 
+// simple == true: simple_modis_interpolator = the same bilinear form with c_exp = c_ali = 0
 template <int P>
 static void run(const double* lon, const double* lat, const double* satz, long n_scans,
-                double* out_lon, double* out_lat, long* mode_counts)
+                double* out_lon, double* out_lat, long* mode_counts, bool simple = false)
 {
     const int W = 1354, L = 10, Wf = W * P, N = L * P, H = P / 2;
     for (long s = 0; s < n_scans; ++s) {
@@ -24,9 +25,11 @@ static void run(const double* lon, const double* lat, const double* satz, long n
                 auto zen = [&](int r, int c) { long o = (s * L + r) * W + c; return tie_zen(satz[o]); };
                 const TieGeo A = geo(qr, ca);
                 const Vec3 Ax = tie_xyz(A), B = tie_xyz(geo(qr, cb)), D = tie_xyz(geo(qr + 1, ca)), C = tie_xyz(geo(qr + 1, cb));
-                const TieZen za = zen(qr, ca), zb = zen(qr, cb);
-                double ce, cal;
-                quad_coefficients(za, zb.za, zb.sphi, zb.cphi, 1, ce, cal);
+                double ce = 0.0, cal = 0.0;
+                if (!simple) {
+                    const TieZen za = zen(qr, ca), zb = zen(qr, cb);
+                    quad_coefficients(za, zb.za, zb.sphi, zb.cphi, 1, ce, cal);
+                }
                 const Quad q = quad_setup(A, Ax, B, C, D, ce, cal);
                 mode_counts[q.mode]++;
                 const int j0 = (qr == 0) ? 0 : qr * P + H;
@@ -54,6 +57,16 @@ static void run(const double* lon, const double* lat, const double* satz, long n
             }
         }
     }
+}
+
+extern "C" int gtp_emul_simple_fast_f64(const double* lon, const double* lat, long n_scans, int fine_res,
+                                        double* out_lon, double* out_lat, long* mode_counts)
+{
+    for (int k = 0; k < 4; ++k) mode_counts[k] = 0;
+    if (fine_res == 250) run<4>(lon, lat, nullptr, n_scans, out_lon, out_lat, mode_counts, true);
+    else if (fine_res == 500) run<2>(lon, lat, nullptr, n_scans, out_lon, out_lat, mode_counts, true);
+    else return 1;
+    return 0;
 }
 
 extern "C" int gtp_emul_cviirs_fast_f64(const double* lon, const double* lat, const double* satz, long n_scans,

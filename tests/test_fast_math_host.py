@@ -38,6 +38,17 @@ def emul():
                                           out_lat.ctypes.data_as(dp), modes)
         assert rc == 0
         return out_lon, out_lat, dict(zip(("slow", "low", "high", "both"), modes))
+
+    def run_simple(lon, lat, fine):
+        ns, p = lon.shape[0] // 10, 1000 // fine
+        out_lon = np.full((ns * 10 * p, 1354 * p), np.nan)
+        out_lat = np.full_like(out_lon, np.nan)
+        modes = (ctypes.c_long * 4)()
+        rc = lib.gtp_emul_simple_fast_f64(lon.ctypes.data_as(dp), lat.ctypes.data_as(dp), ctypes.c_long(ns), fine,
+                                          out_lon.ctypes.data_as(dp), out_lat.ctypes.data_as(dp), modes)
+        assert rc == 0
+        return out_lon, out_lat, dict(zip(("slow", "low", "high", "both"), modes))
+    run.simple = run_simple
     return run
 
 
@@ -89,3 +100,24 @@ def test_unphysical_inputs_fall_back(emul):
     s = compare(got_lon, got_lat, *exp)
     assert s["nan_pattern_equal"], s
     assert s["max_dlat"] < 1e-7 and max(s["max_dlon_outside_band"], s["max_dlon_in_band"]) < 1e-7, s
+
+
+@pytest.mark.parametrize("fine", [250, 500])
+@pytest.mark.parametrize("granule", [0, 3, 5, 14, 287])
+def test_simple_fast_math_matches_oracle(emul, granule, fine):
+    """simple_modis_interpolator as the bilinear form with c_exp = c_ali = 0 (SURVEY.md 8a
+    closed form) against the oracle's map_coordinates + extrapolation restatement."""
+    lon, lat, _ = testing.modis_granule(granule, n_scans=3)
+    got_lon, got_lat, modes = emul.simple(lon, lat, fine)
+    exp = gtp_oracle.simple(lon, lat, 1000, fine, n_threads=4)
+    assert_parity(got_lon, got_lat, *exp, what=f"host emulation simple granule {granule} -> {fine} m, modes {modes}")
+
+
+@pytest.mark.parametrize("name", ["antimeridian", "pole", "south_pole", "prime_meridian", "lat_switch", "zeros", "nan_holes"])
+def test_simple_fast_math_stress_inputs(emul, golden_inputs, name):
+    lon, lat, _ = (a.astype(np.float64) for a in golden_inputs[name])
+    for fine in (250, 500):
+        got_lon, got_lat, modes = emul.simple(lon, lat, fine)
+        with np.errstate(all="ignore"):
+            exp = gtp_oracle.simple(lon, lat, 1000, fine)
+        assert_parity(got_lon, got_lat, *exp, what=f"host emulation simple {name} -> {fine} m, modes {modes}")

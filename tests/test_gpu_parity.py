@@ -113,6 +113,24 @@ def test_generic_f64_kernel_matches_oracle_tightly():
     assert s["max_dlat"] < 1e-12 and s["max_dlon_outside_band"] < 1e-12, s
 
 
+def test_generic_f64_simple_kernel_matches_oracle_tightly():
+    """The rounding-faithful simple kernel (map_coordinates + extrapolation, tap by tap)."""
+    import ctypes
+    import torch
+    lon, lat, _ = testing.modis_granule(21, n_scans=6)
+    exp = gtp_oracle.simple(lon, lat, 1000, 250, n_threads=8)
+    d = [torch.from_numpy(a).cuda() for a in (lon, lat)]
+    out_lon = torch.empty(exp[0].shape, dtype=torch.float64, device="cuda")
+    out_lat = torch.empty_like(out_lon)
+    rc = _capi.lib().gtp_simple_interp_generic_f64(d[0].data_ptr(), d[1].data_ptr(), 6, 1354, 4,
+                                                    out_lon.data_ptr(), out_lat.data_ptr(), 0,
+                                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _capi.check(rc)
+    torch.cuda.synchronize()
+    s = compare(out_lon.cpu().numpy(), out_lat.cpu().numpy(), *exp)
+    assert s["max_dlat"] < 1e-12 and s["max_dlon_outside_band"] < 1e-12, s
+
+
 def test_torch_device_path_matches_host_path():
     import torch
     lon, lat, satz = testing.modis_granule(3, n_scans=5)
