@@ -74,6 +74,8 @@ def parse_args():
                     help="workload; the default is the headline metric, the others are SURVEY 8(d) secondary configs")
     ap.add_argument("--kernel", choices=["auto", "generic"], default="auto",
                     help="auto = what the public API runs; generic = force the rounding-faithful kernel")
+    ap.add_argument("--sustained-seconds", type=float, default=1.0,
+                    help="extra load before the `sustained` measurement (0 = skip it)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -102,55 +104,90 @@ def make_granules(first, count, dtype, cfg=None):
 # clocks
 # ------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons sampled every few ms through NVML (nvidia-ml-py) in a
+    background thread, so that even a 50 ms timed region gets its own samples; falls back to
+    `nvidia-smi -lms` when NVML is not importable."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+               "hw_power_brake_slowdown": 0x80}
 
-    def __init__(self, gpu_index):
-        self.gpu_index = gpu_index
-        self.proc = None
-        self.lines = []
+    def __init__(self, gpu_index, period_s=0.004):
+        self.gpu_index, self.period_s = gpu_index, period_s
+        self.samples = []          # (t, sm_mhz, power_w, reasons_bitmask)
+        self.sm_max = None
+        self._stop = threading.Event()
+        self._thread = None
+        self.source = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        mhz = pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
+                        watts = pynvml.nvmlDeviceGetPowerUsage(handle) / 1000.0
+                        try:
+                            mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                        except AttributeError:
+                            mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                        self.samples.append((time.perf_counter(), float(mhz), watts, int(mask)))
+                    except Exception:
+                        pass
+                    self._stop.wait(self.period_s)
+            self._thread = threading.Thread(target=loop, daemon=True)
+            self._thread.start()
+        except Exception:
+            self._start_smi()
+
+    def _start_smi(self):
+        self.source = "nvidia-smi"
+        query = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active"
+        try:
+            proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={query}",
+                                     "--format=csv,noheader,nounits", "-lms", "50"],
+                                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.source = None
+            return
+
+        def loop():
+            for line in proc.stdout:
+                parts = [x.strip() for x in line.split(",")]
+                try:
+                    self.sm_max = float(parts[1])
+                    self.samples.append((time.perf_counter(), float(parts[0]), float(parts[2]), int(parts[3], 16)))
+                except (ValueError, IndexError):
+                    continue
+                if self._stop.is_set():
+                    break
+            proc.terminate()
+        self._thread = threading.Thread(target=loop, daemon=True)
+        self._thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, sm_max, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 8:
-                continue
-            try:
-                sm.append(float(parts[1])); sm_max.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": float(max(sm_max)) if sm_max else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+
+    def window(self, t0, t1):
+        """Summary of the samples taken in [t0, t1] (perf_counter seconds)."""
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"], "samples": 0}
+        rows = [r for r in self.samples if t0 <= r[0] <= t1]
+        if not rows:       # region shorter than the sampling period: take the nearest sample
+            rows = sorted(self.samples, key=lambda r: abs(r[0] - 0.5 * (t0 + t1)))[:1]
+        mask = 0
+        for r in rows:
+            mask |= r[3]
+        return {"sm_mhz": float(np.median([r[1] for r in rows])) if rows else None,
+                "sm_max_mhz": self.sm_max, "power_w": float(np.median([r[2] for r in rows])) if rows else None,
+                "samples": len(rows), "source": self.source,
+                "reasons": sorted(k for k, bit in self.REASONS.items() if mask & bit)}
 
 
 # ------------------------------------------------------------------------------------
@@ -296,16 +333,10 @@ def run_b200_arm(args, dtype):
             dist.barrier()
         torch.cuda.synchronize(device)
 
-    # clocks are sampled from before the warm-up to the end of the timed region (the timed
-    # region alone can be shorter than one 200 ms nvidia-smi period)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    t_load = time.perf_counter()
-    while time.perf_counter() - t_load < 0.6:      # keep the GPU under the same load for >= 3 samples
         step()
     barrier()
 
@@ -314,6 +345,7 @@ def run_b200_arm(args, dtype):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    wall0 = time.perf_counter()
     t_begin.record(stream)
     for a, b in ev:
         a.record(stream)
@@ -321,10 +353,35 @@ def run_b200_arm(args, dtype):
         b.record(stream)
     t_end.record(stream)
     barrier()
+    wall1 = time.perf_counter()
     elapsed_ms = t_begin.elapsed_time(t_end)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     launches = _capi.launch_count() - launches_before
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.window(wall0, wall1) if rank == 0 else None
+
+    # -- sustained regime (reported beside the contract number, not instead of it): the kernel is
+    # FP64-heavy and a B200 reaches its 1 kW power cap after a few hundred ms of it ------------
+    sustained = None
+    if args.sustained_seconds > 0:
+        t_s = time.perf_counter()
+        while time.perf_counter() - t_s < args.sustained_seconds:
+            for _ in range(8):
+                step()
+            torch.cuda.synchronize(device)
+        n_sus = max(8, int(0.4 / max(kernel_ms * 1e-3, 1e-4)))
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        wall2 = time.perf_counter()
+        s0.record(stream)
+        for _ in range(n_sus):
+            step()
+        s1.record(stream)
+        torch.cuda.synchronize(device)
+        wall3 = time.perf_counter()
+        sus_ms = sharding.max_over_ranks(s0.elapsed_time(s1) / n_sus, dist if world > 1 else None)
+        sustained = {"ms_per_step": sus_ms, "steps": n_sus, "after_seconds_of_load": args.sustained_seconds,
+                     "clocks": sampler.window(wall2, wall3) if rank == 0 else None}
+    if rank == 0:
+        sampler.stop()
     elapsed_ms = sharding.max_over_ranks(elapsed_ms, dist if world > 1 else None)
     kernel_ms_max = sharding.max_over_ranks(kernel_ms, dist if world > 1 else None)
 
@@ -429,6 +486,11 @@ def run_b200_arm(args, dtype):
                          "px_per_launch": int(px_per_rank_step)},
             "parity": parity,
         }
+        if sustained is not None:
+            sus_value = px_per_rank_step * world / (sustained["ms_per_step"] * 1e-3)
+            sustained.update({"value": sus_value, "unit": UNIT,
+                              "roofline_frac": bpp * px_per_rank_step / (sustained["ms_per_step"] * 1e-3) / 1e9 / peak})
+            line["sustained"] = sustained
         if e2e is not None:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline and headline:

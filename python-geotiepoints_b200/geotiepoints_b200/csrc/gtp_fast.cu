@@ -40,6 +40,9 @@ __device__ __forceinline__ void store_px(double* p, const double (&v)[P]);
 template <>
 __device__ __forceinline__ void store_px<4>(double* p, const double (&v)[4])
 {
+#ifdef GTP_EXP_NO_STORE      // power experiment: keep the math, drop the HBM writes
+    if (v[0] != 1234.56789) return;
+#endif
     asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
 }
 
@@ -72,7 +75,11 @@ __device__ __forceinline__ void quad_rows(const Quad& q, const double (&a_col)[P
         const RowCoef rc = row_setup(q, s_t);
         double vlon[P], vlat[P];
 #pragma unroll
+#ifdef GTP_EXP_NO_MATH        // power experiment: keep the HBM writes, drop the per-pixel math
+        for (int k = 0; k < P; ++k) { vlon[k] = a_col[k] + rc.a_base; vlat[k] = a_col[k] - rc.Ue; }
+#else
         for (int k = 0; k < P; ++k) pixel_eval<MODE, WRAP>(q, rc, a_col[k], vlon[k], vlat[k]);
+#endif
         store_px<P>(olon, vlon);
         store_px<P>(olat, vlat);
         olon += kPitch; olat += kPitch;
@@ -195,7 +202,8 @@ modis_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restri
 #ifdef GTP_FAST_MIXED
                     if (q.mode == kLow) quad_rows_low_mixed<P, false>(q, a_col, s_t0, nrows, olon, olat);
 #else
-                    if (q.mode == kLow) quad_rows<P, kLow, false>(q, a_col, s_t0, nrows, olon, olat);
+                    if (q.small) quad_rows<P, kLowSmall, false>(q, a_col, s_t0, nrows, olon, olat);
+                    else if (q.mode == kLow) quad_rows<P, kLow, false>(q, a_col, s_t0, nrows, olon, olat);
 #endif
                     else if (q.mode == kHigh) quad_rows<P, kHigh, false>(q, a_col, s_t0, nrows, olon, olat);
                     else quad_rows<P, kBoth, false>(q, a_col, s_t0, nrows, olon, olat);
@@ -208,9 +216,11 @@ modis_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restri
                     const double s_t = s_t0 + m * (1.0 / P);
                     double vlon[P], vlat[P];
 #pragma unroll 1
-                    for (int k = 0; k < P; ++k)
-                        pixel_eval_slow(topA_xyz, topB, curB, curA_xyz, q.ce, q.ca,
-                                        (double)(xoff + k) / (double)P, s_t, vlon[k], vlat[k]);
+                    for (int k = 0; k < P; ++k) {
+                        const LonLat ll = pixel_eval_slow(topA_xyz, topB, curB, curA_xyz, q.ce, q.ca,
+                                                          (double)(xoff + k) / (double)P, s_t);
+                        vlon[k] = ll.lon; vlat[k] = ll.lat;
+                    }
                     store_px<P>(olon + (long long)m * kWf, vlon);
                     store_px<P>(olat + (long long)m * kWf, vlat);
                 }

@@ -24,6 +24,7 @@
 // on the CPU against the oracle.
 #pragma once
 #include <math.h>
+#include <string.h>
 #include "gtp_common.cuh"
 
 // Under nvcc these functions are device-only so that they may read __constant__ data: a
@@ -32,9 +33,11 @@
 // functions and static const doubles.
 #ifdef __CUDACC__
 #define GTP_FD __device__ __forceinline__
+#define GTP_FD_COLD __device__ __noinline__      // rarely taken paths: keep them out of the hot I-cache lines
 #define GTP_DCONST(name, value) static __constant__ double name = value
 #else
 #define GTP_FD inline
+#define GTP_FD_COLD inline
 #define GTP_DCONST(name, value) static const double name = value
 #endif
 
@@ -75,9 +78,10 @@ GTP_DCONST(kTBound, 1.4);
 GTP_DCONST(kATBound, 3.3);
 GTP_DCONST(kMaxRelHoriz, 0.01);
 GTP_DCONST(kMaxRelZ, 2.0e-3);
+GTP_DCONST(kSmallHoriz, 2.5e-3);
 GTP_DCONST(kLatSwitch, 0.8);
 
-enum QuadMode { kSlow = 0, kLow = 1, kHigh = 2, kBoth = 3 };
+enum QuadMode { kSlow = 0, kLow = 1, kHigh = 2, kBoth = 3, kLowSmall = 5 };   // kLowSmall: kLow with Quad::small
 
 // The reference's latitude switch: z < thr*R and z > -thr*R with thr = 0.8
 #define GTP_LAT_SWITCH 0.8
@@ -108,6 +112,7 @@ struct Quad {
     double a1, a2, a3, a4, a5;           // low-latitude series (degrees per w^k)
     double b1, b2, b3, b4, b5;           // high-latitude series (degrees per v^k), v = (rho-rho_A)/rho_A
     bool wrap;                           // lon may cross +-180
+    bool small;                          // low-latitude quad small enough for the shortened series
 };
 
 // ---- lean elementary functions ------------------------------------------------------------
@@ -149,10 +154,26 @@ GTP_FD double fast_sqrt(double x)
 #endif
 }
 
+// x with its sign bit flipped where `mask` has bit 63 set (an integer op instead of an FP64 one)
+GTP_FD double xor_sign(double x, unsigned long long mask)
+{
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double(__double_as_longlong(x) ^ (long long)mask);
+#else
+    unsigned long long u;
+    memcpy(&u, &x, 8); u ^= mask; memcpy(&x, &u, 8);
+    return x;
+#endif
+}
+
+struct SinCos { double s, c; };
+GTP_FD_COLD SinCos library_sincos(double x) { SinCos r; sincos(x, &r.s, &r.c); return r; }
+GTP_FD_COLD double library_asin(double x) { return asin(x); }
+
 // sin and cos of |x| <= 8 (longitudes, latitudes, zenith angles in radians)
 GTP_FD void fast_sincos(double x, double& sn, double& cs)
 {
-    if (!(fabs(x) <= 8.0)) { sincos(x, &sn, &cs); return; }    // out-of-range or NaN input: library path
+    if (!(fabs(x) <= 8.0)) { const SinCos r = library_sincos(x); sn = r.s; cs = r.c; return; }   // out-of-range / NaN: library path
     const double kf = rint(x * kTwoOverPi);
     double r = fma(-kf, kPio2Hi, x);
     r = fma(-kf, kPio2Lo, r);
@@ -172,8 +193,8 @@ GTP_FD void fast_sincos(double x, double& sn, double& cs)
     const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
     const double s0 = (quad & 1) ? cr : sr;
     const double c0 = (quad & 1) ? sr : cr;
-    sn = (quad & 2) ? -s0 : s0;
-    cs = ((quad + 1) & 2) ? -c0 : c0;
+    sn = xor_sign(s0, (unsigned long long)(quad & 2) << 62);
+    cs = xor_sign(c0, (unsigned long long)((quad + 1) & 2) << 62);
 }
 
 GTP_FD TieGeo tie_geo(double lon, double lat)
@@ -240,7 +261,7 @@ GTP_FD bool quad_exp_ali(double za, double sza, double cza, double sphi_a, doubl
     const double sdel = fma(szeta, czm, -(czeta * szm));
     const double delta = fma(sdel * (sdel * sdel), kSixth, sdel);
     double den = dphi - dz;                                          // theta_a - theta_b
-    if (dz == 0.0) den = 2.0 * (za - asin(sphi_a));                  // :61-62, symmetric tie points
+    if (dz == 0.0) den = 2.0 * (za - library_asin(sphi_a));          // :61-62, symmetric tie points
     const double inv_den = 4.0 * fast_rcp(den);
     ce = -delta * inv_den;
     const double d = (K * cphi - czeta) * ((double)km * kInv2H);
@@ -250,8 +271,11 @@ GTP_FD bool quad_exp_ali(double za, double sza, double cza, double sphi_a, doubl
 }
 
 // the same coefficients, written exactly like the reference (:52-70), library functions
-GTP_FD void quad_exp_ali_exact(double za, double zb, int km, double& ce, double& ca)
+struct ExpAli { double ce, ca; };
+
+GTP_FD_COLD ExpAli quad_exp_ali_exact(double za, double zb, int km)
 {
+    double ce, ca;
     const double phi_a = asin((GTP_RK * sin(za)) / (GTP_RK + GTP_H));
     const double phi_b = asin((GTP_RK * sin(zb)) / (GTP_RK + GTP_H));
     const double theta_a = za - phi_a, theta_b = zb - phi_b;
@@ -263,13 +287,17 @@ GTP_FD void quad_exp_ali_exact(double za, double zb, int km, double& ce, double&
     const double d = ((((GTP_RK + GTP_H) / GTP_RK) * cos(phi)) - cos(zeta)) * ((double)km / (2.0 * GTP_H));
     const double e = cos(zeta) - sqrt((cos(zeta) * cos(zeta)) - (d * d));
     ca = ((4.0 * e) * sin(zeta)) / den;
+    ExpAli r; r.ce = ce; r.ca = ca;
+    return r;
 }
 
 GTP_FD void quad_coefficients(const TieZen& a, double zb, double sphi_b, double cphi_b, int km,
                               double& ce, double& ca)
 {
-    if (!quad_exp_ali(a.za, a.sz, a.cz, a.sphi, a.cphi, zb, sphi_b, cphi_b, km, ce, ca))
-        quad_exp_ali_exact(a.za, zb, km, ce, ca);
+    if (!quad_exp_ali(a.za, a.sz, a.cz, a.sphi, a.cphi, zb, sphi_b, cphi_b, km, ce, ca)) {
+        const ExpAli r = quad_exp_ali_exact(a.za, zb, km);
+        ce = r.ce; ca = r.ca;
+    }
 }
 
 GTP_FD double absd(double x) { return fabs(x); }
@@ -283,6 +311,7 @@ GTP_FD Quad quad_setup(const TieGeo& A, const Vec3& Axyz, const Vec3& B, const V
     q.a1 = q.a2 = q.a3 = q.a4 = q.a5 = 0.0;
     q.b1 = q.b2 = q.b3 = q.b4 = q.b5 = 0.0;
     q.wrap = false;
+    q.small = false;
     q.ce = ce; q.ca = ca;
 
     const double inv_c = fast_rcp(A.cp);
@@ -321,6 +350,10 @@ GTP_FD Quad quad_setup(const TieGeo& A, const Vec3& Axyz, const Vec3& B, const V
         m *= u; q.a3 = fma(2.0, s2, 1.0) * kSixth * m;
         m *= u; q.a4 = s * fma(2.0, s2, 3.0) * 0.125 * m;
         m *= u; q.a5 = fma(s2, fma(8.0, s2, 24.0), 3.0) * k1_40 * m;
+        // shortened series (pixel_eval<kLowSmall>): 1/(1+h) to h^4, atan to t^3, asin to w^4.
+        // Dropped terms: h^5 t <= 2.4e-16 rad, t^5/5 <= 2e-14 rad = 1.1e-12 deg, a5 w^5 <= 2e-14 deg.
+        const double w2 = wmax * wmax;
+        q.small = (q.mode == kLow) && (horiz <= kSmallHoriz) && (absd(q.a5) * (w2 * w2 * wmax) <= 2e-14);
     }
     if (q.mode & kHigh) {
         // lat = sign(z) * acos(rho / R);  rho / R = c * (1 + v),  v = (rho - rho_A) / rho_A.
@@ -362,6 +395,15 @@ GTP_FD void pixel_eval(const Quad& q, const RowCoef& r, double a_col, double& lo
     const double e = fma(a, r.Ue, r.Ve);
     const double h = fma(a, r.Uh, r.Vh);
     const double w = fma(a, r.Uw, r.Vw);
+    if (MODE == kLowSmall) {
+        // t = e / (1 + h) with 1/(1+h) = 1 - h + h^2 - h^3 + h^4 (|h| <= 2.5e-3)
+        const double rcp = fma(h, fma(h, fma(h, h - 1.0, 1.0), -1.0), 1.0);
+        const double t = e * rcp;
+        const double at = fma((t * t) * t, -kThird, t);             // atan(t) = t - t^3/3
+        lon = fma(at, kRad2Deg, q.lon0);
+        lat = fma(w, fma(w, fma(w, fma(w, q.a4, q.a3), q.a2), q.a1), q.lat0);
+        return;
+    }
     // t = e / (1 + h): 1/(1+h) ~ 1 - h + h^2, one Newton step (|h| <= 0.01 -> rel. error 1e-12)
     const double g = 1.0 + h;
     double rcp = fma(h, h - 1.0, 1.0);
@@ -454,14 +496,19 @@ GTP_FD double blend(double a_scan, double a_track, double A, double B, double C,
     return (1.0 - a_track) * scan1 + a_track * scan2;
 }
 
-GTP_FD void pixel_eval_slow(const Vec3& A, const Vec3& B, const Vec3& C, const Vec3& D, double ce, double ca,
-                            double s_s, double s_t, double& lon, double& lat)
+struct LonLat { double lon, lat; };
+
+// by-value arguments on purpose: a noinline call with reference arguments would force the
+// caller's tie points into local memory
+GTP_FD_COLD LonLat pixel_eval_slow(Vec3 A, Vec3 B, Vec3 C, Vec3 D, double ce, double ca, double s_s, double s_t)
 {
     const double a_scan = (s_s + (s_s * (1.0 - s_s)) * ce) + (s_t * (1.0 - s_t)) * ca;
     const double x = blend(a_scan, s_t, A.x, B.x, C.x, D.x);
     const double y = blend(a_scan, s_t, A.y, B.y, C.y, D.y);
     const double z = blend(a_scan, s_t, A.z, B.z, C.z, D.z);
-    xyz_to_lonlat(x, y, z, lon, lat);
+    LonLat r;
+    xyz_to_lonlat(x, y, z, r.lon, r.lat);
+    return r;
 }
 
 // y[j] of _get_coords_1km (a4): 0.5 + j - h on the first h rows of the scan, continuing

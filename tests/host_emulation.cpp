@@ -32,6 +32,7 @@ static void run(const double* lon, const double* lat, const double* satz, long n
                 }
                 const Quad q = quad_setup(A, Ax, B, C, D, ce, cal);
                 mode_counts[q.mode]++;
+                if (q.small) mode_counts[4]++;
                 const int j0 = (qr == 0) ? 0 : qr * P + H;
                 const int j1 = (qr == L - 2) ? N : (qr + 1) * P + H;
                 for (int j = j0; j < j1; ++j) {
@@ -41,11 +42,12 @@ static void run(const double* lon, const double* lat, const double* satz, long n
                         const double s_s = (double)(xoff + k) / (double)P;
                         double lo, la;
                         const double a_col = fma(s_s * (1.0 - s_s), q.ce, s_s);
-                        if (q.mode == kSlow) pixel_eval_slow(Ax, B, C, D, q.ce, q.ca, s_s, s_t, lo, la);
+                        if (q.mode == kSlow) { const LonLat ll = pixel_eval_slow(Ax, B, C, D, q.ce, q.ca, s_s, s_t); lo = ll.lon; la = ll.lat; }
                         else if (q.wrap) pixel_eval<kBoth, true>(q, rc, a_col, lo, la);
 #ifdef GTP_FAST_MIXED
                         else if (q.mode == kLow) pixel_eval_low_mixed<false>(q, quad_float_terms(q), rc, a_col, lo, la);
 #else
+                        else if (q.small) pixel_eval<kLowSmall, false>(q, rc, a_col, lo, la);
                         else if (q.mode == kLow) pixel_eval<kLow, false>(q, rc, a_col, lo, la);
 #endif
                         else if (q.mode == kHigh) pixel_eval<kHigh, false>(q, rc, a_col, lo, la);
@@ -62,7 +64,7 @@ static void run(const double* lon, const double* lat, const double* satz, long n
 extern "C" int gtp_emul_simple_fast_f64(const double* lon, const double* lat, long n_scans, int fine_res,
                                         double* out_lon, double* out_lat, long* mode_counts)
 {
-    for (int k = 0; k < 4; ++k) mode_counts[k] = 0;
+    for (int k = 0; k < 5; ++k) mode_counts[k] = 0;
     if (fine_res == 250) run<4>(lon, lat, nullptr, n_scans, out_lon, out_lat, mode_counts, true);
     else if (fine_res == 500) run<2>(lon, lat, nullptr, n_scans, out_lon, out_lat, mode_counts, true);
     else return 1;
@@ -72,7 +74,7 @@ extern "C" int gtp_emul_simple_fast_f64(const double* lon, const double* lat, lo
 extern "C" int gtp_emul_cviirs_fast_f64(const double* lon, const double* lat, const double* satz, long n_scans,
                                         int fine_res, double* out_lon, double* out_lat, long* mode_counts)
 {
-    for (int k = 0; k < 4; ++k) mode_counts[k] = 0;
+    for (int k = 0; k < 5; ++k) mode_counts[k] = 0;
     if (fine_res == 250) run<4>(lon, lat, satz, n_scans, out_lon, out_lat, mode_counts);
     else if (fine_res == 500) run<2>(lon, lat, satz, n_scans, out_lon, out_lat, mode_counts);
     else return 1;

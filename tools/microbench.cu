@@ -2,6 +2,8 @@
 // (FP64 FMA, FP32 FMA, MUFU, F2F conversions, 64-bit shuffles) and a plain HBM write/copy rate.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/microbench tools/microbench.cu
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <cuda_runtime.h>
 
 #define ITERS 4096
@@ -73,8 +75,48 @@ void run_pipe(const char* name, int sms, double clock_ghz, double ops_per_iter)
     cudaFree(out);
 }
 
-int main()
+// `microbench loop <op> <seconds>`: keep one pipe (or the HBM write path) busy for a while so that
+// tools/power_probe.py can read the sustained clock and power through NVML.
+template <int OP>
+void loop_pipe(int sms, double seconds)
 {
+    double* out; cudaMalloc(&out, 8);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    float ms = 0; long launches = 0;
+    while (ms < seconds * 1e3) {
+        for (int i = 0; i < 16; ++i) pipe_kernel<OP><<<sms * 4, 512>>>(out, 1.0);
+        launches += 16;
+        cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
+    }
+    double ops = (double)launches * sms * 4 * 512 * ITERS * ILP * (OP == 8 ? 4 : 1);
+    printf("loop op %d: %.1f Gop/s over %.2f s\n", OP, ops / ms * 1e-6, ms * 1e-3);
+}
+
+void loop_write(int sms, double seconds)
+{
+    size_t bytes = 4ull << 30; void* a; cudaMalloc(&a, bytes);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    float ms = 0; long launches = 0;
+    while (ms < seconds * 1e3) {
+        for (int i = 0; i < 4; ++i) write_kernel<<<sms * 8, 512>>>((double4*)a, bytes / 32);
+        launches += 4;
+        cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
+    }
+    printf("loop write: %.1f GB/s over %.2f s\n", (double)launches * bytes / ms * 1e-6, ms * 1e-3);
+}
+
+int main(int argc, char** argv)
+{
+    if (argc == 4 && !strcmp(argv[1], "loop")) {
+        cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+        const double seconds = atof(argv[3]);
+        if (!strcmp(argv[2], "dfma")) loop_pipe<8>(p.multiProcessorCount, seconds);
+        else if (!strcmp(argv[2], "ffma")) loop_pipe<1>(p.multiProcessorCount, seconds);
+        else if (!strcmp(argv[2], "write")) loop_write(p.multiProcessorCount, seconds);
+        return 0;
+    }
     cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
     int clk_khz = 0; cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
     double ghz = clk_khz * 1e-6;
