@@ -76,6 +76,8 @@ def parse_args():
                     help="auto = what the public API runs; generic = force the rounding-faithful kernel")
     ap.add_argument("--sustained-seconds", type=float, default=1.0,
                     help="extra load before the `sustained` measurement (0 = skip it)")
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="do not pin each rank to the CPU cores local to its GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -295,6 +297,7 @@ def run_b200_arm(args, dtype):
         raise SystemExit("bench.py needs a CUDA device: geotiepoints_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    bound_cpus = None if args.no_numa_bind else _capi.bind_host_thread_to_gpu(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
@@ -315,8 +318,8 @@ def run_b200_arm(args, dtype):
     out_lat = torch.empty_like(out_lon)
     lib = _capi.lib()
     suffix = "f64" if dtype == np.float64 else "f32"
-    generic = args.kernel == "generic" and suffix == "f64"
-    fn = getattr(lib, f"gtp_{cfg['kind']}_interp_" + ("generic_f64" if generic else suffix))
+    generic = args.kernel == "generic" and (suffix == "f64" or cfg["kind"] == "cviirs")
+    fn = getattr(lib, f"gtp_{cfg['kind']}_interp_" + (("generic_" + suffix) if generic else suffix))
     stream = torch.cuda.current_stream(device)
     if cfg["kind"] == "cviirs":
         scalars = (cfg["coarse"], cfg["fine"], cfg["width"])
@@ -447,6 +450,7 @@ def run_b200_arm(args, dtype):
                "h2d_bytes_per_step": int(cfg["n_in"] * rows * cfg["tie_cols"] * itemsize),
                "d2h_bytes_per_step": int(2 * e2e_px * itemsize),
                "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
+               "host_cpus_bound_to_gpu": len(bound_cpus) if bound_cpus else None,
                "sample": f"{ge} granules per GPU per call through the public numpy API "
                          f"({'geotiepoints_b200.modisinterpolator.modis_1km_to_250m' if headline else args.config}), "
                          f"pinned host inputs, pinned host outputs",

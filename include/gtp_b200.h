@@ -72,13 +72,15 @@ int gtp_simple_interp_f32(const float* lon, const float* lat, int64_t n_scans, i
 int gtp_simple_interp_f64(const double* lon, const double* lat, int64_t n_scans, int64_t width, int res_factor,
                           double* out_lon, double* out_lat, int device, void* stream);
 
-/* Same as gtp_cviirs_interp_f64 but always through the rounding-faithful generic
- * kernel (never the anchor-relative fast path); used by tests and by the bench to
- * show the two side by side. */
+/* Same operators, but always through the rounding-faithful generic kernels (never the
+ * anchor-relative fast paths); used by tests and by the bench to show the two side by side. */
 int gtp_cviirs_interp_generic_f64(const double* lon, const double* lat, const double* satz, int64_t n_scans,
                                   int coarse_res, int fine_res, int coarse_width,
                                   double* out_lon, double* out_lat, int device, void* stream);
 
+int gtp_cviirs_interp_generic_f32(const float* lon, const float* lat, const float* satz, int64_t n_scans,
+                                  int coarse_res, int fine_res, int coarse_width,
+                                  float* out_lon, float* out_lat, int device, void* stream);
 int gtp_simple_interp_generic_f64(const double* lon, const double* lat, int64_t n_scans, int64_t width, int res_factor,
                                   double* out_lon, double* out_lat, int device, void* stream);
 

@@ -42,6 +42,7 @@ for _suf in ("f32", "f64"):
     SIGNATURES[f"gtp_simple_interp_host_{_suf}"] = (_int, [_vp, _vp, _i64, _i64, _int, _vp, _vp, _int])
 SIGNATURES["gtp_cviirs_interp_generic_f64"] = SIGNATURES["gtp_cviirs_interp_f64"]
 SIGNATURES["gtp_simple_interp_generic_f64"] = SIGNATURES["gtp_simple_interp_f64"]
+SIGNATURES["gtp_cviirs_interp_generic_f32"] = SIGNATURES["gtp_cviirs_interp_f32"]
 
 
 class GtpError(RuntimeError):
@@ -151,3 +152,25 @@ def device_count():
 
 def launch_count():
     return int(lib().gtp_launch_count())
+
+
+def bind_host_thread_to_gpu(device_index):
+    """Pin the calling process to the CPU cores NVML reports as local to ``device_index`` so that
+    page-locked staging buffers are first-touched on the NUMA node next to that GPU (a D2H copy
+    into the far socket can run several times slower than one into the near socket).
+    Returns the CPU set applied, or None when NVML / sched_setaffinity is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        n_words = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, n_words)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None

@@ -70,7 +70,10 @@ int cviirs_device(const T* lon, const T* lat, const T* satz, int64_t n_scans, in
         else
             e = gtp_launch_cviirs_generic<T>(lon, lat, satz, out_lon, out_lat, n_scans, cfg, (cudaStream_t)stream);
     } else {
-        e = gtp_launch_cviirs_generic<T>(lon, lat, satz, out_lon, out_lat, n_scans, cfg, (cudaStream_t)stream);
+        if (allow_fast && gtp_cviirs_fast_f32_supported(cfg))
+            e = gtp_launch_cviirs_fast_f32(lon, lat, satz, out_lon, out_lat, n_scans, cfg, (cudaStream_t)stream);
+        else
+            e = gtp_launch_cviirs_generic<T>(lon, lat, satz, out_lon, out_lat, n_scans, cfg, (cudaStream_t)stream);
     }
     if (e != cudaSuccess) return cuda_fail(e, "cviirs launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -239,6 +242,11 @@ int gtp_cviirs_interp_generic_f64(const double* lon, const double* lat, const do
                                   int coarse_res, int fine_res, int coarse_width,
                                   double* out_lon, double* out_lat, int device, void* stream)
 { return cviirs_device<double>(lon, lat, satz, n_scans, coarse_res, fine_res, coarse_width, out_lon, out_lat, device, stream, false); }
+
+int gtp_cviirs_interp_generic_f32(const float* lon, const float* lat, const float* satz, int64_t n_scans,
+                                  int coarse_res, int fine_res, int coarse_width,
+                                  float* out_lon, float* out_lat, int device, void* stream)
+{ return cviirs_device<float>(lon, lat, satz, n_scans, coarse_res, fine_res, coarse_width, out_lon, out_lat, device, stream, false); }
 
 int gtp_simple_interp_f32(const float* lon, const float* lat, int64_t n_scans, int64_t width, int res_factor,
                           float* out_lon, float* out_lat, int device, void* stream)

@@ -1,0 +1,207 @@
+// gtp_fast_f32.cu - float32 CVIIRS 1 km -> 250 m / 500 m fast path for sm_100a.
+//
+// Same work decomposition as gtp_fast.cu (one thread per tie-point quad column, ten tie rows
+// top to bottom, right neighbour by warp shuffle, cp.async prefetch of the next tie row, one
+// 128-bit / 64-bit streaming store per lane, fine row and output array); the math is
+// gtp_fast_f32_math.cuh: the reference's float32 rounding points for everything up to the fine
+// Cartesian coordinates, then the anchor-relative double-precision back-transform.
+// Compiled with -fmad=false: the rounding-faithful part must not be contracted; the series use
+// explicit fma().
+#include <cuda_runtime.h>
+#include "gtp_kernels.h"
+#include "gtp_fast_f32_math.cuh"
+
+namespace {
+
+using namespace gtpfast32;
+
+constexpr int kW = 1354;
+constexpr int kL = 10;
+constexpr int kQuadColsPerWarp = 31;
+constexpr int kWarpsPerScan = (kW + kQuadColsPerWarp - 1) / kQuadColsPerWarp;   // 44
+constexpr int kThreads = 128;
+constexpr unsigned kFull = 0xffffffffu;
+
+template <int P>
+__device__ __forceinline__ void store_px(float* p, const float (&v)[P]);
+
+template <>
+__device__ __forceinline__ void store_px<4>(float* p, const float (&v)[4])
+{
+    asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+}
+
+template <>
+__device__ __forceinline__ void store_px<2>(float* p, const float (&v)[2])
+{
+    asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v[0]), "f"(v[1]) : "memory");
+}
+
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src)
+{
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int P, int MODE, bool WRAP>
+__device__ __forceinline__ void quad_rows(const QuadF32& q, const float (&s_s)[P], const double (&k1d)[P],
+                                          float s_t0, int nrows, float* olon, float* olat)
+{
+    constexpr long long kPitch = (long long)kW * P;
+    float s_t = s_t0;
+#pragma unroll 1
+    for (int m = 0; m < nrows; ++m) {
+        const RowF32 rc = row_setup_f32(q, s_t);
+        float vlon[P], vlat[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+            float v[3];
+            blend_f32(q, rc, s_s[k], k1d[k], v);
+            if (MODE == kSlow) {
+                const LonLatF ll = backtransform_f32_slow(v[0], v[1], v[2]);
+                vlon[k] = ll.lon; vlat[k] = ll.lat;
+            } else {
+                backtransform_f32<MODE, WRAP>(q, v, vlon[k], vlat[k]);
+            }
+        }
+        store_px<P>(olon, vlon);
+        store_px<P>(olat, vlat);
+        olon += kPitch; olat += kPitch;
+        s_t += 1.0f / P;             // exact: multiples of 1/8
+    }
+}
+
+template <int P>
+__global__ void __launch_bounds__(kThreads, 4)
+cviirs_fast_1km_f32_kernel(const float* __restrict__ lon, const float* __restrict__ lat,
+                           const float* __restrict__ satz, float* __restrict__ out_lon,
+                           float* __restrict__ out_lat, long long n_scans)
+{
+    constexpr int kWf = kW * P;
+    constexpr int kN = kL * P;
+    constexpr int kHalf = P / 2;
+
+    const long long warp_global = (blockIdx.x * (long long)kThreads + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long scan = warp_global / kWarpsPerScan;
+    if (scan >= n_scans) return;
+    const int w = (int)(warp_global - scan * kWarpsPerScan);
+    const int c = w * kQuadColsPerWarp + lane;
+    const int tc = min(c, kW - 1);
+    const bool extra = (c == kW - 1);      // the lane of tie column 1353: pixels right of the last quad
+    const bool quad_lane = (lane < kQuadColsPerWarp) && (c <= kW - 2);
+    const bool active = quad_lane || extra;
+    const int quad_col = extra ? kW - 2 : c;
+    const int xoff = extra ? P : 0;
+
+    const long long scan_base = scan * (long long)(kL * kW);
+    const float* plon = lon + scan_base + tc;
+    const float* plat = lat + scan_base + tc;
+    const float* psatz = satz + scan_base + tc;
+    float* olon = out_lon + scan * (long long)kN * kWf + (long long)quad_col * P + xoff;
+    float* olat = out_lat + scan * (long long)kN * kWf + (long long)quad_col * P + xoff;
+
+    float s_s[P];
+    double k1d[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+        s_s[k] = (float)(xoff + k) / (float)P;                      // x[i] / f, a float division (:341)
+        k1d[k] = mul_rn((double)s_s[k], add_rn(1.0, -(double)s_s[k]));
+    }
+
+    TieGeoF topA;
+    Vec3F topB;
+    float top_ce = 0.0f, top_ca = 0.0f;
+    __shared__ float stage[2][3][kThreads];
+    cp_async4(&stage[0][0][threadIdx.x], plon);
+    cp_async4(&stage[0][1][threadIdx.x], plat);
+    cp_async4(&stage[0][2][threadIdx.x], psatz);
+    cp_async_commit();
+
+#pragma unroll 1
+    for (int r = 0; r < kL; ++r) {
+        cp_async_wait_all();
+        const float clon = stage[r & 1][0][threadIdx.x], clat = stage[r & 1][1][threadIdx.x],
+                    csatz = stage[r & 1][2][threadIdx.x];
+        if (r + 1 < kL) {
+            plon += kW; plat += kW; psatz += kW;
+            cp_async4(&stage[(r + 1) & 1][0][threadIdx.x], plon);
+            cp_async4(&stage[(r + 1) & 1][1][threadIdx.x], plat);
+            cp_async4(&stage[(r + 1) & 1][2][threadIdx.x], psatz);
+            cp_async_commit();
+        }
+        const TieGeoF own = tie_geo_f32(clon, clat);
+        TieGeoF curA = own;
+        Vec3F curB;
+        curB.x = __shfl_down_sync(kFull, own.x, 1);
+        curB.y = __shfl_down_sync(kFull, own.y, 1);
+        curB.z = __shfl_down_sync(kFull, own.z, 1);
+        if (extra) {                 // A = tie column 1352 (recomputed by this one lane), B = own column 1353
+            const long long o = scan_base + (long long)r * kW + (kW - 2);
+            curA = tie_geo_f32(__ldg(lon + o), __ldg(lat + o));
+            curB.x = own.x; curB.y = own.y; curB.z = own.z;
+        }
+
+        if (r > 0 && active) {
+            const int qr = r - 1;
+            const int nrows = P + ((qr == 0 || qr == kL - 2) ? kHalf : 0);
+            const float s_t0 = ((qr == 0) ? (0.5f - kHalf) : 0.5f) / P;     // y[j] / f (:342)
+            Vec3F curAv; curAv.x = curA.x; curAv.y = curA.y; curAv.z = curA.z;
+            const QuadF32 q = quad_setup_f32(topA, topB, curB, curAv, top_ce, top_ca);
+            if (q.mode == kSlow) quad_rows<P, kSlow, false>(q, s_s, k1d, s_t0, nrows, olon, olat);
+            else if (q.wrap) quad_rows<P, kBoth, true>(q, s_s, k1d, s_t0, nrows, olon, olat);
+            else if (q.mode == kLow) quad_rows<P, kLow, false>(q, s_s, k1d, s_t0, nrows, olon, olat);
+            else if (q.mode == kHigh) quad_rows<P, kHigh, false>(q, s_s, k1d, s_t0, nrows, olon, olat);
+            else quad_rows<P, kBoth, false>(q, s_s, k1d, s_t0, nrows, olon, olat);
+            olon += (long long)nrows * kWf;
+            olat += (long long)nrows * kWf;
+        }
+        topA = curA;
+        topB = curB;
+
+        if (r + 1 < kL) {
+            // expansion / alignment of the quad row below this tie row (upper corners only, :307-308)
+            const TieZenF zen = tie_zen_f32(csatz);
+            float phi_b = __shfl_down_sync(kFull, zen.phi, 1);
+            float theta_b = __shfl_down_sync(kFull, zen.theta, 1);
+            TieZenF za = zen;
+            if (extra) {
+                za = tie_zen_f32(__ldg(satz + scan_base + (long long)r * kW + (kW - 2)));
+                phi_b = zen.phi; theta_b = zen.theta;
+            }
+            quad_exp_ali_f32(za, phi_b, theta_b, 1, top_ce, top_ca);
+        }
+    }
+}
+
+template <int P>
+cudaError_t launch(const float* lon, const float* lat, const float* satz, float* out_lon, float* out_lat,
+                   long long n_scans, cudaStream_t stream)
+{
+    const long long warps = n_scans * kWarpsPerScan;
+    const long long blocks = (warps * 32 + kThreads - 1) / kThreads;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    cviirs_fast_1km_f32_kernel<P><<<(unsigned)blocks, kThreads, 0, stream>>>(lon, lat, satz, out_lon, out_lat, n_scans);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+bool gtp_cviirs_fast_f32_supported(const CviirsCfg& cfg)
+{
+    return cfg.km == 1 && (cfg.p == 4 || cfg.p == 2);
+}
+
+cudaError_t gtp_launch_cviirs_fast_f32(const float* lon, const float* lat, const float* satz,
+                                       float* out_lon, float* out_lat,
+                                       long long n_scans, const CviirsCfg& cfg, cudaStream_t stream)
+{
+    if (n_scans <= 0) return cudaSuccess;
+    const uintptr_t align = (cfg.p == 4) ? 16 : 8;       // 128-bit / 64-bit stores; the row pitch already is
+    if (((uintptr_t)out_lon | (uintptr_t)out_lat) & (align - 1))
+        return gtp_launch_cviirs_generic<float>(lon, lat, satz, out_lon, out_lat, n_scans, cfg, stream);
+    return cfg.p == 4 ? launch<4>(lon, lat, satz, out_lon, out_lat, n_scans, stream)
+                      : launch<2>(lon, lat, satz, out_lon, out_lat, n_scans, stream);
+}

@@ -1,0 +1,274 @@
+// gtp_fast_f32_math.cuh - float32 CVIIRS 1 km fast path: rounding-faithful blend, anchor-relative
+// back-transform.
+//
+// The float32 specialisation of the reference stores everything in float but evaluates every
+// expression that holds a double literal or a libm call in double and rounds to float at the
+// assignment (SURVEY.md 8a "precision model", read off the C Cython generates).  Its fine
+// Cartesian coordinates are therefore float32 (0.25-0.5 m granularity) BEFORE the back-transform,
+// and a result within 1e-5 deg of the reference has to reproduce those rounding points, not just
+// the formulas.  So this path
+//   * computes the tie points, the expansion/alignment coefficients, a_scan and the three
+//     bilinear blends with exactly the reference's float/double mix (explicit conversions,
+//     plain * and + only; the translation unit is compiled with -fmad=false), and
+//   * back-transforms the float32 xyz (promoted to double, as the reference does,
+//     _modis_utils.pyx:51-57) with the anchor-relative series of gtp_fast_math.cuh around the
+//     FLOAT32-ROUNDED corner A of the quad: two inverse-trig calls, a sqrt and two divisions per
+//     pixel become ~25 FMAs, accurate to ~1e-13 deg before the final rounding to float32.
+// Per pixel that is ~28 float<->double conversions (16/clk/SM on B200) and ~45 FP64 instructions,
+// against ~370 FP64-pipe slots of the rounding-faithful kernel in gtp_generic.cu.
+#pragma once
+#include "gtp_fast_math.cuh"
+
+namespace gtpfast32 {
+
+using namespace gtpfast;
+
+GTP_DCONST(kLatSwitchF32, 0.800000011920928955078125);     // (double)0.8f, _modis_utils.pyx:48
+
+// No-FMA double arithmetic: the reference is built for baseline x86-64 (no contraction).
+#ifdef __CUDA_ARCH__
+GTP_FD double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+GTP_FD double add_rn(double a, double b) { return __dadd_rn(a, b); }
+GTP_FD float fmul_rn(float a, float b) { return __fmul_rn(a, b); }
+GTP_FD float fsub_rn(float a, float b) { return __fsub_rn(a, b); }
+GTP_FD float fadd_rn(float a, float b) { return __fadd_rn(a, b); }
+#else
+GTP_FD double mul_rn(double a, double b) { volatile double r = a * b; return r; }
+GTP_FD double add_rn(double a, double b) { volatile double r = a + b; return r; }
+GTP_FD float fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+GTP_FD float fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+GTP_FD float fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+#endif
+
+struct TieGeoF {           // geometry of one float32 tie point
+    float x, y, z;         // lonlat2xyz, rounded to float (_modis_utils.pyx:38-40)
+    double lam, phi;       // (double) of the float32 radians the reference feeds to sin/cos
+    double sl, cl, sp, cp; // their sines / cosines (double)
+};
+
+struct Vec3F { float x, y, z; };
+
+struct TieZenF { float za, phi, theta; };   // :52-57 rounded to float
+
+GTP_FD TieGeoF tie_geo_f32(float lon, float lat)
+{
+    TieGeoF t;
+    const float lon_rad = (float)mul_rn((double)lon, kDeg2Rad);      // deg2rad, rounded to float (:76-77)
+    const float lat_rad = (float)mul_rn((double)lat, kDeg2Rad);
+    t.lam = (double)lon_rad; t.phi = (double)lat_rad;
+    fast_sincos(t.lam, t.sl, t.cl);
+    fast_sincos(t.phi, t.sp, t.cp);
+    const double rc = mul_rn(kEarthR, t.cp);
+    t.x = (float)mul_rn(rc, t.cl);
+    t.y = (float)mul_rn(rc, t.sl);
+    t.z = (float)mul_rn(kEarthR, t.sp);
+    return t;
+}
+
+GTP_FD TieZenF tie_zen_f32(float satz)
+{
+    TieZenF t;
+    t.za = (float)mul_rn((double)satz, kDeg2Rad);
+    double s, c;
+    fast_sincos((double)t.za, s, c);
+    t.phi = (float)asin(mul_rn(GTP_RK, s) / (GTP_RK + GTP_H));       // :74
+    t.theta = fsub_rn(t.za, t.phi);                                  // :78
+    return t;
+}
+
+// _compute_expansion_alignment for one quad, float32 rounding points (:41-70)
+GTP_FD void quad_exp_ali_f32(const TieZenF& a, float phi_b, float theta_b, int km, float& c_exp, float& c_ali)
+{
+    const float phi = (float)((double)fadd_rn(a.phi, phi_b) / 2.0);
+    double sphi, cphi;
+    fast_sincos((double)phi, sphi, cphi);
+    const float zeta = (float)asin(mul_rn(GTP_RK + GTP_H, sphi) / GTP_RK);
+    const float theta = fsub_rn(zeta, phi);
+    const float den = (a.theta == theta_b) ? (float)mul_rn((double)a.theta, 2.0) : fsub_rn(a.theta, theta_b);
+    c_exp = (float)mul_rn(4.0, add_rn((double)fadd_rn(a.theta, theta_b) / 2.0, -(double)theta) / (double)den);
+    const float sin_beta_2 = (float)((double)km / (2.0 * GTP_H));
+    double szeta, czeta;
+    fast_sincos((double)zeta, szeta, czeta);
+    const float d = (float)mul_rn(add_rn(mul_rn((GTP_RK + GTP_H) / GTP_RK, cphi), -czeta), (double)sin_beta_2);
+    const float dd = fmul_rn(d, d);                                   // powf(d, 2)
+    const float e = (float)add_rn(czeta, -sqrt(add_rn(mul_rn(czeta, czeta), -(double)dd)));
+    c_ali = (float)(mul_rn(mul_rn(4.0, (double)e), szeta) / (double)den);
+}
+
+// Everything the pixels of one quad need.
+struct QuadF32 {
+    int mode;
+    bool wrap;
+    double A[3], D[3];                  // corners A and D widened to double (exact)
+    float B[3], C[3];                   // corners B and C stay float: a * B is a float product (:396-397)
+    float ce, ca;
+    double ue0, ue1, uh0, uh1;          // rows of the local frame at A', pre-scaled by 1 / rho_A'
+    double lon0;                        // longitude of A', degrees
+    double lat0_low, lat0_high;         // latitude of A' by the low / high latitude formula, degrees
+    double s0;                          // z_A' / R
+    double a1, a2, a3, a4, a5;          // series of asin((z_A' + dz)/R) around z_A'/R, degrees
+    double b1, b2, b3, b4, b5;          // series of sign(z) acos(rho/R) around rho_A'/R, degrees
+};
+
+GTP_FD QuadF32 quad_setup_f32(const TieGeoF& A, const Vec3F& B, const Vec3F& C, const Vec3F& D, float ce, float ca)
+{
+    QuadF32 q;
+    q.ce = ce; q.ca = ca;
+    q.wrap = false;
+    q.a1 = q.a2 = q.a3 = q.a4 = q.a5 = 0.0;
+    q.b1 = q.b2 = q.b3 = q.b4 = q.b5 = 0.0;
+    q.lat0_low = q.lat0_high = 0.0;
+    q.A[0] = (double)A.x; q.A[1] = (double)A.y; q.A[2] = (double)A.z;
+    q.D[0] = (double)D.x; q.D[1] = (double)D.y; q.D[2] = (double)D.z;
+    q.B[0] = B.x; q.B[1] = B.y; q.B[2] = B.z;
+    q.C[0] = C.x; q.C[1] = C.y; q.C[2] = C.z;
+
+    // local frame at A' = the float32-rounded corner A (what the reference back-transforms)
+    const double rho = fast_sqrt(fma(q.A[0], q.A[0], q.A[1] * q.A[1]));
+    const double inv_rho = fast_rcp(rho);
+    const double cl = q.A[0] * inv_rho, sl = q.A[1] * inv_rho;
+    q.ue0 = -sl * inv_rho; q.ue1 = cl * inv_rho;
+    q.uh0 = cl * inv_rho; q.uh1 = sl * inv_rho;
+    // lon(A') = lambda + asin(sin(lon(A') - lambda)): A' is within half a float32 ulp of the exact point
+    q.lon0 = (A.lam + fma(A.cl, sl, -(A.sl * cl))) * kRad2Deg;
+    q.s0 = q.A[2] * kInvEarthR;
+
+    // displacement bounds over the quad (same role as in gtp_fast_math.cuh)
+    const double Px = (double)B.x - q.A[0], Py = (double)B.y - q.A[1], Pz = (double)B.z - q.A[2];
+    const double Qx = q.D[0] - q.A[0], Qy = q.D[1] - q.A[1], Qz = q.D[2] - q.A[2];
+    const double Sx = ((double)C.x - q.D[0]) - Px, Sy = ((double)C.y - q.D[1]) - Py, Sz = ((double)C.z - q.D[2]) - Pz;
+    const double Pe = fma(q.ue0, Px, q.ue1 * Py), Ph = fma(q.uh0, Px, q.uh1 * Py);
+    const double Qe = fma(q.ue0, Qx, q.ue1 * Qy), Qh = fma(q.uh0, Qx, q.uh1 * Qy);
+    const double Se = fma(q.ue0, Sx, q.ue1 * Sy), Sh = fma(q.uh0, Sx, q.uh1 * Sy);
+    // 2 m of slack for the float32 roundings of the fine xyz themselves
+    const double horiz = kABound * (absd(Pe) + absd(Ph)) + kTBound * (absd(Qe) + absd(Qh))
+                         + kATBound * (absd(Se) + absd(Sh)) + 2.0 * inv_rho;
+    const double wmax = (kABound * absd(Pz) + kTBound * absd(Qz) + kATBound * absd(Sz) + 2.0) * kInvEarthR;
+    const bool ok = (horiz <= kMaxRelHoriz) && (wmax <= kMaxRelZ)
+                    && (absd((double)ce) <= 1.0) && (absd((double)ca) <= 0.5) && (A.cp > 1e-6);
+    if (!ok) { q.mode = kSlow; return q; }
+
+    const double zr_lo = q.s0 - wmax, zr_hi = q.s0 + wmax;
+    const double margin = 1e-9;
+    if (zr_hi < kLatSwitchF32 - margin && zr_lo > -kLatSwitchF32 + margin) q.mode = kLow;
+    else if (zr_lo > kLatSwitchF32 + margin || zr_hi < -kLatSwitchF32 - margin) q.mode = kHigh;
+    else q.mode = kBoth;
+    q.wrap = (absd(q.lon0) + 1.05 * horiz * kRad2Deg) >= 180.0;
+
+    if (q.mode & kLow) {
+        // asin around s0 = z_A'/R with c0 = sqrt(1 - s0^2); asin(s0) = phi + asin(s0 cos phi - c0 sin phi)
+        const double s = q.s0, s2 = s * s;
+        const double c0 = fast_sqrt(fma(-s, s, 1.0));
+        const double inv_c = fast_rcp(c0), u = inv_c * inv_c;
+        q.lat0_low = (A.phi + fma(s, A.cp, -(c0 * A.sp))) * kRad2Deg;
+        double m = inv_c * kRad2Deg;
+        q.a1 = m;
+        m *= u; q.a2 = 0.5 * s * m;
+        m *= u; q.a3 = fma(2.0, s2, 1.0) * kSixth * m;
+        m *= u; q.a4 = s * fma(2.0, s2, 3.0) * 0.125 * m;
+        m *= u; q.a5 = fma(s2, fma(8.0, s2, 24.0), 3.0) * k1_40 * m;
+    }
+    if (q.mode & kHigh) {
+        // sign(z) acos(rho/R) around c = rho_A'/R with s' = sqrt(1 - c^2):
+        // acos(c) = |phi| - asin(|sin phi| c - cos phi s')
+        const double c = rho * kInvEarthR, c2 = c * c;
+        const double sa = fast_sqrt(fma(-c, c, 1.0));
+        const double inv_s = fast_rcp(sa), u = inv_s * inv_s;
+        const double sign = (q.A[2] < 0.0) ? -1.0 : 1.0;
+        q.lat0_high = sign * (absd(A.phi) - fma(absd(A.sp), c, -(A.cp * sa))) * kRad2Deg;
+        double m = inv_s * c * (-sign * kRad2Deg);
+        q.b1 = m;
+        m *= u * c; q.b2 = 0.5 * c * m;
+        m *= u * c; q.b3 = fma(2.0, c2, 1.0) * kSixth * m;
+        m *= u * c; q.b4 = c * fma(2.0, c2, 3.0) * 0.125 * m;
+        m *= u * c; q.b5 = fma(c2, fma(8.0, c2, 24.0), 3.0) * k1_40 * m;
+    }
+    return q;
+}
+
+// per (quad, fine row): a_track = s_t (:343) and the s_t-dependent part of a_scan (:344)
+struct RowF32 {
+    float s_t;
+    double omt;          // 1.0 - a_track
+    double row_ca;       // (s_t (1 - s_t)) c_ali
+};
+
+GTP_FD RowF32 row_setup_f32(const QuadF32& q, float s_t)
+{
+    RowF32 r;
+    r.s_t = s_t;
+    r.omt = add_rn(1.0, -(double)s_t);
+    r.row_ca = mul_rn(mul_rn((double)s_t, r.omt), (double)q.ca);
+    return r;
+}
+
+// The float32 fine xyz of one pixel, with the reference's rounding points (:344, :396-398).
+// k1d = (double)s_s * (1.0 - (double)s_s)
+GTP_FD void blend_f32(const QuadF32& q, const RowF32& r, float s_s, double k1d, float (&v)[3])
+{
+    const double a_d = add_rn(add_rn((double)s_s, mul_rn(k1d, (double)q.ce)), r.row_ca);
+    const float a = (float)a_d;
+    const double oma = add_rn(1.0, -(double)a);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float s1 = (float)add_rn(mul_rn(oma, q.A[k]), (double)fmul_rn(a, q.B[k]));
+        const float s2 = (float)add_rn(mul_rn(oma, q.D[k]), (double)fmul_rn(a, q.C[k]));
+        v[k] = (float)add_rn(mul_rn(r.omt, (double)s1), (double)fmul_rn(r.s_t, s2));
+    }
+}
+
+// xyz2lonlat of the float32 xyz, anchor-relative in double, result rounded to float (:51-65)
+template <int MODE, bool WRAP>
+GTP_FD void backtransform_f32(const QuadF32& q, const float (&v)[3], float& lon, float& lat)
+{
+    const double zd = (double)v[2];
+    const double dx = (double)v[0] - q.A[0], dy = (double)v[1] - q.A[1], dz = zd - q.A[2];
+    const double e = fma(q.ue0, dx, q.ue1 * dy);
+    const double h = fma(q.uh0, dx, q.uh1 * dy);
+    const double w = dz * kInvEarthR;
+    const double g = 1.0 + h;
+    double rcp = fma(h, h - 1.0, 1.0);
+    rcp = fma(rcp, fma(-g, rcp, 1.0), rcp);
+    const double t = e * rcp;
+    const double t2 = t * t;
+    const double at = fma(t * t2, fma(t2, 0.2, -kThird), t);
+    double lo = fma(at, kRad2Deg, q.lon0);
+    if (WRAP) {
+        if (lo > 180.0) lo -= 360.0;
+        else if (lo < -180.0) lo += 360.0;
+    }
+    lon = (float)lo;
+    double la_low = 0.0, la_high = 0.0;
+    if (MODE & kLow)
+        la_low = fma(w, fma(w, fma(w, fma(w, fma(w, q.a5, q.a4), q.a3), q.a2), q.a1), q.lat0_low);
+    if (MODE & kHigh) {
+        const double vv = fma(g, t2 * fma(t2, fma(t2, 0.0625, -0.125), 0.5), h);
+        la_high = fma(vv, fma(vv, fma(vv, fma(vv, fma(vv, q.b5, q.b4), q.b3), q.b2), q.b1), q.lat0_high);
+    }
+    double la;
+    if (MODE == kLow) la = la_low;
+    else if (MODE == kHigh) la = la_high;
+    else {
+        // the reference's own test, on the float32 z promoted to double, thr = 0.8f (:62)
+        const double thr_r = kLatSwitchF32 * GTP_EARTH_RADIUS;
+        la = (zd < thr_r && zd > -thr_r) ? la_low : la_high;
+    }
+    lat = (float)la;
+}
+
+struct LonLatF { float lon, lat; };
+
+// the reference's formulas with library functions, for quads the series cannot take
+GTP_FD_COLD LonLatF backtransform_f32_slow(float xf, float yf, float zf)
+{
+    const double x = (double)xf, y = (double)yf, z = (double)zf;
+    const double rho = sqrt(x * x + y * y);
+    LonLatF r;
+    r.lon = (float)((acos(x / rho) * GTP_RAD2DEG) * (double)sign_of(y));
+    const double thr_r = kLatSwitchF32 * GTP_EARTH_RADIUS;
+    if ((z < thr_r) && (z > -thr_r)) r.lat = (float)(90.0 - acos(z / GTP_EARTH_RADIUS) * GTP_RAD2DEG);
+    else r.lat = (float)((double)sign_of(z) * (90.0 - asin(rho / GTP_EARTH_RADIUS) * GTP_RAD2DEG));
+    return r;
+}
+
+}  // namespace gtpfast32

@@ -33,7 +33,7 @@
 // functions and static const doubles.
 #ifdef __CUDACC__
 #define GTP_FD __device__ __forceinline__
-#define GTP_FD_COLD __device__ __noinline__      // rarely taken paths: keep them out of the hot I-cache lines
+#define GTP_FD_COLD static __device__ __noinline__      // rarely taken paths: keep them out of the hot I-cache lines
 #define GTP_DCONST(name, value) static __constant__ double name = value
 #else
 #define GTP_FD inline

@@ -7,6 +7,7 @@
 // the product and is never loaded by geotiepoints_b200.
 #include <cstdint>
 #include "../python-geotiepoints_b200/geotiepoints_b200/csrc/gtp_fast_math.cuh"
+#include "../python-geotiepoints_b200/geotiepoints_b200/csrc/gtp_fast_f32_math.cuh"
 
 using namespace gtpfast;
 
@@ -77,6 +78,63 @@ extern "C" int gtp_emul_cviirs_fast_f64(const double* lon, const double* lat, co
     for (int k = 0; k < 5; ++k) mode_counts[k] = 0;
     if (fine_res == 250) run<4>(lon, lat, satz, n_scans, out_lon, out_lat, mode_counts);
     else if (fine_res == 500) run<2>(lon, lat, satz, n_scans, out_lon, out_lat, mode_counts);
+    else return 1;
+    return 0;
+}
+
+
+// ---- float32 fast path (gtp_fast_f32_math.cuh) -------------------------------------------------
+template <int P>
+static void run_f32(const float* lon, const float* lat, const float* satz, long n_scans,
+                    float* out_lon, float* out_lat, long* mode_counts)
+{
+    using namespace gtpfast32;
+    const int W = 1354, L = 10, Wf = W * P, N = L * P, H = P / 2;
+    for (long s = 0; s < n_scans; ++s) {
+        for (int qc = 0; qc <= W - 1; ++qc) {
+            const bool extra = (qc == W - 1);
+            const int ca = extra ? W - 2 : qc, cb = ca + 1, xoff = extra ? P : 0;
+            for (int qr = 0; qr < L - 1; ++qr) {
+                auto geo = [&](int r, int c) { long o = (s * L + r) * W + c; return tie_geo_f32(lon[o], lat[o]); };
+                auto zen = [&](int r, int c) { long o = (s * L + r) * W + c; return tie_zen_f32(satz[o]); };
+                auto v3 = [](const TieGeoF& t) { Vec3F v; v.x = t.x; v.y = t.y; v.z = t.z; return v; };
+                const TieGeoF A = geo(qr, ca);
+                const Vec3F B = v3(geo(qr, cb)), D = v3(geo(qr + 1, ca)), C = v3(geo(qr + 1, cb));
+                const TieZenF za = zen(qr, ca), zb = zen(qr, cb);
+                float ce, cal;
+                quad_exp_ali_f32(za, zb.phi, zb.theta, 1, ce, cal);
+                const QuadF32 q = quad_setup_f32(A, B, C, D, ce, cal);
+                mode_counts[q.mode]++;
+                const int j0 = (qr == 0) ? 0 : qr * P + H;
+                const int j1 = (qr == L - 2) ? N : (qr + 1) * P + H;
+                float s_t = ((qr == 0) ? (0.5f - H) : 0.5f) / P;
+                for (int j = j0; j < j1; ++j, s_t += 1.0f / P) {
+                    const RowF32 rc = row_setup_f32(q, s_t);
+                    for (int k = 0; k < P; ++k) {
+                        const float s_s = (float)(xoff + k) / (float)P;
+                        const double k1d = mul_rn((double)s_s, add_rn(1.0, -(double)s_s));
+                        float v[3], lo, la;
+                        blend_f32(q, rc, s_s, k1d, v);
+                        if (q.mode == kSlow) { const LonLatF ll = backtransform_f32_slow(v[0], v[1], v[2]); lo = ll.lon; la = ll.lat; }
+                        else if (q.wrap) backtransform_f32<kBoth, true>(q, v, lo, la);
+                        else if (q.mode == kLow) backtransform_f32<kLow, false>(q, v, lo, la);
+                        else if (q.mode == kHigh) backtransform_f32<kHigh, false>(q, v, lo, la);
+                        else backtransform_f32<kBoth, false>(q, v, lo, la);
+                        const long o = (s * N + j) * (long)Wf + (long)ca * P + xoff + k;
+                        out_lon[o] = lo; out_lat[o] = la;
+                    }
+                }
+            }
+        }
+    }
+}
+
+extern "C" int gtp_emul_cviirs_fast_f32(const float* lon, const float* lat, const float* satz, long n_scans,
+                                        int fine_res, float* out_lon, float* out_lat, long* mode_counts)
+{
+    for (int k = 0; k < 5; ++k) mode_counts[k] = 0;
+    if (fine_res == 250) run_f32<4>(lon, lat, satz, n_scans, out_lon, out_lat, mode_counts);
+    else if (fine_res == 500) run_f32<2>(lon, lat, satz, n_scans, out_lon, out_lat, mode_counts);
     else return 1;
     return 0;
 }

@@ -17,13 +17,14 @@ from parity import assert_parity
 SRC = os.path.join(ROOT, "tests", "host_emulation.cpp")
 LIB = os.path.join(ROOT, "tests", "libgtp_host_emulation.so")
 HDRS = [os.path.join(ROOT, "python-geotiepoints_b200", "geotiepoints_b200", "csrc", n)
-        for n in ("gtp_fast_math.cuh", "gtp_common.cuh")]
+        for n in ("gtp_fast_math.cuh", "gtp_fast_f32_math.cuh", "gtp_common.cuh")]
 
 
 @pytest.fixture(scope="module")
 def emul():
     if not os.path.exists(LIB) or any(os.path.getmtime(LIB) < os.path.getmtime(f) for f in [SRC] + HDRS):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=fast", "-mfma",
+        # -ffp-contract=off: only the explicit fma() calls of the series are fused, as on the GPU
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-mfma",
                                SRC, "-o", LIB])
     lib = ctypes.CDLL(LIB)
     dp = ctypes.POINTER(ctypes.c_double)
@@ -49,6 +50,19 @@ def emul():
         assert rc == 0
         return out_lon, out_lat, dict(zip(("slow", "low", "high", "both", "small"), modes))
     run.simple = run_simple
+    fp = ctypes.POINTER(ctypes.c_float)
+
+    def run_f32(lon, lat, satz, fine):
+        ns, p = lon.shape[0] // 10, 1000 // fine
+        out_lon = np.full((ns * 10 * p, 1354 * p), np.nan, np.float32)
+        out_lat = np.full_like(out_lon, np.nan)
+        modes = (ctypes.c_long * 5)()
+        rc = lib.gtp_emul_cviirs_fast_f32(lon.ctypes.data_as(fp), lat.ctypes.data_as(fp), satz.ctypes.data_as(fp),
+                                          ctypes.c_long(ns), fine, out_lon.ctypes.data_as(fp),
+                                          out_lat.ctypes.data_as(fp), modes)
+        assert rc == 0
+        return out_lon, out_lat, dict(zip(("slow", "low", "high", "both", "small"), modes))
+    run.f32 = run_f32
     return run
 
 
@@ -121,3 +135,27 @@ def test_simple_fast_math_stress_inputs(emul, golden_inputs, name):
         with np.errstate(all="ignore"):
             exp = gtp_oracle.simple(lon, lat, 1000, fine)
         assert_parity(got_lon, got_lat, *exp, what=f"host emulation simple {name} -> {fine} m, modes {modes}")
+
+
+@pytest.mark.parametrize("fine", [250, 500])
+@pytest.mark.parametrize("granule", [0, 3, 5, 14, 287])
+def test_f32_fast_math_matches_oracle(emul, granule, fine):
+    """float32 fast path: the blend reproduces the reference's rounding points, the back-transform
+    is the anchor-relative series in double; the float32 result is (almost always) bit-identical."""
+    from parity import compare
+    lon, lat, satz = testing.modis_granule(granule, n_scans=3, dtype=np.float32)
+    got_lon, got_lat, modes = emul.f32(lon, lat, satz, fine)
+    exp = gtp_oracle.cviirs(lon, lat, satz, 1000, fine, n_threads=4)
+    s = assert_parity(got_lon, got_lat, *exp, what=f"host emulation f32 granule {granule} -> {fine} m, modes {modes}")
+    assert s["bit_exact_fraction"] > 0.999, s
+
+
+@pytest.mark.parametrize("name", ["real", "antimeridian", "pole", "south_pole", "prime_meridian", "lat_switch",
+                                  "symmetric_satz", "zeros", "nan_holes"])
+def test_f32_fast_math_stress_inputs(emul, golden_inputs, name):
+    lon, lat, satz = golden_inputs[name]
+    for fine in (250, 500):
+        got_lon, got_lat, modes = emul.f32(lon, lat, satz, fine)
+        with np.errstate(all="ignore"):
+            exp = gtp_oracle.cviirs(lon, lat, satz, 1000, fine)
+        assert_parity(got_lon, got_lat, *exp, what=f"host emulation f32 {name} -> {fine} m, modes {modes}")
