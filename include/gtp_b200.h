@@ -19,8 +19,9 @@
  *   gtp_*_interp_host_{f32,f64}        the same operators for HOST buffers (numpy
  *                                      callers): pipelined H2D / kernel / D2H inside.
  *
- * Conventions: plain pointers and sizes, no exceptions, no global mutable state other
- * than a thread-local error string.  Every function returns 0 on success, a GTP_E_*
+ * Conventions: plain pointers and sizes, no exceptions, re-entrant and thread-safe; the only
+ * process state is a thread-local error string, a launch counter and the cache of idle
+ * streams + device scratch of the host entry points (gtp_trim() empties it).  Every function returns 0 on success, a GTP_E_*
  * code (>0) for invalid arguments, or -(cudaError_t) for CUDA failures;
  * gtp_last_error() describes the last failure on the calling thread.  The *_interp_*
  * device entry points are asynchronous on `stream` (a cudaStream_t, NULL = default
@@ -86,7 +87,7 @@ int gtp_simple_interp_generic_f64(const double* lon, const double* lat, int64_t 
 
 /* ---- host-pointer entry points (synchronous; copies inside) -------------------- */
 /* Inputs and outputs are host buffers (pageable or pinned).  The call splits the scans
- * into chunks and overlaps H2D, kernel and D2H on three streams; it returns when the
+ * into chunks and overlaps H2D, kernel and D2H on three cached streams; it returns when the
  * outputs are complete.  Pinned buffers (gtp_host_alloc) reach PCIe line rate. */
 int gtp_cviirs_interp_host_f32(const float* lon, const float* lat, const float* satz, int64_t n_scans,
                                int coarse_res, int fine_res, int coarse_width,
@@ -98,6 +99,10 @@ int gtp_simple_interp_host_f32(const float* lon, const float* lat, int64_t n_sca
                                float* out_lon, float* out_lat, int device);
 int gtp_simple_interp_host_f64(const double* lon, const double* lat, int64_t n_scans, int64_t width, int res_factor,
                                double* out_lon, double* out_lat, int device);
+
+/* The host entry points keep up to 4 idle sets of (3 streams + chunk scratch, ~300 MB of
+ * device memory each) per process for the next call; gtp_trim() frees them. */
+int gtp_trim(void);
 
 /* page-locked host memory for the host entry points */
 int gtp_host_alloc(void** ptr, uint64_t bytes);

@@ -34,6 +34,7 @@ SIGNATURES = {
     "gtp_cviirs_geometry": (_int, [_int, _int, _int] + [ctypes.POINTER(_int)] * 4),
     "gtp_host_alloc": (_int, [ctypes.POINTER(_vp), ctypes.c_uint64]),
     "gtp_host_free": (_int, [_vp]),
+    "gtp_trim": (_int, []),
 }
 for _suf in ("f32", "f64"):
     SIGNATURES[f"gtp_cviirs_interp_{_suf}"] = (_int, [_vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _int, _vp])

@@ -7,6 +7,9 @@
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
+#include <cstdlib>
+#include <mutex>
+#include <vector>
 #include <cuda_runtime.h>
 #include "../../../include/gtp_b200.h"
 #include "gtp_kernels.h"
@@ -107,12 +110,86 @@ int simple_device(const T* lon, const T* lat, int64_t n_scans, int64_t width, in
 
 // ---------------------------------------------------------------------------------
 // Host-buffer pipeline.  The scans are cut into chunks; chunk k runs H2D -> kernel ->
-// D2H in order on stream k % kStreams, so the copy engines and the SMs overlap across
-// chunks.  Device scratch comes from the stream-ordered pool (cudaMallocAsync), which
-// the driver keeps warm between calls.
+// D2H in order on stream k % kStreams, so the two copy engines and the SMs overlap
+// across chunks.  Streams and device scratch live in a HostPipe that is checked out of
+// a small per-process cache for the duration of one call and handed back afterwards
+// (creating streams and mapping ~300 MB of device memory costs as much as moving one
+// granule over PCIe; measured, profiles/r01_e2e_probe.txt).  A pipe is owned by exactly
+// one call at a time, so concurrent callers (dask worker threads) never share state.
 // ---------------------------------------------------------------------------------
 constexpr int kStreams = 3;
-constexpr int64_t kChunkOutBytes = 48ll << 20;   // per output array and chunk
+constexpr int kMaxIdlePipes = 4;
+
+int64_t chunk_out_bytes()
+{
+    // per output array and chunk; GTP_CHUNK_MB is a tuning knob for the e2e probe
+    static const int64_t bytes = [] {
+        const char* env = getenv("GTP_CHUNK_MB");
+        long mb = env ? atol(env) : 0;
+        if (mb < 1 || mb > 4096) mb = 64;
+        return (int64_t)mb << 20;
+    }();
+    return bytes;
+}
+
+struct HostPipe {
+    int device = -1;
+    cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr};
+    char* scratch[kStreams] = {nullptr, nullptr, nullptr};
+    size_t capacity[kStreams] = {0, 0, 0};
+
+    cudaError_t reserve(int s, size_t bytes)
+    {
+        if (!streams[s]) {
+            cudaError_t e = cudaStreamCreateWithFlags(&streams[s], cudaStreamNonBlocking);
+            if (e != cudaSuccess) return e;
+        }
+        if (capacity[s] >= bytes) return cudaSuccess;
+        if (scratch[s]) { cudaFree(scratch[s]); scratch[s] = nullptr; capacity[s] = 0; }
+        cudaError_t e = cudaMalloc((void**)&scratch[s], bytes);
+        if (e == cudaSuccess) capacity[s] = bytes;
+        return e;
+    }
+    void destroy()
+    {
+        for (int s = 0; s < kStreams; ++s) {
+            if (scratch[s]) cudaFree(scratch[s]);
+            if (streams[s]) cudaStreamDestroy(streams[s]);
+            scratch[s] = nullptr; streams[s] = nullptr; capacity[s] = 0;
+        }
+    }
+};
+
+std::mutex g_pipe_mutex;
+std::vector<HostPipe*> g_idle_pipes;
+
+HostPipe* acquire_pipe(int device)
+{
+    {
+        std::lock_guard<std::mutex> lock(g_pipe_mutex);
+        for (size_t i = 0; i < g_idle_pipes.size(); ++i)
+            if (g_idle_pipes[i]->device == device) {
+                HostPipe* p = g_idle_pipes[i];
+                g_idle_pipes.erase(g_idle_pipes.begin() + i);
+                return p;
+            }
+    }
+    HostPipe* p = new HostPipe;
+    p->device = device;
+    return p;
+}
+
+void release_pipe(HostPipe* p, bool healthy)
+{
+    if (healthy) {
+        std::lock_guard<std::mutex> lock(g_pipe_mutex);
+        if ((int)g_idle_pipes.size() < kMaxIdlePipes) { g_idle_pipes.push_back(p); return; }
+    }
+    p->destroy();      // the caller still has p->device current
+    delete p;
+}
+
+size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 #define GTP_CUDA_TRY(expr, where)                                  \
     do {                                                           \
@@ -127,43 +204,48 @@ int host_pipeline(const T* const (&in)[N_IN], T* out_lon, T* out_lat, int64_t n_
     if (n_scans == 0) return GTP_OK;
     DeviceGuard guard(device);
     if (guard.err != cudaSuccess) { cudaGetLastError(); return fail(GTP_E_NO_DEVICE, "no usable CUDA device: %s", cudaGetErrorString(guard.err)); }
+    int current = -1;
+    if (cudaGetDevice(&current) != cudaSuccess) { cudaGetLastError(); return fail(GTP_E_NO_DEVICE, "no usable CUDA device%s"); }
     int status = GTP_OK;
-    int64_t chunk = std::max<int64_t>(1, kChunkOutBytes / (int64_t)(out_elems_per_scan * sizeof(T)));
+    int64_t chunk = std::max<int64_t>(1, chunk_out_bytes() / (int64_t)(out_elems_per_scan * sizeof(T)));
     chunk = std::min(chunk, n_scans);
     const int64_t n_chunks = (n_scans + chunk - 1) / chunk;
     const int n_streams = (int)std::min<int64_t>(kStreams, n_chunks);
-    cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr};
+    const size_t in_bytes = align_up((size_t)chunk * in_elems_per_scan * sizeof(T));
+    const size_t out_bytes = align_up((size_t)chunk * out_elems_per_scan * sizeof(T));
+    HostPipe* pipe = acquire_pipe(current);
     T* d_in[kStreams][N_IN] = {};
     T* d_out[kStreams][2] = {};
     for (int s = 0; s < n_streams; ++s) {
-        GTP_CUDA_TRY(cudaStreamCreateWithFlags(&streams[s], cudaStreamNonBlocking), "stream create");
-        for (int a = 0; a < N_IN; ++a)
-            GTP_CUDA_TRY(cudaMallocAsync((void**)&d_in[s][a], chunk * in_elems_per_scan * sizeof(T), streams[s]), "scratch alloc");
-        for (int a = 0; a < 2; ++a)
-            GTP_CUDA_TRY(cudaMallocAsync((void**)&d_out[s][a], chunk * out_elems_per_scan * sizeof(T), streams[s]), "scratch alloc");
+        GTP_CUDA_TRY(pipe->reserve(s, N_IN * in_bytes + 2 * out_bytes), "scratch alloc");
+        for (int a = 0; a < N_IN; ++a) d_in[s][a] = (T*)(pipe->scratch[s] + a * in_bytes);
+        for (int a = 0; a < 2; ++a) d_out[s][a] = (T*)(pipe->scratch[s] + N_IN * in_bytes + a * out_bytes);
     }
     for (int64_t k = 0; k < n_chunks; ++k) {
         const int s = (int)(k % n_streams);
+        const cudaStream_t st = pipe->streams[s];
         const int64_t s0 = k * chunk, ns = std::min(chunk, n_scans - s0);
         for (int a = 0; a < N_IN; ++a)
             GTP_CUDA_TRY(cudaMemcpyAsync(d_in[s][a], in[a] + s0 * in_elems_per_scan, ns * in_elems_per_scan * sizeof(T),
-                                         cudaMemcpyHostToDevice, streams[s]), "H2D");
-        status = launch(d_in[s], d_out[s][0], d_out[s][1], ns, streams[s]);
+                                         cudaMemcpyHostToDevice, st), "H2D");
+        status = launch(d_in[s], d_out[s][0], d_out[s][1], ns, st);
         if (status != GTP_OK) goto done;
         GTP_CUDA_TRY(cudaMemcpyAsync(out_lon + s0 * out_elems_per_scan, d_out[s][0], ns * out_elems_per_scan * sizeof(T),
-                                     cudaMemcpyDeviceToHost, streams[s]), "D2H");
+                                     cudaMemcpyDeviceToHost, st), "D2H");
         GTP_CUDA_TRY(cudaMemcpyAsync(out_lat + s0 * out_elems_per_scan, d_out[s][1], ns * out_elems_per_scan * sizeof(T),
-                                     cudaMemcpyDeviceToHost, streams[s]), "D2H");
+                                     cudaMemcpyDeviceToHost, st), "D2H");
     }
 done:
-    for (int s = 0; s < n_streams; ++s) {
-        if (!streams[s]) continue;
-        for (int a = 0; a < N_IN; ++a) if (d_in[s][a]) cudaFreeAsync(d_in[s][a], streams[s]);
-        for (int a = 0; a < 2; ++a) if (d_out[s][a]) cudaFreeAsync(d_out[s][a], streams[s]);
-        cudaError_t e = cudaStreamSynchronize(streams[s]);
-        if (e != cudaSuccess && status == GTP_OK) status = cuda_fail(e, "pipeline sync");
-        cudaStreamDestroy(streams[s]);
+    bool healthy = true;
+    for (int s = 0; s < kStreams; ++s) {
+        if (!pipe->streams[s]) continue;
+        cudaError_t e = cudaStreamSynchronize(pipe->streams[s]);
+        if (e != cudaSuccess) {
+            healthy = false;
+            if (status == GTP_OK) status = cuda_fail(e, "pipeline sync");
+        }
     }
+    release_pipe(pipe, healthy && status == GTP_OK);
     return status;
 }
 
@@ -275,6 +357,23 @@ int gtp_simple_interp_host_f32(const float* lon, const float* lat, int64_t n_sca
 int gtp_simple_interp_host_f64(const double* lon, const double* lat, int64_t n_scans, int64_t width, int res_factor,
                                double* out_lon, double* out_lat, int device)
 { return simple_host<double>(lon, lat, n_scans, width, res_factor, out_lon, out_lat, device); }
+
+int gtp_trim(void)
+{
+    std::vector<HostPipe*> pipes;
+    {
+        std::lock_guard<std::mutex> lock(g_pipe_mutex);
+        pipes.swap(g_idle_pipes);
+    }
+    int status = GTP_OK;
+    for (HostPipe* p : pipes) {
+        DeviceGuard guard(p->device);
+        if (guard.err != cudaSuccess) { cudaGetLastError(); status = fail(GTP_E_NO_DEVICE, "no usable CUDA device: %s", cudaGetErrorString(guard.err)); }
+        else p->destroy();
+        delete p;
+    }
+    return status;
+}
 
 int gtp_host_alloc(void** ptr, uint64_t bytes)
 {
