@@ -5,7 +5,7 @@
 // by warp shuffle, so nothing is staged in shared memory and there is no barrier.
 // For every quad the thread projects the quad on the local frame of its corner A once
 // (gtp_fast_math.cuh) and then produces the quad's P x (P | P + P/2) fine pixels with
-// ~25 FP64 FMAs each; a warp therefore writes 31 x 32 B = 992 contiguous bytes per
+// ~16 FP64 FMAs each; a warp therefore writes 31 x 32 B = 992 contiguous bytes per
 // fine row and output array with one 256-bit store per lane (st.global.v4.f64).
 //
 // HBM traffic per output pixel (1 km -> 250 m): 16 B written + 3 x 8 B / 16 read =
@@ -72,11 +72,11 @@ __device__ __forceinline__ void quad_rows(const Quad& q, const double (&a_col)[P
     double s_t = s_t0;
 #pragma unroll 1
     for (int m = 0; m < nrows; ++m) {
-        const RowCoef rc = row_setup(q, s_t);
+        const RowCoef rc = row_setup(q, s_t, s_t * (1.0 - s_t));
         double vlon[P], vlat[P];
 #pragma unroll
 #ifdef GTP_EXP_NO_MATH        // power experiment: keep the HBM writes, drop the per-pixel math
-        for (int k = 0; k < P; ++k) { vlon[k] = a_col[k] + rc.a_base; vlat[k] = a_col[k] - rc.Ue; }
+        for (int k = 0; k < P; ++k) { vlon[k] = a_col[k] + rc.Ve; vlat[k] = a_col[k] - rc.Ue; }
 #else
         for (int k = 0; k < P; ++k) pixel_eval<MODE, WRAP>(q, rc, a_col[k], vlon[k], vlat[k]);
 #endif
@@ -84,27 +84,6 @@ __device__ __forceinline__ void quad_rows(const Quad& q, const double (&a_col)[P
         store_px<P>(olat, vlat);
         olon += kPitch; olat += kPitch;
         s_t += 1.0 / P;              // exact: multiples of 1/8
-    }
-}
-
-// same loop for low-latitude quads, small correction terms in float32 (pixel_eval_low_mixed)
-template <int P, bool WRAP>
-__device__ __forceinline__ void quad_rows_low_mixed(const Quad& q, const double (&a_col)[P], double s_t0, int nrows,
-                                                    double* olon, double* olat)
-{
-    constexpr long long kPitch = (long long)kW * P;
-    const QuadF qf = quad_float_terms(q);
-    double s_t = s_t0;
-#pragma unroll 1
-    for (int m = 0; m < nrows; ++m) {
-        const RowCoef rc = row_setup(q, s_t);
-        double vlon[P], vlat[P];
-#pragma unroll
-        for (int k = 0; k < P; ++k) pixel_eval_low_mixed<WRAP>(q, qf, rc, a_col[k], vlon[k], vlat[k]);
-        store_px<P>(olon, vlon);
-        store_px<P>(olat, vlat);
-        olon += kPitch; olat += kPitch;
-        s_t += 1.0 / P;
     }
 }
 
@@ -144,10 +123,12 @@ modis_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restri
     double* olon = out_lon + scan * (long long)kN * kWf + (long long)quad_col * P + xoff;
     double* olat = out_lat + scan * (long long)kN * kWf + (long long)quad_col * P + xoff;
 
-    // carried from the tie row above: corner A (frame + anchor), corner B, and the quad row's
-    // expansion / alignment coefficients (they depend on the upper corners only, :307-308)
-    TieGeo topA;
-    Vec3 topB;
+    // carried from the tie row above: this lane's tie point (frame + anchor; the next row's sines
+    // and cosines are rotated out of it), corner B, and the quad row's expansion / alignment
+    // coefficients (they depend on the upper corners only, :307-308)
+    TieGeo top = {0.0, 1.0, 0.0, 1.0, 0.0, 0.0};
+    TieZen zen = {0.0, 0.0, 1.0, 0.0, 1.0};
+    Vec3 topB = {0.0, 0.0, 0.0};
     double top_ce = 0.0, top_ca = 0.0;
     __shared__ double stage[2][3][kThreads];     // double-buffered next-row inputs, one slot per thread
     cp_async8(&stage[0][0][threadIdx.x], plon);
@@ -168,19 +149,25 @@ modis_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restri
             cp_async_commit();
         }
         // this lane's tie point of row r; corner B of the lane's quad column comes from lane + 1
-        const TieGeo own = tie_geo(clon, clat);
+        TieGeo own = top;
+        tie_advance<!SIMPLE>(own, zen, clon, clat, csatz, r == 0);
         const Vec3 own_xyz = tie_xyz(own);
-        TieGeo curA = own;
-        Vec3 curA_xyz = own_xyz, curB;
+        Vec3 curB;
         curB.x = __shfl_down_sync(kFull, own_xyz.x, 1);
         curB.y = __shfl_down_sync(kFull, own_xyz.y, 1);
         curB.z = __shfl_down_sync(kFull, own_xyz.z, 1);
-        if (last_warp) {             // warp-uniform: the lane of tie column 1353 takes A from its left neighbour
+        TieGeo A = top;                  // corner A of the quad row above this tie row
+        Vec3 D = own_xyz;
+        if (last_warp) {                 // warp-uniform: the lane of tie column 1353 evaluates the quad of its left neighbour
             TieGeo up;
-            up.sl = __shfl_up_sync(kFull, own.sl, 1); up.cl = __shfl_up_sync(kFull, own.cl, 1);
-            up.sp = __shfl_up_sync(kFull, own.sp, 1); up.cp = __shfl_up_sync(kFull, own.cp, 1);
-            up.lon = __shfl_up_sync(kFull, own.lon, 1); up.lat = __shfl_up_sync(kFull, own.lat, 1);
-            if (extra) { curA = up; curA_xyz = tie_xyz(up); curB = own_xyz; }
+            up.sl = __shfl_up_sync(kFull, top.sl, 1); up.cl = __shfl_up_sync(kFull, top.cl, 1);
+            up.sp = __shfl_up_sync(kFull, top.sp, 1); up.cp = __shfl_up_sync(kFull, top.cp, 1);
+            up.lon = __shfl_up_sync(kFull, top.lon, 1); up.lat = __shfl_up_sync(kFull, top.lat, 1);
+            Vec3 upD;
+            upD.x = __shfl_up_sync(kFull, own_xyz.x, 1);
+            upD.y = __shfl_up_sync(kFull, own_xyz.y, 1);
+            upD.z = __shfl_up_sync(kFull, own_xyz.z, 1);
+            if (extra) { A = up; D = upD; curB = own_xyz; }
         }
 
         if (r > 0 && active) {
@@ -189,22 +176,21 @@ modis_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restri
             const int qr = r - 1;
             const int nrows = P + ((qr == 0 || qr == kL - 2) ? kHalf : 0);
             const double s_t0 = ((qr == 0) ? (0.5 - kHalf) : 0.5) / P;
-            const Vec3 topA_xyz = tie_xyz(topA);
-            const Quad q = quad_setup(topA, topA_xyz, topB, curB, curA_xyz, top_ce, top_ca);
+            const Vec3 A_xyz = tie_xyz(A);
+            Quad q;
+            quad_setup(q, A, A_xyz, topB, curB, D, top_ce, top_ca, extra ? (double)kABoundExtra : 1.0);
             if (q.mode != kSlow) {
-                double a_col[P];     // s_s + s_s (1 - s_s) c_exp  (:341, :344)
+                // s_s + s_s (1 - s_s) c_exp  (:341, :344); s_s = k / P inside the quad, 1 + k / P right of it
+                double a_col[P];
+                const double s_base = extra ? 1.0 : 0.0;
 #pragma unroll
                 for (int k = 0; k < P; ++k) {
-                    const double s_s = (double)(xoff + k) / (double)P;
+                    const double s_s = s_base + (double)k / (double)P;
                     a_col[k] = fma(s_s * (1.0 - s_s), q.ce, s_s);
                 }
                 if (!q.wrap) {
-#ifdef GTP_FAST_MIXED
-                    if (q.mode == kLow) quad_rows_low_mixed<P, false>(q, a_col, s_t0, nrows, olon, olat);
-#else
                     if (q.small) quad_rows<P, kLowSmall, false>(q, a_col, s_t0, nrows, olon, olat);
                     else if (q.mode == kLow) quad_rows<P, kLow, false>(q, a_col, s_t0, nrows, olon, olat);
-#endif
                     else if (q.mode == kHigh) quad_rows<P, kHigh, false>(q, a_col, s_t0, nrows, olon, olat);
                     else quad_rows<P, kBoth, false>(q, a_col, s_t0, nrows, olon, olat);
                 } else {
@@ -217,7 +203,7 @@ modis_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restri
                     double vlon[P], vlat[P];
 #pragma unroll 1
                     for (int k = 0; k < P; ++k) {
-                        const LonLat ll = pixel_eval_slow(topA_xyz, topB, curB, curA_xyz, q.ce, q.ca,
+                        const LonLat ll = pixel_eval_slow(A_xyz, topB, curB, D, q.ce, q.ca,
                                                           (double)(xoff + k) / (double)P, s_t);
                         vlon[k] = ll.lon; vlat[k] = ll.lat;
                     }
@@ -228,12 +214,11 @@ modis_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restri
             olon += (long long)nrows * kWf;
             olat += (long long)nrows * kWf;
         }
-        topA = curA;
+        top = own;
         topB = curB;
 
         if (!SIMPLE && r + 1 < kL) {
             // expansion / alignment of the quad row BELOW this tie row, from this row's zenith angles
-            const TieZen zen = tie_zen(csatz);
             double zb = __shfl_down_sync(kFull, zen.za, 1);
             double sphi_b = __shfl_down_sync(kFull, zen.sphi, 1);
             double cphi_b = __shfl_down_sync(kFull, zen.cphi, 1);
@@ -245,7 +230,8 @@ modis_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restri
                 up.sphi = __shfl_up_sync(kFull, zen.sphi, 1); up.cphi = __shfl_up_sync(kFull, zen.cphi, 1);
                 if (extra) { za = up; zb = zen.za; sphi_b = zen.sphi; cphi_b = zen.cphi; }
             }
-            quad_coefficients(za, zb, sphi_b, cphi_b, 1, top_ce, top_ca);
+            // lanes without a quad (lane 31, clamped columns) would see two equal zenith angles
+            if (active) quad_coefficients(za, zb, sphi_b, cphi_b, 1, top_ce, top_ca);
         }
     }
 }

@@ -73,9 +73,17 @@ GTP_DCONST(k1_120, 1.0 / 120.0);
 GTP_DCONST(k1_720, 1.0 / 720.0);
 GTP_DCONST(k1_5040, 1.0 / 5040.0);
 GTP_DCONST(k3_40, 0.075);
-GTP_DCONST(kABound, 2.3);
-GTP_DCONST(kTBound, 1.4);
+GTP_DCONST(kABoundExtra, 2.3);     // |a_scan| bound of the pixels right of the last quad
+GTP_DCONST(kABound, 2.3);          // float32 path (gtp_fast_f32_math.cuh): one bound for every lane
 GTP_DCONST(kATBound, 3.3);
+GTP_DCONST(kTBound, 1.4);          // |a_track| bound (first / last rows of a scan extrapolate)
+GTP_DCONST(kIncMax, 2.0e-3);       // largest angle step (rad) the row-to-row rotation takes
+GTP_DCONST(kDzMin, 1.0e-9);
+GTP_DCONST(kLonC3, GTP_DEG2RAD * GTP_DEG2RAD / 3.0);                           // atan series in degrees
+GTP_DCONST(kLonC5, GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD / 5.0);
+GTP_DCONST(kV1, 0.5 * GTP_DEG2RAD * GTP_DEG2RAD);                              // sqrt(1 + t^2) - 1 series, t in degrees
+GTP_DCONST(kV2, -0.125 * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD);
+GTP_DCONST(kV3, 0.0625 * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD);
 GTP_DCONST(kMaxRelHoriz, 0.01);
 GTP_DCONST(kMaxRelZ, 2.0e-3);
 GTP_DCONST(kSmallHoriz, 2.5e-3);
@@ -87,7 +95,7 @@ enum QuadMode { kSlow = 0, kLow = 1, kHigh = 2, kBoth = 3, kLowSmall = 5 };   //
 #define GTP_LAT_SWITCH 0.8
 // Acceptance limits of the series (see header), in the constant table above:
 //   kMaxRelHoriz  bound on |d_horizontal| / rho_A;  kMaxRelZ  bound on |d_z| / R;
-//   kABound, kTBound, kATBound  bounds on |a_scan|, |a_track|, |a_scan a_track| used to bound |d|
+//   a_max (1 | kABoundExtra), kTBound  bounds on |a_scan|, |a_track| used to bound |d|
 
 struct TieGeo {            // geometry of one tie point (lonlat2xyz and the local frame)
     double sl, cl;         // sin / cos of the longitude
@@ -106,7 +114,8 @@ struct TieZen {            // satellite-zenith chain of one tie point (:52-57, :
 struct Quad {
     int mode;
     double ce, ca;                       // c_expansion, c_alignment
-    double Pe, Ph, Pw, Qe, Qh, Qw, Se, Sh, Sw;   // scaled frame components of P, Q, S
+    // frame components of P, Q, S scaled by 1/rho_A (h), 1/R (w) and 180/(pi rho_A) (e: degrees)
+    double Pe, Ph, Pw, Qe, Qh, Qw, Se, Sh, Sw;
     double lon0, lat0;                   // anchor, degrees
     double s0;                           // z_A / R
     double a1, a2, a3, a4, a5;           // low-latitude series (degrees per w^k)
@@ -138,8 +147,8 @@ GTP_FD double fast_rcp(double x)
 #endif
 }
 
-// sqrt(x) to ~1 ulp for x > 0 (0 gives NaN -> slow path)
-GTP_FD double fast_sqrt(double x)
+// sqrt(x) and 1/sqrt(x) to ~1 ulp for x > 0 (0 gives NaN -> slow path)
+GTP_FD double fast_sqrt_rsqrt(double x, double& rsq)
 {
 #ifdef __CUDA_ARCH__
     double y;
@@ -147,12 +156,17 @@ GTP_FD double fast_sqrt(double x)
     const double hx = 0.5 * x;
     y = y * fma(-hx * y, y, 1.5);
     y = y * fma(-hx * y, y, 1.5);
+    rsq = y;
     const double sq = x * y;
     return fma(fma(-sq, sq, x), 0.5 * y, sq);
 #else
-    return sqrt(x);
+    const double sq = sqrt(x);
+    rsq = 1.0 / sq;
+    return sq;
 #endif
 }
+
+GTP_FD double fast_sqrt(double x) { double y; return fast_sqrt_rsqrt(x, y); }
 
 // x with its sign bit flipped where `mask` has bit 63 set (an integer op instead of an FP64 one)
 GTP_FD double xor_sign(double x, unsigned long long mask)
@@ -168,12 +182,10 @@ GTP_FD double xor_sign(double x, unsigned long long mask)
 
 struct SinCos { double s, c; };
 GTP_FD_COLD SinCos library_sincos(double x) { SinCos r; sincos(x, &r.s, &r.c); return r; }
-GTP_FD_COLD double library_asin(double x) { return asin(x); }
 
-// sin and cos of |x| <= 8 (longitudes, latitudes, zenith angles in radians)
-GTP_FD void fast_sincos(double x, double& sn, double& cs)
+// sin and cos of |x| <= 8 (longitudes, latitudes, zenith angles in radians); the caller checks the range
+GTP_FD void sincos_bounded(double x, double& sn, double& cs)
 {
-    if (!(fabs(x) <= 8.0)) { const SinCos r = library_sincos(x); sn = r.s; cs = r.c; return; }   // out-of-range / NaN: library path
     const double kf = rint(x * kTwoOverPi);
     double r = fma(-kf, kPio2Hi, x);
     r = fma(-kf, kPio2Lo, r);
@@ -197,6 +209,24 @@ GTP_FD void fast_sincos(double x, double& sn, double& cs)
     cs = xor_sign(c0, (unsigned long long)((quad + 1) & 2) << 62);
 }
 
+GTP_FD void fast_sincos(double x, double& sn, double& cs)
+{
+    if (!(fabs(x) <= 8.0)) { const SinCos r = library_sincos(x); sn = r.s; cs = r.c; return; }   // out-of-range / NaN: library path
+    sincos_bounded(x, sn, cs);
+}
+
+// (sin, cos)(x + d) from (sin, cos)(x) for |d| <= kIncMax: sin d = d - d^3/6 (next term 2.7e-16),
+// cos d - 1 = -d^2/2 + d^4/24.  Nine such steps (one scan) add < 2e-15 of rounding.
+GTP_FD void rotate_small(double& sn, double& cs, double d)
+{
+    const double d2 = d * d;
+    const double sd = fma(d * d2, -kSixth, d);
+    const double cm = d2 * fma(d2, k1_24, -0.5);
+    const double s1 = fma(sn, cm, fma(cs, sd, sn));
+    const double c1 = fma(cs, cm, fma(-sn, sd, cs));
+    sn = s1; cs = c1;
+}
+
 GTP_FD TieGeo tie_geo(double lon, double lat)
 {
     TieGeo t;
@@ -214,14 +244,60 @@ GTP_FD Vec3 tie_xyz(const TieGeo& t)             // _modis_utils.pyx:38-40
     return v;
 }
 
+GTP_FD void tie_zen_phi(TieZen& t)
+{
+    t.sphi = t.sz * kSinPhiScale;                                  // :74
+    t.cphi = fast_sqrt(fma(-t.sphi, t.sphi, 1.0));
+}
+
 GTP_FD TieZen tie_zen(double satz)
 {
     TieZen t;
     t.za = satz * kDeg2Rad;
     fast_sincos(t.za, t.sz, t.cz);
-    t.sphi = t.sz * kSinPhiScale;                                  // :74
-    t.cphi = fast_sqrt(fma(-t.sphi, t.sphi, 1.0));
+    tie_zen_phi(t);
     return t;
+}
+
+struct TieFull { TieGeo g; TieZen z; };
+GTP_FD_COLD TieFull tie_full_library(double lon, double lat, double satz)
+{
+    TieFull f;
+    f.g = tie_geo(lon, lat);
+    f.z = tie_zen(satz);
+    return f;
+}
+
+// The tie point below `g` / `z` in the same tie column (the kernel walks down the ten tie rows of
+// a scan): consecutive rows are ~1 km apart, so the sines and cosines follow from the previous
+// row's by a small rotation (9 FMAs per angle instead of a 23-instruction sincos + quadrant
+// logic).  `first` (tie row 0 of a scan), steps beyond kIncMax (poles, the antimeridian),
+// NaN and out-of-range inputs take the full evaluation.
+template <bool WITH_ZEN>
+GTP_FD void tie_advance(TieGeo& g, TieZen& z, double lon, double lat, double satz, bool first)
+{
+    const double dl = (lon - g.lon) * kDeg2Rad, dp = (lat - g.lat) * kDeg2Rad;
+    const double za = satz * kDeg2Rad, dzr = WITH_ZEN ? za - z.za : 0.0;
+    g.lon = lon; g.lat = lat;
+    if (WITH_ZEN) z.za = za;
+    const bool step = !first && (fabs(dl) <= kIncMax) && (fabs(dp) <= kIncMax) && (fabs(dzr) <= kIncMax);
+    if (step) {
+        rotate_small(g.sl, g.cl, dl);
+        rotate_small(g.sp, g.cp, dp);
+        if (WITH_ZEN) rotate_small(z.sz, z.cz, dzr);
+    } else {
+        const double xl = lon * kDeg2Rad, xp = lat * kDeg2Rad;
+        if ((fabs(xl) <= 8.0) && (fabs(xp) <= 8.0) && (fabs(za) <= 8.0)) {
+            sincos_bounded(xl, g.sl, g.cl);
+            sincos_bounded(xp, g.sp, g.cp);
+            if (WITH_ZEN) sincos_bounded(za, z.sz, z.cz);
+        } else {
+            const TieFull f = tie_full_library(lon, lat, WITH_ZEN ? satz : 0.0);
+            g = f.g;
+            if (WITH_ZEN) z = f.z;
+        }
+    }
+    if (WITH_ZEN) tie_zen_phi(z);
 }
 
 // Expansion / alignment of the quad whose upper corners are a (left) and b (right),
@@ -230,9 +306,12 @@ GTP_FD TieZen tie_zen(double satz)
 //   phi follow from angle-difference identities with small-argument series;
 //   (theta_a + theta_b)/2 - theta  =  zm - zeta   (phi is the exact mean of phi_a, phi_b), and
 //   zeta - zm = asin(sin(zeta) cos(zm) - cos(zeta) sin(zm)) is a tiny angle;
-//   theta_a - theta_b = dphi - dz.
+//   theta_a - theta_b = dphi - dz;
+//   e = cos(zeta) - sqrt(cos(zeta)^2 - d^2) = (d^2 / 2 cos(zeta)) (1 + d^2 / 4 cos(zeta)^2)
+//   (d <= 7e-4, next term 1e-14 relative; the reference's own form cancels 7 digits there).
 // Returns false (ce, ca untouched) when the two zenith angles are too far apart for the
-// small-argument series; the caller then uses quad_exp_ali_exact.
+// small-argument series or so close that the reference's theta_a == theta_b test (:62) may
+// fire; the caller then uses quad_exp_ali_exact.
 GTP_FD bool quad_exp_ali(double za, double sza, double cza, double sphi_a, double cphi_a,
                          double zb, double sphi_b, double cphi_b, int km, double& ce, double& ca)
 {
@@ -240,7 +319,7 @@ GTP_FD bool quad_exp_ali(double za, double sza, double cza, double sphi_a, doubl
     // dphi = asin(sin(phi_b - phi_a))
     const double sd = fma(sphi_b, cphi_a, -(sphi_a * cphi_b));
     const double dz = zb - za;
-    if (!(fabs(sd) <= 0.01 && fabs(dz) <= 0.02)) return false;      // also catches NaN
+    if (!(fabs(sd) <= 0.01 && fabs(dz) <= 0.02 && fabs(dz) >= kDzMin)) return false;      // also catches NaN
     const double sd2 = sd * sd;
     const double dphi = fma(sd * sd2, fma(sd2, k3_40, kSixth), sd);
     // mean phi = phi_a + dphi / 2
@@ -250,7 +329,8 @@ GTP_FD bool quad_exp_ali(double za, double sza, double cza, double sphi_a, doubl
     const double sphi = fma(sphi_a, ch, cphi_a * sh);
     const double cphi = fma(cphi_a, ch, -(sphi_a * sh));
     const double szeta = K * sphi;                                   // sin(zeta) of :82
-    const double czeta = fast_sqrt(fma(-szeta, szeta, 1.0));
+    double inv_czeta;
+    const double czeta = fast_sqrt_rsqrt(fma(-szeta, szeta, 1.0), inv_czeta);
     // zm = za + dz / 2
     const double hz = 0.5 * dz, hz2 = hz * hz;
     const double shz = fma(hz * hz2, fma(hz2, fma(hz2, -k1_5040, k1_120), -kSixth), hz);
@@ -260,12 +340,12 @@ GTP_FD bool quad_exp_ali(double za, double sza, double cza, double sphi_a, doubl
     // delta = zeta - zm
     const double sdel = fma(szeta, czm, -(czeta * szm));
     const double delta = fma(sdel * (sdel * sdel), kSixth, sdel);
-    double den = dphi - dz;                                          // theta_a - theta_b
-    if (dz == 0.0) den = 2.0 * (za - library_asin(sphi_a));          // :61-62, symmetric tie points
+    const double den = dphi - dz;                                    // theta_a - theta_b
     const double inv_den = 4.0 * fast_rcp(den);
     ce = -delta * inv_den;
     const double d = (K * cphi - czeta) * ((double)km * kInv2H);
-    const double e = czeta - fast_sqrt(fma(czeta, czeta, -(d * d)));
+    const double u = (d * d) * inv_czeta;
+    const double e = (0.5 * u) * fma(0.25 * u, inv_czeta, 1.0);
     ca = (e * szeta) * inv_den;
     return true;
 }
@@ -303,36 +383,38 @@ GTP_FD void quad_coefficients(const TieZen& a, double zb, double sphi_b, double 
 GTP_FD double absd(double x) { return fabs(x); }
 
 // A, B = upper left / right, D, C = lower left / right corner of the quad; ce, ca from
-// quad_exp_ali (they only depend on the zenith angles of A and B)
-GTP_FD Quad quad_setup(const TieGeo& A, const Vec3& Axyz, const Vec3& B, const Vec3& C, const Vec3& D,
-                       double ce, double ca)
+// quad_exp_ali (they only depend on the zenith angles of A and B).  a_max bounds |a_scan| over
+// the pixels this quad is evaluated at: 1 for the P pixels inside the quad (s_s <= 3/4, and
+// |ce|, |ca| <= 1/4 is part of the acceptance), kABoundExtra for the P pixels right of the last
+// quad (s_s <= 7/4, s_s (1 - s_s) >= -21/16).
+GTP_FD void quad_setup(Quad& q, const TieGeo& A, const Vec3& Axyz, const Vec3& B, const Vec3& C, const Vec3& D,
+                       double ce, double ca, double a_max)
 {
-    Quad q;
-    q.a1 = q.a2 = q.a3 = q.a4 = q.a5 = 0.0;
-    q.b1 = q.b2 = q.b3 = q.b4 = q.b5 = 0.0;
     q.wrap = false;
     q.small = false;
     q.ce = ce; q.ca = ca;
 
     const double inv_c = fast_rcp(A.cp);
     const double inv_rho = inv_c * kInvEarthR;
+    const double inv_rho_deg = inv_rho * kRad2Deg;
     const double inv_R = kInvEarthR;
     const double Px = B.x - Axyz.x, Py = B.y - Axyz.y, Pz = B.z - Axyz.z;
     const double Qx = D.x - Axyz.x, Qy = D.y - Axyz.y, Qz = D.z - Axyz.z;
     const double Sx = (C.x - D.x) - Px, Sy = (C.y - D.y) - Py, Sz = (C.z - D.z) - Pz;
-    q.Pe = fma(-A.sl, Px, A.cl * Py) * inv_rho; q.Ph = fma(A.cl, Px, A.sl * Py) * inv_rho; q.Pw = Pz * inv_R;
-    q.Qe = fma(-A.sl, Qx, A.cl * Qy) * inv_rho; q.Qh = fma(A.cl, Qx, A.sl * Qy) * inv_rho; q.Qw = Qz * inv_R;
-    q.Se = fma(-A.sl, Sx, A.cl * Sy) * inv_rho; q.Sh = fma(A.cl, Sx, A.sl * Sy) * inv_rho; q.Sw = Sz * inv_R;
+    q.Pe = fma(-A.sl, Px, A.cl * Py) * inv_rho_deg; q.Ph = fma(A.cl, Px, A.sl * Py) * inv_rho; q.Pw = Pz * inv_R;
+    q.Qe = fma(-A.sl, Qx, A.cl * Qy) * inv_rho_deg; q.Qh = fma(A.cl, Qx, A.sl * Qy) * inv_rho; q.Qw = Qz * inv_R;
+    q.Se = fma(-A.sl, Sx, A.cl * Sy) * inv_rho_deg; q.Sh = fma(A.cl, Sx, A.sl * Sy) * inv_rho; q.Sw = Sz * inv_R;
     q.lon0 = A.lon; q.lat0 = A.lat; q.s0 = A.sp;
 
-    // size of the displacement over the whole quad (incl. the extrapolated edge pixels)
-    const double horiz = kABound * (absd(q.Pe) + absd(q.Ph)) + kTBound * (absd(q.Qe) + absd(q.Qh))
-                         + kATBound * (absd(q.Se) + absd(q.Sh));
-    const double wmax = kABound * absd(q.Pw) + kTBound * absd(q.Qw) + kATBound * absd(q.Sw);
+    // size of the displacement over the whole quad (incl. the extrapolated edge pixels), radians
+    const double at_max = a_max * kTBound;
+    const double horiz = a_max * fma(absd(q.Pe), kDeg2Rad, absd(q.Ph)) + kTBound * fma(absd(q.Qe), kDeg2Rad, absd(q.Qh))
+                         + at_max * fma(absd(q.Se), kDeg2Rad, absd(q.Sh));
+    const double wmax = a_max * absd(q.Pw) + kTBound * absd(q.Qw) + at_max * absd(q.Sw);
     // written so that any NaN (lon/lat/satz) fails the test and takes the slow path
     const bool ok = (horiz <= kMaxRelHoriz) && (wmax <= kMaxRelZ)
-                    && (absd(q.ce) <= 1.0) && (absd(q.ca) <= 0.5) && (A.cp > 1e-6);
-    if (!ok) { q.mode = kSlow; return q; }
+                    && (absd(q.ce) <= 0.25) && (absd(q.ca) <= 0.25) && (A.cp > 1e-6);
+    if (!ok) { q.mode = kSlow; return; }
 
     const double zr_lo = q.s0 - wmax, zr_hi = q.s0 + wmax;
     const double margin = 1e-9;
@@ -368,39 +450,36 @@ GTP_FD Quad quad_setup(const TieGeo& A, const Vec3& Axyz, const Vec3& B, const V
         m *= u * c; q.b4 = c * fma(2.0, c2, 3.0) * 0.125 * m;
         m *= u * c; q.b5 = fma(c2, fma(8.0, c2, 24.0), 3.0) * k1_40 * m;
     }
-    return q;
 }
 
 struct RowCoef {           // per (quad, fine row): the a_track-dependent half of the bilinear form
-    double Ue, Uh, Uw, Ve, Vh, Vw;
-    double a_base;         // s_t (1 - s_t) c_ali
+    double Ue, Uh, Uw, Ve, Vh, Vw;     // (e, h, w) = a_col U + V, with the row's alignment term folded into V
 };
 
-GTP_FD RowCoef row_setup(const Quad& q, double s_t)
+// s_t = a_track of the fine row, c_t = s_t (1 - s_t)
+GTP_FD RowCoef row_setup(const Quad& q, double s_t, double c_t)
 {
     RowCoef r;
+    const double a_base = c_t * q.ca;            // the per-(quad, row) part of a_scan (:344)
     r.Ue = fma(s_t, q.Se, q.Pe); r.Uh = fma(s_t, q.Sh, q.Ph); r.Uw = fma(s_t, q.Sw, q.Pw);
-    r.Ve = s_t * q.Qe; r.Vh = s_t * q.Qh; r.Vw = s_t * q.Qw;
-    r.a_base = (s_t * (1.0 - s_t)) * q.ca;
+    r.Ve = fma(a_base, r.Ue, s_t * q.Qe); r.Vh = fma(a_base, r.Uh, s_t * q.Qh); r.Vw = fma(a_base, r.Uw, s_t * q.Qw);
     return r;
 }
 
 // One fine pixel.  `a_col` = s_s + s_s (1 - s_s) c_exp is the per-(quad, column) part of
-// a_scan (:344), r.a_base the per-(quad, row) part.  MODE and WRAP are compile-time so that
-// the row loops of the kernel are branch-free; they are quad properties (Quad::mode, ::wrap).
+// a_scan (:344).  MODE and WRAP are compile-time so that the row loops of the kernel are
+// branch-free; they are quad properties (Quad::mode, ::wrap).  e is in degrees (Quad).
 template <int MODE, bool WRAP>
 GTP_FD void pixel_eval(const Quad& q, const RowCoef& r, double a_col, double& lon, double& lat)
 {
-    const double a = a_col + r.a_base;
-    const double e = fma(a, r.Ue, r.Ve);
-    const double h = fma(a, r.Uh, r.Vh);
-    const double w = fma(a, r.Uw, r.Vw);
+    const double e = fma(a_col, r.Ue, r.Ve);
+    const double h = fma(a_col, r.Uh, r.Vh);
+    const double w = fma(a_col, r.Uw, r.Vw);
     if (MODE == kLowSmall) {
         // t = e / (1 + h) with 1/(1+h) = 1 - h + h^2 - h^3 + h^4 (|h| <= 2.5e-3)
         const double rcp = fma(h, fma(h, fma(h, h - 1.0, 1.0), -1.0), 1.0);
         const double t = e * rcp;
-        const double at = fma((t * t) * t, -kThird, t);             // atan(t) = t - t^3/3
-        lon = fma(at, kRad2Deg, q.lon0);
+        lon = fma(t, fma(t * t, -kLonC3, 1.0), q.lon0);              // atan(t) = t - t^3/3, in degrees
         lat = fma(w, fma(w, fma(w, fma(w, q.a4, q.a3), q.a2), q.a1), q.lat0);
         return;
     }
@@ -410,9 +489,8 @@ GTP_FD void pixel_eval(const Quad& q, const RowCoef& r, double a_col, double& lo
     rcp = fma(rcp, fma(-g, rcp, 1.0), rcp);
     const double t = e * rcp;
     const double t2 = t * t;
-    // atan(t) = t - t^3/3 + t^5/5   (|t| <= 0.011 -> next term 3e-15 rad)
-    const double at = fma(t * t2, fma(t2, 0.2, -kThird), t);
-    double lo = fma(at, kRad2Deg, q.lon0);
+    // atan(t) = t - t^3/3 + t^5/5   (|t| <= 0.011 rad -> next term 3e-15 rad), t in degrees
+    double lo = fma(t, fma(t2, fma(t2, kLonC5, -kLonC3), 1.0), q.lon0);
     if (WRAP) {
         if (lo > 180.0) lo -= 360.0;
         else if (lo < -180.0) lo += 360.0;
@@ -424,7 +502,7 @@ GTP_FD void pixel_eval(const Quad& q, const RowCoef& r, double a_col, double& lo
         la_low = fma(w, fma(w, fma(w, fma(w, fma(w, q.a5, q.a4), q.a3), q.a2), q.a1), q.lat0);
     if (MODE & kHigh) {
         // rho / rho_A = (1 + h) sqrt(1 + t^2);  v = h + g (t^2/2 - t^4/8 + t^6/16)
-        const double v = fma(g, t2 * fma(t2, fma(t2, 0.0625, -0.125), 0.5), h);
+        const double v = fma(g, t2 * fma(t2, fma(t2, kV3, kV2), kV1), h);
         la_high = fma(v, fma(v, fma(v, fma(v, fma(v, q.b5, q.b4), q.b3), q.b2), q.b1), q.lat0);
     }
     if (MODE == kLow) lat = la_low;
@@ -433,47 +511,6 @@ GTP_FD void pixel_eval(const Quad& q, const RowCoef& r, double a_col, double& lo
         const double zr = q.s0 + w;
         lat = (zr < kLatSwitch && zr > -kLatSwitch) ? la_low : la_high;
     }
-}
-
-// Low-latitude pixel with the small correction terms in float32.  Everything that is added to
-// a large term is still float64; only terms that are themselves < 2e-6 rad / 1e-6 deg are
-// evaluated in float (relative error 2e-7 -> below 3e-13 rad / 2e-13 deg):
-//   1/(1+h) = (1 - h) + rb,          rb = h^2 - h^3 + h^4 - h^5          (|h| <= 0.01)
-//   atan(e/(1+h)) = e (1 - h) + [e rb - t^3/3 + t^5/5]                    (|t| <= 0.011)
-//   lat = lat_A + w (a1 + a2 w) + [w^3 (a3 + a4 w + a5 w^2)]
-// 11 FP64 instructions and 5 conversions per pixel instead of 20 FP64 instructions.
-struct QuadF { float a3, a4, a5; };
-
-GTP_FD QuadF quad_float_terms(const Quad& q)
-{
-    QuadF f;
-    f.a3 = (float)q.a3; f.a4 = (float)q.a4; f.a5 = (float)q.a5;
-    return f;
-}
-
-template <bool WRAP>
-GTP_FD void pixel_eval_low_mixed(const Quad& q, const QuadF& qf, const RowCoef& r, double a_col,
-                                 double& lon, double& lat)
-{
-    const double a = a_col + r.a_base;
-    const double e = fma(a, r.Ue, r.Ve);
-    const double h = fma(a, r.Uh, r.Vh);
-    const double w = fma(a, r.Uw, r.Vw);
-    const float ef = (float)e, hf = (float)h, wf = (float)w;
-    const float omhf = 1.0f - hf;
-    const float rb = (hf * hf) * fmaf(hf * hf, omhf, omhf);          // (h^2)(1 - h)(1 + h^2)
-    const float tf = ef * (omhf + rb);
-    const float t2f = tf * tf;
-    const float corr = fmaf(tf * t2f, fmaf(t2f, 0.2f, -0.33333334f), ef * rb);
-    const double omh = 1.0 - h;
-    double lo = fma(e * omh, kRad2Deg, q.lon0 + (double)(corr * 57.29578f));
-    if (WRAP) {
-        if (lo > 180.0) lo -= 360.0;
-        else if (lo < -180.0) lo += 360.0;
-    }
-    lon = lo;
-    const float br = (wf * wf) * wf * fmaf(wf, fmaf(wf, qf.a5, qf.a4), qf.a3);
-    lat = fma(w, fma(w, q.a2, q.a1), q.lat0 + (double)br);
 }
 
 // ---- rounding-faithful per-pixel evaluation (fallback for quads the series cannot take) ----

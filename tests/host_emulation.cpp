@@ -6,51 +6,62 @@
 // test and the fallback can be checked against the oracle without a GPU.  It is not part of
 // the product and is never loaded by geotiepoints_b200.
 #include <cstdint>
+#include <vector>
 #include "../python-geotiepoints_b200/geotiepoints_b200/csrc/gtp_fast_math.cuh"
 #include "../python-geotiepoints_b200/geotiepoints_b200/csrc/gtp_fast_f32_math.cuh"
 
 using namespace gtpfast;
 
-// simple == true: simple_modis_interpolator = the same bilinear form with c_exp = c_ali = 0
+// simple == true: simple_modis_interpolator = the same bilinear form with c_exp = c_ali = 0.
+// Like the kernel, every tie column is walked down the ten tie rows of a scan with tie_advance
+// (row 0: full sincos, rows 1..9: small rotations of the row above).
 template <int P>
 static void run(const double* lon, const double* lat, const double* satz, long n_scans,
                 double* out_lon, double* out_lat, long* mode_counts, bool simple = false)
 {
     const int W = 1354, L = 10, Wf = W * P, N = L * P, H = P / 2;
+    std::vector<TieGeo> geo((size_t)L * W);
+    std::vector<TieZen> zen((size_t)L * W);
     for (long s = 0; s < n_scans; ++s) {
+        for (int c = 0; c < W; ++c) {
+            TieGeo g = {0.0, 1.0, 0.0, 1.0, 0.0, 0.0};
+            TieZen z = {0.0, 0.0, 1.0, 0.0, 1.0};
+            for (int r = 0; r < L; ++r) {
+                const long o = (s * L + r) * W + c;
+                if (simple) tie_advance<false>(g, z, lon[o], lat[o], 0.0, r == 0);
+                else tie_advance<true>(g, z, lon[o], lat[o], satz[o], r == 0);
+                geo[(size_t)r * W + c] = g; zen[(size_t)r * W + c] = z;
+            }
+        }
         for (int qc = 0; qc <= W - 1; ++qc) {            // qc == W-1: the "extra" pixels of the last quad
             const bool extra = (qc == W - 1);
             const int ca = extra ? W - 2 : qc, cb = ca + 1, xoff = extra ? P : 0;
             for (int qr = 0; qr < L - 1; ++qr) {
-                auto geo = [&](int r, int c) { long o = (s * L + r) * W + c; return tie_geo(lon[o], lat[o]); };
-                auto zen = [&](int r, int c) { long o = (s * L + r) * W + c; return tie_zen(satz[o]); };
-                const TieGeo A = geo(qr, ca);
-                const Vec3 Ax = tie_xyz(A), B = tie_xyz(geo(qr, cb)), D = tie_xyz(geo(qr + 1, ca)), C = tie_xyz(geo(qr + 1, cb));
+                const TieGeo A = geo[(size_t)qr * W + ca];
+                const Vec3 Ax = tie_xyz(A), B = tie_xyz(geo[(size_t)qr * W + cb]),
+                           D = tie_xyz(geo[(size_t)(qr + 1) * W + ca]), C = tie_xyz(geo[(size_t)(qr + 1) * W + cb]);
                 double ce = 0.0, cal = 0.0;
                 if (!simple) {
-                    const TieZen za = zen(qr, ca), zb = zen(qr, cb);
+                    const TieZen za = zen[(size_t)qr * W + ca], zb = zen[(size_t)qr * W + cb];
                     quad_coefficients(za, zb.za, zb.sphi, zb.cphi, 1, ce, cal);
                 }
-                const Quad q = quad_setup(A, Ax, B, C, D, ce, cal);
+                Quad q;
+                quad_setup(q, A, Ax, B, C, D, ce, cal, extra ? (double)kABoundExtra : 1.0);
                 mode_counts[q.mode]++;
-                if (q.small) mode_counts[4]++;
+                if (q.mode != kSlow && q.small) mode_counts[4]++;
                 const int j0 = (qr == 0) ? 0 : qr * P + H;
                 const int j1 = (qr == L - 2) ? N : (qr + 1) * P + H;
                 for (int j = j0; j < j1; ++j) {
                     const double s_t = fine_row_y<P>(j) / (double)P;
-                    const RowCoef rc = row_setup(q, s_t);
+                    const RowCoef rc = (q.mode != kSlow) ? row_setup(q, s_t, s_t * (1.0 - s_t)) : RowCoef();
                     for (int k = 0; k < P; ++k) {
                         const double s_s = (double)(xoff + k) / (double)P;
                         double lo, la;
                         const double a_col = fma(s_s * (1.0 - s_s), q.ce, s_s);
                         if (q.mode == kSlow) { const LonLat ll = pixel_eval_slow(Ax, B, C, D, q.ce, q.ca, s_s, s_t); lo = ll.lon; la = ll.lat; }
                         else if (q.wrap) pixel_eval<kBoth, true>(q, rc, a_col, lo, la);
-#ifdef GTP_FAST_MIXED
-                        else if (q.mode == kLow) pixel_eval_low_mixed<false>(q, quad_float_terms(q), rc, a_col, lo, la);
-#else
                         else if (q.small) pixel_eval<kLowSmall, false>(q, rc, a_col, lo, la);
                         else if (q.mode == kLow) pixel_eval<kLow, false>(q, rc, a_col, lo, la);
-#endif
                         else if (q.mode == kHigh) pixel_eval<kHigh, false>(q, rc, a_col, lo, la);
                         else pixel_eval<kBoth, false>(q, rc, a_col, lo, la);
                         const long o = (s * N + j) * (long)Wf + (long)ca * P + xoff + k;
