@@ -78,13 +78,32 @@ __device__ __forceinline__ void quad_rows(const Quad& q, const double (&a_col)[P
 #ifdef GTP_EXP_NO_MATH        // power experiment: keep the HBM writes, drop the per-pixel math
         for (int k = 0; k < P; ++k) { vlon[k] = a_col[k] + rc.Ve; vlat[k] = a_col[k] - rc.Ue; }
 #else
-        for (int k = 0; k < P; ++k) pixel_eval<MODE, WRAP>(q, rc, a_col[k], vlon[k], vlat[k]);
+        for (int k = 0; k < P; ++k) {
+            if (MODE == kWide) pixel_eval_wide(q, rc, a_col[k], vlon[k], vlat[k]);
+            else pixel_eval<MODE, WRAP>(q, rc, a_col[k], vlon[k], vlat[k]);
+        }
 #endif
         store_px<P>(olon, vlon);
         store_px<P>(olat, vlat);
         olon += kPitch; olat += kPitch;
         s_t += 1.0 / P;              // exact: multiples of 1/8
     }
+}
+
+// The rarely taken evaluation modes (quads straddling |lat| = 53.13 deg or the antimeridian, polar
+// quads) run out of line on a copy of the quad, so that their coefficient sets (a1..a5 AND b1..b8)
+// do not weigh on the register allocation of the three hot loops.
+template <int P>
+__device__ __noinline__ void quad_rows_cold(const Quad* qp, const double* a_colp, double s_t0, int nrows,
+                                            double* olon, double* olat)
+{
+    const Quad q = *qp;
+    double a_col[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) a_col[k] = a_colp[k];
+    if (q.mode == kWide) quad_rows<P, kWide, true>(q, a_col, s_t0, nrows, olon, olat);
+    else if (q.wrap) quad_rows<P, kBoth, true>(q, a_col, s_t0, nrows, olon, olat);
+    else quad_rows<P, kBoth, false>(q, a_col, s_t0, nrows, olon, olat);
 }
 
 // SIMPLE = true is simple_modis_interpolator: the same bilinear form with a_scan = s_s and
@@ -188,13 +207,15 @@ modis_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restri
                     const double s_s = s_base + (double)k / (double)P;
                     a_col[k] = fma(s_s * (1.0 - s_s), q.ce, s_s);
                 }
-                if (!q.wrap) {
-                    if (q.small) quad_rows<P, kLowSmall, false>(q, a_col, s_t0, nrows, olon, olat);
-                    else if (q.mode == kLow) quad_rows<P, kLow, false>(q, a_col, s_t0, nrows, olon, olat);
-                    else if (q.mode == kHigh) quad_rows<P, kHigh, false>(q, a_col, s_t0, nrows, olon, olat);
-                    else quad_rows<P, kBoth, false>(q, a_col, s_t0, nrows, olon, olat);
-                } else {
-                    quad_rows<P, kBoth, true>(q, a_col, s_t0, nrows, olon, olat);
+                if (!q.wrap && q.small) quad_rows<P, kLowSmall, false>(q, a_col, s_t0, nrows, olon, olat);
+                else if (!q.wrap && q.mode == kLow) quad_rows<P, kLow, false>(q, a_col, s_t0, nrows, olon, olat);
+                else if (!q.wrap && q.mode == kHigh) quad_rows<P, kHigh, false>(q, a_col, s_t0, nrows, olon, olat);
+                else {
+                    const Quad qc = q;
+                    double a_colc[P];
+#pragma unroll
+                    for (int k = 0; k < P; ++k) a_colc[k] = a_col[k];
+                    quad_rows_cold<P>(&qc, a_colc, s_t0, nrows, olon, olat);
                 }
             } else {
 #pragma unroll 1

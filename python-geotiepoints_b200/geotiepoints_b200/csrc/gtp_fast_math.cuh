@@ -85,11 +85,23 @@ GTP_DCONST(kV1, 0.5 * GTP_DEG2RAD * GTP_DEG2RAD);                              /
 GTP_DCONST(kV2, -0.125 * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD);
 GTP_DCONST(kV3, 0.0625 * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD);
 GTP_DCONST(kMaxRelHoriz, 0.01);
+GTP_DCONST(kMaxRelHorizWide, 0.1);   // polar quads (cos lat <= kMaxCosWide) up to here take the long series
+GTP_DCONST(kMaxCosWide, 0.3);
+// atan(t) = t (1 - t^2/3 + t^4/5 - ... + t^12/13) with t in degrees (|t| <= 0.112 rad: next term 3e-16 rad)
+GTP_DCONST(kLonC7, -GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD / 7.0);
+GTP_DCONST(kLonC9, GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD / 9.0);
+GTP_DCONST(kLonC11, -GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD / 11.0);
+GTP_DCONST(kLonC13, GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD / 13.0);
+// sqrt(1 + x) - 1 = x/2 - x^2/8 + x^3/16 - 5x^4/128 + 7x^5/256 - 21x^6/1024, x = (t deg2rad)^2
+GTP_DCONST(kV4, -5.0 / 128.0 * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD);
+GTP_DCONST(kV5, 7.0 / 256.0 * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD);
+GTP_DCONST(kV6, -21.0 / 1024.0 * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD * GTP_DEG2RAD);
 GTP_DCONST(kMaxRelZ, 2.0e-3);
 GTP_DCONST(kSmallHoriz, 2.5e-3);
 GTP_DCONST(kLatSwitch, 0.8);
 
-enum QuadMode { kSlow = 0, kLow = 1, kHigh = 2, kBoth = 3, kLowSmall = 5 };   // kLowSmall: kLow with Quad::small
+enum QuadMode { kSlow = 0, kLow = 1, kHigh = 2, kBoth = 3, kLowSmall = 5, kWide = 8 };   // kLowSmall: kLow with Quad::small
+// kWide: polar quad whose displacement is up to 10 % of its distance from the axis (8-term high-latitude series)
 
 // The reference's latitude switch: z < thr*R and z > -thr*R with thr = 0.8
 #define GTP_LAT_SWITCH 0.8
@@ -120,6 +132,7 @@ struct Quad {
     double s0;                           // z_A / R
     double a1, a2, a3, a4, a5;           // low-latitude series (degrees per w^k)
     double b1, b2, b3, b4, b5;           // high-latitude series (degrees per v^k), v = (rho-rho_A)/rho_A
+    double b6, b7, b8;                   // kWide only
     bool wrap;                           // lon may cross +-180
     bool small;                          // low-latitude quad small enough for the shortened series
 };
@@ -268,36 +281,58 @@ GTP_FD_COLD TieFull tie_full_library(double lon, double lat, double satz)
     return f;
 }
 
+// First tie row of a scan: full evaluation (library functions for out-of-range / NaN inputs).
+template <bool WITH_ZEN>
+GTP_FD void tie_first(TieGeo& g, TieZen& z, double lon, double lat, double satz)
+{
+    const double xl = lon * kDeg2Rad, xp = lat * kDeg2Rad, za = satz * kDeg2Rad;
+    if ((fabs(xl) <= 8.0) && (fabs(xp) <= 8.0) && (fabs(za) <= 8.0)) {
+        g.lon = lon; g.lat = lat;
+        sincos_bounded(xl, g.sl, g.cl);
+        sincos_bounded(xp, g.sp, g.cp);
+        if (WITH_ZEN) { z.za = za; sincos_bounded(za, z.sz, z.cz); tie_zen_phi(z); }
+    } else {
+        const TieFull f = tie_full_library(lon, lat, WITH_ZEN ? satz : 0.0);
+        g = f.g;
+        if (WITH_ZEN) z = f.z;
+    }
+}
+
+template <bool WITH_ZEN>
+GTP_FD_COLD TieFull tie_first_cold(double lon, double lat, double satz)
+{
+    TieFull f;
+    tie_first<WITH_ZEN>(f.g, f.z, lon, lat, satz);
+    return f;
+}
+
 // The tie point below `g` / `z` in the same tie column (the kernel walks down the ten tie rows of
 // a scan): consecutive rows are ~1 km apart, so the sines and cosines follow from the previous
 // row's by a small rotation (9 FMAs per angle instead of a 23-instruction sincos + quadrant
-// logic).  `first` (tie row 0 of a scan), steps beyond kIncMax (poles, the antimeridian),
-// NaN and out-of-range inputs take the full evaluation.
+// logic).  Steps beyond kIncMax (poles, the antimeridian), NaN and out-of-range inputs take the
+// full evaluation, out of line.
 template <bool WITH_ZEN>
-GTP_FD void tie_advance(TieGeo& g, TieZen& z, double lon, double lat, double satz, bool first)
+GTP_FD void tie_next(TieGeo& g, TieZen& z, double lon, double lat, double satz)
 {
     const double dl = (lon - g.lon) * kDeg2Rad, dp = (lat - g.lat) * kDeg2Rad;
     const double za = satz * kDeg2Rad, dzr = WITH_ZEN ? za - z.za : 0.0;
-    g.lon = lon; g.lat = lat;
-    if (WITH_ZEN) z.za = za;
-    const bool step = !first && (fabs(dl) <= kIncMax) && (fabs(dp) <= kIncMax) && (fabs(dzr) <= kIncMax);
-    if (step) {
+    if ((fabs(dl) <= kIncMax) && (fabs(dp) <= kIncMax) && (fabs(dzr) <= kIncMax)) {
+        g.lon = lon; g.lat = lat;
         rotate_small(g.sl, g.cl, dl);
         rotate_small(g.sp, g.cp, dp);
-        if (WITH_ZEN) rotate_small(z.sz, z.cz, dzr);
+        if (WITH_ZEN) { z.za = za; rotate_small(z.sz, z.cz, dzr); tie_zen_phi(z); }
     } else {
-        const double xl = lon * kDeg2Rad, xp = lat * kDeg2Rad;
-        if ((fabs(xl) <= 8.0) && (fabs(xp) <= 8.0) && (fabs(za) <= 8.0)) {
-            sincos_bounded(xl, g.sl, g.cl);
-            sincos_bounded(xp, g.sp, g.cp);
-            if (WITH_ZEN) sincos_bounded(za, z.sz, z.cz);
-        } else {
-            const TieFull f = tie_full_library(lon, lat, WITH_ZEN ? satz : 0.0);
-            g = f.g;
-            if (WITH_ZEN) z = f.z;
-        }
+        const TieFull f = tie_first_cold<WITH_ZEN>(lon, lat, satz);
+        g = f.g;
+        if (WITH_ZEN) z = f.z;
     }
-    if (WITH_ZEN) tie_zen_phi(z);
+}
+
+template <bool WITH_ZEN>
+GTP_FD void tie_advance(TieGeo& g, TieZen& z, double lon, double lat, double satz, bool first)
+{
+    if (first) tie_first<WITH_ZEN>(g, z, lon, lat, satz);
+    else tie_next<WITH_ZEN>(g, z, lon, lat, satz);
 }
 
 // Expansion / alignment of the quad whose upper corners are a (left) and b (right),
@@ -309,9 +344,11 @@ GTP_FD void tie_advance(TieGeo& g, TieZen& z, double lon, double lat, double sat
 //   theta_a - theta_b = dphi - dz;
 //   e = cos(zeta) - sqrt(cos(zeta)^2 - d^2) = (d^2 / 2 cos(zeta)) (1 + d^2 / 4 cos(zeta)^2)
 //   (d <= 7e-4, next term 1e-14 relative; the reference's own form cancels 7 digits there).
-// Returns false (ce, ca untouched) when the two zenith angles are too far apart for the
+// Returns false (ce, ca meaningless) when the two zenith angles are too far apart for the
 // small-argument series or so close that the reference's theta_a == theta_b test (:62) may
-// fire; the caller then uses quad_exp_ali_exact.
+// fire; the caller then uses quad_exp_ali_exact.  Straight-line on purpose: the check is the
+// last thing evaluated so that the compiler can interleave this dependent chain with the
+// quad projection that follows it in the kernel.
 GTP_FD bool quad_exp_ali(double za, double sza, double cza, double sphi_a, double cphi_a,
                          double zb, double sphi_b, double cphi_b, int km, double& ce, double& ca)
 {
@@ -319,7 +356,6 @@ GTP_FD bool quad_exp_ali(double za, double sza, double cza, double sphi_a, doubl
     // dphi = asin(sin(phi_b - phi_a))
     const double sd = fma(sphi_b, cphi_a, -(sphi_a * cphi_b));
     const double dz = zb - za;
-    if (!(fabs(sd) <= 0.01 && fabs(dz) <= 0.02 && fabs(dz) >= kDzMin)) return false;      // also catches NaN
     const double sd2 = sd * sd;
     const double dphi = fma(sd * sd2, fma(sd2, k3_40, kSixth), sd);
     // mean phi = phi_a + dphi / 2
@@ -347,7 +383,7 @@ GTP_FD bool quad_exp_ali(double za, double sza, double cza, double sphi_a, doubl
     const double u = (d * d) * inv_czeta;
     const double e = (0.5 * u) * fma(0.25 * u, inv_czeta, 1.0);
     ca = (e * szeta) * inv_den;
-    return true;
+    return fabs(sd) <= 0.01 && fabs(dz) <= 0.02 && fabs(dz) >= kDzMin;      // false for NaN
 }
 
 // the same coefficients, written exactly like the reference (:52-70), library functions
@@ -387,13 +423,12 @@ GTP_FD double absd(double x) { return fabs(x); }
 // the pixels this quad is evaluated at: 1 for the P pixels inside the quad (s_s <= 3/4, and
 // |ce|, |ca| <= 1/4 is part of the acceptance), kABoundExtra for the P pixels right of the last
 // quad (s_s <= 7/4, s_s (1 - s_s) >= -21/16).
-GTP_FD void quad_setup(Quad& q, const TieGeo& A, const Vec3& Axyz, const Vec3& B, const Vec3& C, const Vec3& D,
-                       double ce, double ca, double a_max)
-{
-    q.wrap = false;
-    q.small = false;
-    q.ce = ce; q.ca = ca;
+struct QuadSize { double horiz, wmax, inv_c; };
 
+// frame projection and size of the quad: straight-line
+GTP_FD QuadSize quad_project(Quad& q, const TieGeo& A, const Vec3& Axyz, const Vec3& B, const Vec3& C, const Vec3& D,
+                             double a_max)
+{
     const double inv_c = fast_rcp(A.cp);
     const double inv_rho = inv_c * kInvEarthR;
     const double inv_rho_deg = inv_rho * kRad2Deg;
@@ -411,15 +446,29 @@ GTP_FD void quad_setup(Quad& q, const TieGeo& A, const Vec3& Axyz, const Vec3& B
     const double horiz = a_max * fma(absd(q.Pe), kDeg2Rad, absd(q.Ph)) + kTBound * fma(absd(q.Qe), kDeg2Rad, absd(q.Qh))
                          + at_max * fma(absd(q.Se), kDeg2Rad, absd(q.Sh));
     const double wmax = a_max * absd(q.Pw) + kTBound * absd(q.Qw) + at_max * absd(q.Sw);
-    // written so that any NaN (lon/lat/satz) fails the test and takes the slow path
-    const bool ok = (horiz <= kMaxRelHoriz) && (wmax <= kMaxRelZ)
-                    && (absd(q.ce) <= 0.25) && (absd(q.ca) <= 0.25) && (A.cp > 1e-6);
-    if (!ok) { q.mode = kSlow; return; }
+    QuadSize sz; sz.horiz = horiz; sz.wmax = wmax; sz.inv_c = inv_c;
+    return sz;
+}
 
-    const double zr_lo = q.s0 - wmax, zr_hi = q.s0 + wmax;
+// acceptance test, evaluation mode and series coefficients
+GTP_FD void quad_classify(Quad& q, const TieGeo& A, const QuadSize& sz, double ce, double ca)
+{
+    const double horiz = sz.horiz, wmax = sz.wmax, inv_c = sz.inv_c;
+    q.wrap = false;
+    q.small = false;
+    q.ce = ce; q.ca = ca;
+    // written so that any NaN (lon/lat/satz) fails the test and takes the slow path
+    const bool sane = (wmax <= kMaxRelZ) && (absd(q.ce) <= 0.25) && (absd(q.ca) <= 0.25) && (A.cp > 1e-6);
+    const bool narrow = sane && (horiz <= kMaxRelHoriz);
+    // next to a pole the quad may span up to 10 % of its distance from the axis: longer series (kWide)
+    const bool wide = !narrow && sane && (horiz <= kMaxRelHorizWide) && (A.cp <= kMaxCosWide);
+    if (!(narrow || wide)) { q.mode = kSlow; return; }
+
+    const double as0 = absd(q.s0);
     const double margin = 1e-9;
-    if (zr_hi < kLatSwitch - margin && zr_lo > -kLatSwitch + margin) q.mode = kLow;
-    else if (zr_lo > kLatSwitch + margin || zr_hi < -kLatSwitch - margin) q.mode = kHigh;
+    if (wide) q.mode = kWide;
+    else if (as0 + wmax < kLatSwitch - margin) q.mode = kLow;          // z_hi < 0.8 R and z_lo > -0.8 R
+    else if (as0 - wmax > kLatSwitch + margin) q.mode = kHigh;         // z_lo > 0.8 R or z_hi < -0.8 R
     else q.mode = kBoth;
     q.wrap = (absd(q.lon0) + 1.05 * horiz * kRad2Deg) >= 180.0;
 
@@ -437,19 +486,34 @@ GTP_FD void quad_setup(Quad& q, const TieGeo& A, const Vec3& Axyz, const Vec3& B
         const double w2 = wmax * wmax;
         q.small = (q.mode == kLow) && (horiz <= kSmallHoriz) && (absd(q.a5) * (w2 * w2 * wmax) <= 2e-14);
     }
-    if (q.mode & kHigh) {
-        // lat = sign(z) * acos(rho / R);  rho / R = c * (1 + v),  v = (rho - rho_A) / rho_A.
-        // acos(c + c v) = |lat_A| - sum_k asinser_k(s -> c, c -> |s|) (c v)^k
-        const double c = A.cp, c2 = c * c, sa = absd(A.sp);
-        const double inv_s = fast_rcp(sa), u = inv_s * inv_s;
+    if (q.mode & (kHigh | kWide)) {
+        // lat = sign(z) * acos(rho / R);  rho / R = c (1 + v),  v = (rho - rho_A) / rho_A, c = cos(lat_A):
+        // lat = lat_A + sum_k b_k v^k with b_k = -sign(z) rad2deg c^k a_k, a_k the Taylor coefficients of
+        // asin around c.  They obey  a_{m+2} = (c (m+1)(2m+1) a_{m+1} + m^2 a_m) / ((1 - c^2)(m+2)(m+1)), so
+        //   b_{m+2} = (c^2/s^2) ((2m+1)/(m+2) b_{m+1} + m^2/((m+2)(m+1)) b_m),   b_1 = -sign(z) rad2deg c/s.
+        // kWide: 8 terms, (c v / s)^9 <= 5e-14 with c <= 0.3, |v| <= 0.1.
+        const double c = A.cp, sa = absd(A.sp);
+        const double inv_s = fast_rcp(sa);
+        const double cs = c * inv_s, kap = cs * cs;
         const double sgn = (A.sp < 0.0) ? kRad2Deg : -kRad2Deg;   // -sign(z) * rad2deg
-        double m = inv_s * c * sgn;
-        q.b1 = m;
-        m *= u * c; q.b2 = 0.5 * c * m;
-        m *= u * c; q.b3 = fma(2.0, c2, 1.0) * kSixth * m;
-        m *= u * c; q.b4 = c * fma(2.0, c2, 3.0) * 0.125 * m;
-        m *= u * c; q.b5 = fma(c2, fma(8.0, c2, 24.0), 3.0) * k1_40 * m;
+        q.b1 = cs * sgn;
+        q.b2 = kap * (0.5 * q.b1);
+        q.b3 = kap * fma(1.0 / 6.0, q.b1, q.b2);
+        q.b4 = kap * fma(1.25, q.b3, (1.0 / 3.0) * q.b2);
+        q.b5 = kap * fma(1.4, q.b4, 0.45 * q.b3);
+        if (wide) {
+            q.b6 = kap * fma(1.5, q.b5, (16.0 / 30.0) * q.b4);
+            q.b7 = kap * fma(11.0 / 7.0, q.b6, (25.0 / 42.0) * q.b5);
+            q.b8 = kap * fma(1.625, q.b7, (36.0 / 56.0) * q.b6);
+        }
     }
+}
+
+GTP_FD void quad_setup(Quad& q, const TieGeo& A, const Vec3& Axyz, const Vec3& B, const Vec3& C, const Vec3& D,
+                       double ce, double ca, double a_max)
+{
+    const QuadSize sz = quad_project(q, A, Axyz, B, C, D, a_max);
+    quad_classify(q, A, sz, ce, ca);
 }
 
 struct RowCoef {           // per (quad, fine row): the a_track-dependent half of the bilinear form
@@ -511,6 +575,39 @@ GTP_FD void pixel_eval(const Quad& q, const RowCoef& r, double a_col, double& lo
         const double zr = q.s0 + w;
         lat = (zr < kLatSwitch && zr > -kLatSwitch) ? la_low : la_high;
     }
+}
+
+// One fine pixel of a kWide quad (always wrap-checked: these quads sit next to a pole).
+GTP_FD void pixel_eval_wide(const Quad& q, const RowCoef& r, double a_col, double& lon, double& lat)
+{
+    const double e = fma(a_col, r.Ue, r.Ve);
+    const double h = fma(a_col, r.Uh, r.Vh);
+    const double g = 1.0 + h;
+    const double t = e * fast_rcp(g);
+    const double t2 = t * t;
+    double p = fma(t2, kLonC13, kLonC11);
+    p = fma(t2, p, kLonC9);
+    p = fma(t2, p, kLonC7);
+    p = fma(t2, p, kLonC5);
+    p = fma(t2, p, -kLonC3);
+    double lo = fma(t, fma(t2, p, 1.0), q.lon0);
+    if (lo > 180.0) lo -= 360.0;
+    else if (lo < -180.0) lo += 360.0;
+    lon = lo;
+    double sq = fma(t2, kV6, kV5);
+    sq = fma(t2, sq, kV4);
+    sq = fma(t2, sq, kV3);
+    sq = fma(t2, sq, kV2);
+    sq = fma(t2, sq, kV1);
+    const double v = fma(g, t2 * sq, h);
+    double b = fma(v, q.b8, q.b7);
+    b = fma(v, b, q.b6);
+    b = fma(v, b, q.b5);
+    b = fma(v, b, q.b4);
+    b = fma(v, b, q.b3);
+    b = fma(v, b, q.b2);
+    b = fma(v, b, q.b1);
+    lat = fma(v, b, q.lat0);
 }
 
 // ---- rounding-faithful per-pixel evaluation (fallback for quads the series cannot take) ----

@@ -47,8 +47,8 @@ static void run(const double* lon, const double* lat, const double* satz, long n
                 }
                 Quad q;
                 quad_setup(q, A, Ax, B, C, D, ce, cal, extra ? (double)kABoundExtra : 1.0);
-                mode_counts[q.mode]++;
-                if (q.mode != kSlow && q.small) mode_counts[4]++;
+                mode_counts[q.mode == kWide ? 5 : q.mode]++;
+                if (q.mode != kSlow && q.mode != kWide && q.small) mode_counts[4]++;
                 const int j0 = (qr == 0) ? 0 : qr * P + H;
                 const int j1 = (qr == L - 2) ? N : (qr + 1) * P + H;
                 for (int j = j0; j < j1; ++j) {
@@ -59,6 +59,7 @@ static void run(const double* lon, const double* lat, const double* satz, long n
                         double lo, la;
                         const double a_col = fma(s_s * (1.0 - s_s), q.ce, s_s);
                         if (q.mode == kSlow) { const LonLat ll = pixel_eval_slow(Ax, B, C, D, q.ce, q.ca, s_s, s_t); lo = ll.lon; la = ll.lat; }
+                        else if (q.mode == kWide) pixel_eval_wide(q, rc, a_col, lo, la);
                         else if (q.wrap) pixel_eval<kBoth, true>(q, rc, a_col, lo, la);
                         else if (q.small) pixel_eval<kLowSmall, false>(q, rc, a_col, lo, la);
                         else if (q.mode == kLow) pixel_eval<kLow, false>(q, rc, a_col, lo, la);
@@ -76,7 +77,7 @@ static void run(const double* lon, const double* lat, const double* satz, long n
 extern "C" int gtp_emul_simple_fast_f64(const double* lon, const double* lat, long n_scans, int fine_res,
                                         double* out_lon, double* out_lat, long* mode_counts)
 {
-    for (int k = 0; k < 5; ++k) mode_counts[k] = 0;
+    for (int k = 0; k < 6; ++k) mode_counts[k] = 0;
     if (fine_res == 250) run<4>(lon, lat, nullptr, n_scans, out_lon, out_lat, mode_counts, true);
     else if (fine_res == 500) run<2>(lon, lat, nullptr, n_scans, out_lon, out_lat, mode_counts, true);
     else return 1;
@@ -86,7 +87,7 @@ extern "C" int gtp_emul_simple_fast_f64(const double* lon, const double* lat, lo
 extern "C" int gtp_emul_cviirs_fast_f64(const double* lon, const double* lat, const double* satz, long n_scans,
                                         int fine_res, double* out_lon, double* out_lat, long* mode_counts)
 {
-    for (int k = 0; k < 5; ++k) mode_counts[k] = 0;
+    for (int k = 0; k < 6; ++k) mode_counts[k] = 0;
     if (fine_res == 250) run<4>(lon, lat, satz, n_scans, out_lon, out_lat, mode_counts);
     else if (fine_res == 500) run<2>(lon, lat, satz, n_scans, out_lon, out_lat, mode_counts);
     else return 1;

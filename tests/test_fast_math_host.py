@@ -33,22 +33,22 @@ def emul():
         ns, p = lon.shape[0] // 10, 1000 // fine
         out_lon = np.full((ns * 10 * p, 1354 * p), np.nan)
         out_lat = np.full_like(out_lon, np.nan)
-        modes = (ctypes.c_long * 5)()
+        modes = (ctypes.c_long * 6)()
         rc = lib.gtp_emul_cviirs_fast_f64(lon.ctypes.data_as(dp), lat.ctypes.data_as(dp), satz.ctypes.data_as(dp),
                                           ctypes.c_long(ns), fine, out_lon.ctypes.data_as(dp),
                                           out_lat.ctypes.data_as(dp), modes)
         assert rc == 0
-        return out_lon, out_lat, dict(zip(("slow", "low", "high", "both", "small"), modes))
+        return out_lon, out_lat, dict(zip(("slow", "low", "high", "both", "small", "wide"), modes))
 
     def run_simple(lon, lat, fine):
         ns, p = lon.shape[0] // 10, 1000 // fine
         out_lon = np.full((ns * 10 * p, 1354 * p), np.nan)
         out_lat = np.full_like(out_lon, np.nan)
-        modes = (ctypes.c_long * 5)()
+        modes = (ctypes.c_long * 6)()
         rc = lib.gtp_emul_simple_fast_f64(lon.ctypes.data_as(dp), lat.ctypes.data_as(dp), ctypes.c_long(ns), fine,
                                           out_lon.ctypes.data_as(dp), out_lat.ctypes.data_as(dp), modes)
         assert rc == 0
-        return out_lon, out_lat, dict(zip(("slow", "low", "high", "both", "small"), modes))
+        return out_lon, out_lat, dict(zip(("slow", "low", "high", "both", "small", "wide"), modes))
     run.simple = run_simple
     fp = ctypes.POINTER(ctypes.c_float)
 
@@ -56,12 +56,12 @@ def emul():
         ns, p = lon.shape[0] // 10, 1000 // fine
         out_lon = np.full((ns * 10 * p, 1354 * p), np.nan, np.float32)
         out_lat = np.full_like(out_lon, np.nan)
-        modes = (ctypes.c_long * 5)()
+        modes = (ctypes.c_long * 6)()
         rc = lib.gtp_emul_cviirs_fast_f32(lon.ctypes.data_as(fp), lat.ctypes.data_as(fp), satz.ctypes.data_as(fp),
                                           ctypes.c_long(ns), fine, out_lon.ctypes.data_as(fp),
                                           out_lat.ctypes.data_as(fp), modes)
         assert rc == 0
-        return out_lon, out_lat, dict(zip(("slow", "low", "high", "both", "small"), modes))
+        return out_lon, out_lat, dict(zip(("slow", "low", "high", "both", "small", "wide"), modes))
     run.f32 = run_f32
     return run
 
@@ -76,9 +76,10 @@ def test_fast_math_matches_oracle(emul, granule, fine):
 
 
 def test_every_mode_is_exercised(emul):
-    seen = {"slow": 0, "low": 0, "high": 0, "both": 0, "small": 0}
-    for granule in (0, 3, 5):
-        lon, lat, satz = testing.modis_granule(granule, n_scans=2)
+    seen = {"slow": 0, "low": 0, "high": 0, "both": 0, "small": 0, "wide": 0}
+    inputs = [testing.modis_granule(granule, n_scans=2) for granule in (0, 3, 5)]
+    inputs.append(testing.stress_granule("pole", n_scans=2))      # the pole itself: rounding-faithful fallback
+    for lon, lat, satz in inputs:
         for k, v in emul(lon, lat, satz, 250)[2].items():
             seen[k] += v
     assert all(v > 0 for v in seen.values()), seen
