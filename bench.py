@@ -464,6 +464,16 @@ def run_b200_arm(args, dtype):
             peak, peak_src = FALLBACK_HBM_GBS, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
         bpp = algorithmic_bytes_per_px(itemsize, cfg)
         achieved = bpp * px_per_rank_step / (kernel_ms_max * 1e-3) / 1e9
+        # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+        # (dram__bytes_read.sum + dram__bytes_write.sum), scaled to this run's granule count
+        traffic, traffic_src = None, None
+        try:
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_headline_traffic.json")))
+            if cap["config_name"] == args.config and cap["dtype"] == args.dtype and args.kernel == "auto":
+                traffic = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) * G / cap["granules_per_launch"]
+                traffic_src = cap["source"]
+        except (OSError, KeyError, ValueError):
+            pass
         line = {
             "metric": METRIC if headline else f"interpolated lon/lat pixels/sec ({args.config})",
             "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -485,7 +495,8 @@ def run_b200_arm(args, dtype):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "algorithmic_bytes": bpp * px_per_rank_step,
                          "kernel_ms": kernel_ms_max, "algorithmic_bytes_per_px": bpp,
                          "px_per_launch": int(px_per_rank_step)},
             "parity": parity,
