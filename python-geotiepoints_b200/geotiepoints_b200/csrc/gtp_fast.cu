@@ -66,8 +66,9 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // the fine rows [0, nrows) of one quad, first row at a_track = s_t0, branch-free per pixel
 template <int P, int MODE, bool WRAP>
 __device__ __forceinline__ void quad_rows(const Quad& q, const double (&a_col)[P], double s_t0, int nrows,
-                                          double* olon, double* olat)
+                                          double* out_lon, double* out_lat, long long out_idx)
 {
+    // one element index for both outputs (2 registers) instead of two running pointers (4)
     constexpr long long kPitch = (long long)kW * P;
     double s_t = s_t0;
 #pragma unroll 1
@@ -83,27 +84,29 @@ __device__ __forceinline__ void quad_rows(const Quad& q, const double (&a_col)[P
             else pixel_eval<MODE, WRAP>(q, rc, a_col[k], vlon[k], vlat[k]);
         }
 #endif
-        store_px<P>(olon, vlon);
-        store_px<P>(olat, vlat);
-        olon += kPitch; olat += kPitch;
+        store_px<P>(out_lon + out_idx, vlon);
+        store_px<P>(out_lat + out_idx, vlat);
+        out_idx += kPitch;
         s_t += 1.0 / P;              // exact: multiples of 1/8
     }
 }
 
 // The rarely taken evaluation modes (quads straddling |lat| = 53.13 deg or the antimeridian, polar
-// quads) run out of line on a copy of the quad, so that their coefficient sets (a1..a5 AND b1..b8)
-// do not weigh on the register allocation of the three hot loops.
+// quads).  Inlined on purpose: as a real (noinline) function this cost 25 % of the whole kernel even
+// on granules that never call it (the caller's register allocation around the call), and ptxas 12.9
+// turned the 256-bit vector store inside the non-entry function into a single 64-bit store - only
+// pixel 0 of 4 was written, caught by the antimeridian parity test (gpurun_out/per_granule.txt, ab10.txt).
 template <int P>
-__device__ __noinline__ void quad_rows_cold(const Quad* qp, const double* a_colp, double s_t0, int nrows,
-                                            double* olon, double* olat)
+__device__ __forceinline__ void quad_rows_cold(const Quad* qp, const double* a_colp, double s_t0, int nrows,
+                                            double* out_lon, double* out_lat, long long out_idx)
 {
     const Quad q = *qp;
     double a_col[P];
 #pragma unroll
     for (int k = 0; k < P; ++k) a_col[k] = a_colp[k];
-    if (q.mode == kWide) quad_rows<P, kWide, true>(q, a_col, s_t0, nrows, olon, olat);
-    else if (q.wrap) quad_rows<P, kBoth, true>(q, a_col, s_t0, nrows, olon, olat);
-    else quad_rows<P, kBoth, false>(q, a_col, s_t0, nrows, olon, olat);
+    if (q.mode == kWide) quad_rows<P, kWide, true>(q, a_col, s_t0, nrows, out_lon, out_lat, out_idx);
+    else if (q.wrap) quad_rows<P, kBoth, true>(q, a_col, s_t0, nrows, out_lon, out_lat, out_idx);
+    else quad_rows<P, kBoth, false>(q, a_col, s_t0, nrows, out_lon, out_lat, out_idx);
 }
 
 // SIMPLE = true is simple_modis_interpolator: the same bilinear form with a_scan = s_s and
@@ -136,11 +139,9 @@ modis_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restri
     const int quad_col = extra ? kW - 2 : c;
     const int xoff = extra ? P : 0;
 
-    const double* plon = lon + scan * (long long)(kL * kW) + tc;
-    const double* plat = lat + scan * (long long)(kL * kW) + tc;
-    const double* psatz = SIMPLE ? nullptr : satz + scan * (long long)(kL * kW) + tc;
-    double* olon = out_lon + scan * (long long)kN * kWf + (long long)quad_col * P + xoff;
-    double* olat = out_lat + scan * (long long)kN * kWf + (long long)quad_col * P + xoff;
+    // element indices instead of five running pointers: the bases are kernel parameters (uniform)
+    long long tie_idx = scan * (long long)(kL * kW) + tc;
+    long long out_idx = scan * (long long)kN * kWf + (long long)quad_col * P + xoff;
 
     // carried from the tie row above: this lane's tie point (frame + anchor; the next row's sines
     // and cosines are rotated out of it), corner B, and the quad row's expansion / alignment
@@ -150,9 +151,9 @@ modis_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restri
     Vec3 topB = {0.0, 0.0, 0.0};
     double top_ce = 0.0, top_ca = 0.0;
     __shared__ double stage[2][3][kThreads];     // double-buffered next-row inputs, one slot per thread
-    cp_async8(&stage[0][0][threadIdx.x], plon);
-    cp_async8(&stage[0][1][threadIdx.x], plat);
-    if (!SIMPLE) cp_async8(&stage[0][2][threadIdx.x], psatz);
+    cp_async8(&stage[0][0][threadIdx.x], lon + tie_idx);
+    cp_async8(&stage[0][1][threadIdx.x], lat + tie_idx);
+    if (!SIMPLE) cp_async8(&stage[0][2][threadIdx.x], satz + tie_idx);
     cp_async_commit();
 
 #pragma unroll 1
@@ -161,10 +162,10 @@ modis_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restri
         const double clon = stage[r & 1][0][threadIdx.x], clat = stage[r & 1][1][threadIdx.x];
         const double csatz = SIMPLE ? 0.0 : stage[r & 1][2][threadIdx.x];
         if (r + 1 < kL) {            // fetch the next tie row while this one is worked on
-            plon += kW; plat += kW;
-            cp_async8(&stage[(r + 1) & 1][0][threadIdx.x], plon);
-            cp_async8(&stage[(r + 1) & 1][1][threadIdx.x], plat);
-            if (!SIMPLE) { psatz += kW; cp_async8(&stage[(r + 1) & 1][2][threadIdx.x], psatz); }
+            tie_idx += kW;
+            cp_async8(&stage[(r + 1) & 1][0][threadIdx.x], lon + tie_idx);
+            cp_async8(&stage[(r + 1) & 1][1][threadIdx.x], lat + tie_idx);
+            if (!SIMPLE) cp_async8(&stage[(r + 1) & 1][2][threadIdx.x], satz + tie_idx);
             cp_async_commit();
         }
         // this lane's tie point of row r; corner B of the lane's quad column comes from lane + 1
@@ -201,21 +202,24 @@ modis_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restri
             if (q.mode != kSlow) {
                 // s_s + s_s (1 - s_s) c_exp  (:341, :344); s_s = k / P inside the quad, 1 + k / P right of it
                 double a_col[P];
-                const double s_base = extra ? 1.0 : 0.0;
+                double s_base = extra ? 1.0 : 0.0;
+                // SIMPLE: a_col = s_s does not depend on the quad; keep the compiler from hoisting the P
+                // values out of the tie-row loop, where they would cost 2 P registers through every loop
+                if (SIMPLE) asm volatile("" : "+d"(s_base));
 #pragma unroll
                 for (int k = 0; k < P; ++k) {
                     const double s_s = s_base + (double)k / (double)P;
-                    a_col[k] = fma(s_s * (1.0 - s_s), q.ce, s_s);
+                    a_col[k] = SIMPLE ? s_s : fma(s_s * (1.0 - s_s), q.ce, s_s);
                 }
-                if (!q.wrap && q.small) quad_rows<P, kLowSmall, false>(q, a_col, s_t0, nrows, olon, olat);
-                else if (!q.wrap && q.mode == kLow) quad_rows<P, kLow, false>(q, a_col, s_t0, nrows, olon, olat);
-                else if (!q.wrap && q.mode == kHigh) quad_rows<P, kHigh, false>(q, a_col, s_t0, nrows, olon, olat);
+                if (!q.wrap && q.small) quad_rows<P, kLowSmall, false>(q, a_col, s_t0, nrows, out_lon, out_lat, out_idx);
+                else if (!q.wrap && q.mode == kLow) quad_rows<P, kLow, false>(q, a_col, s_t0, nrows, out_lon, out_lat, out_idx);
+                else if (!q.wrap && q.mode == kHigh) quad_rows<P, kHigh, false>(q, a_col, s_t0, nrows, out_lon, out_lat, out_idx);
                 else {
                     const Quad qc = q;
                     double a_colc[P];
 #pragma unroll
                     for (int k = 0; k < P; ++k) a_colc[k] = a_col[k];
-                    quad_rows_cold<P>(&qc, a_colc, s_t0, nrows, olon, olat);
+                    quad_rows_cold<P>(&qc, a_colc, s_t0, nrows, out_lon, out_lat, out_idx);
                 }
             } else {
 #pragma unroll 1
@@ -228,12 +232,11 @@ modis_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restri
                                                           (double)(xoff + k) / (double)P, s_t);
                         vlon[k] = ll.lon; vlat[k] = ll.lat;
                     }
-                    store_px<P>(olon + (long long)m * kWf, vlon);
-                    store_px<P>(olat + (long long)m * kWf, vlat);
+                    store_px<P>(out_lon + out_idx + (long long)m * kWf, vlon);
+                    store_px<P>(out_lat + out_idx + (long long)m * kWf, vlat);
                 }
             }
-            olon += (long long)nrows * kWf;
-            olat += (long long)nrows * kWf;
+            out_idx += (long long)nrows * kWf;
         }
         top = own;
         topB = curB;
