@@ -392,22 +392,26 @@ def run_b200_arm(args, dtype):
     total_px = px_per_rank_step * world * args.steps
     value = total_px / (elapsed_ms * 1e-3)
 
-    # -- parity spot check (not timed): 8 scans of this rank against the oracle ---------
+    # -- parity spot check (not timed): 12 scans spread over this rank's batch (every latitude band it
+    # holds, incl. polar and antimeridian scans) against the oracle --------------------------------
     parity = None
     if rank == 0:
         try:
             sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))
             import gtp_oracle
             from parity import compare
-            ns = 8
-            sub = [a[:ns * rows_per_scan] for a in host_in]
+            picks = np.unique(np.linspace(0, n_scans - 1, 12).astype(np.int64))
+            in_rows = np.concatenate([np.arange(s * rows_per_scan, (s + 1) * rows_per_scan) for s in picks])
+            out_rows = np.concatenate([np.arange(s * out_rows_per_scan, (s + 1) * out_rows_per_scan) for s in picks])
+            sub = [np.ascontiguousarray(a[in_rows]) for a in host_in]
             with np.errstate(all="ignore"):
                 if cfg["kind"] == "cviirs":
                     exp = gtp_oracle.cviirs(*sub, cfg["coarse"], cfg["fine"], cfg["width"], n_threads=8)
                 else:
                     exp = gtp_oracle.simple(*sub, cfg["coarse"], cfg["fine"], n_threads=8)
-            parity = compare(out_lon[:ns * out_rows_per_scan].cpu().numpy(),
-                             out_lat[:ns * out_rows_per_scan].cpu().numpy(), *exp)
+            idx = torch.from_numpy(out_rows).to(device)
+            parity = compare(out_lon[idx].cpu().numpy(), out_lat[idx].cpu().numpy(), *exp)
+            parity["scans_checked"] = [int(s) for s in picks]
         except Exception as exc:  # the checker must never take the measurement down
             parity = {"error": repr(exc)}
 

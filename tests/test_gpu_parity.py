@@ -56,6 +56,26 @@ def test_cviirs_synthetic_granules_1km(granule, dtype):
         assert_parity(*got, *exp, what=f"granule {granule} 1km->{fine} {np.dtype(dtype).name}")
 
 
+@pytest.mark.parametrize("granule", [4, 14, 24, 34])
+def test_polar_granules_sampled_scans(granule):
+    """Scans spread over the granules that sweep over a pole (the first 12 scans of a granule never get
+    there): long polar series, wrap-around quads and the rounding-faithful fallback on the GPU, for the
+    CVIIRS and the simple interpolator."""
+    lon, lat, satz = testing.modis_granule(granule)
+    picks = np.concatenate([np.arange(s * 10, s * 10 + 10) for s in range(0, 203, 17)])
+    lon, lat, satz = (np.ascontiguousarray(a[picks]) for a in (lon, lat, satz))
+    assert np.abs(lat).max() > 88.0
+    for fine in (250, 500):
+        got = interpolate(lon, lat, satz, coarse_resolution=1000, fine_resolution=fine)
+        exp = _oracle_cviirs((lon, lat, satz), 1000, fine, 0)
+        assert_parity(*got, *exp, what=f"polar granule {granule} 1km->{fine}")
+        got = simple_modis_interpolator.interpolate_geolocation_cartesian(
+            lon, lat, coarse_resolution=1000, fine_resolution=fine)
+        with np.errstate(all="ignore"):
+            exp = gtp_oracle.simple(lon, lat, 1000, fine, n_threads=8)
+        assert_parity(*got, *exp, what=f"polar granule {granule} simple 1km->{fine}")
+
+
 @pytest.mark.parametrize("dtype", DTYPES, ids=lambda d: np.dtype(d).name)
 def test_cviirs_full_granule_5km(dtype):
     """BASELINE config 3: 406 x 271|270 tie points -> 2030 x 1354."""
