@@ -131,6 +131,7 @@ struct Quad {
     double lon0, lat0;                   // anchor, degrees
     double s0;                           // z_A / R
     double a1, a2, a3, a4, a5;           // low-latitude series (degrees per w^k)
+    double a6, a7, a8;                   // 5 km quads only (quad_classify_long)
     double b1, b2, b3, b4, b5;           // high-latitude series (degrees per v^k), v = (rho-rho_A)/rho_A
     double b6, b7, b8;                   // kWide only
     bool wrap;                           // lon may cross +-180
@@ -583,6 +584,130 @@ GTP_FD void pixel_eval(const Quad& q, const RowCoef& r, double a_col, double& lo
         lat = (zr < kLatSwitch && zr > -kLatSwitch) ? la_low : la_high;
     }
 }
+
+// ---- 5 km tie points: the same anchor-relative evaluation with 8-term series ---------------------
+// A 5 km quad spans 5 x 5 ... 25 x 5 km and is extrapolated to a_track = -0.4 ... 1.4 and, at the
+// swath edges, a_scan = -0.4 ... 2.2 (_get_coords_5km, :231-249): displacements of up to 60 km from
+// corner A.  The series are therefore taken to the 8th order with coefficients from the Taylor
+// recurrence of asin around x0 (1 - x0^2 = q):
+//     a_{m+2} = (x0 (2m+1)/(m+2) a_{m+1} + m^2/((m+2)(m+1)) a_m) / q,
+// low latitudes: x0 = sin(lat_A), variable w = dz/R; high latitudes: x0 = cos(lat_A), variable c v
+// (folded into b_k, see quad_classify).  A quad is accepted when the 9th term is below 1e-13 deg
+// over the quad's extent, |t| <= 0.11 (atan to t^13) - otherwise the rounding-faithful formulas.
+GTP_DCONST(kLongTerm, 1.0e-13);
+
+GTP_FD void quad_classify_long(Quad& q, const TieGeo& A, const QuadSize& sz, double ce, double ca)
+{
+    const double horiz = sz.horiz, wmax = sz.wmax, inv_c = sz.inv_c;
+    q.wrap = false;
+    q.small = false;
+    q.ce = ce; q.ca = ca;
+    const bool sane = (horiz <= kMaxRelHorizWide) && (wmax <= 0.05)
+                      && (absd(q.ce) <= 0.25) && (absd(q.ca) <= 0.25) && (A.cp > 1e-6);
+    if (!sane) { q.mode = kSlow; return; }
+    const double as0 = absd(q.s0);
+    const double margin = 1e-9;
+    if (as0 + wmax < kLatSwitch - margin) q.mode = kLow;
+    else if (as0 - wmax > kLatSwitch + margin) q.mode = kHigh;
+    else q.mode = kBoth;
+    q.wrap = (absd(q.lon0) + 1.05 * horiz * kRad2Deg) >= 180.0;
+
+    bool ok = true;
+    if (q.mode & kLow) {
+        const double s = A.sp, u = inv_c * inv_c, su = s * u;
+        q.a1 = inv_c * kRad2Deg;
+        q.a2 = (0.5 * su) * q.a1;
+        q.a3 = fma(su, q.a2, ((1.0 / 6.0) * u) * q.a1);
+        q.a4 = fma(1.25 * su, q.a3, ((1.0 / 3.0) * u) * q.a2);
+        q.a5 = fma(1.4 * su, q.a4, (0.45 * u) * q.a3);
+        q.a6 = fma(1.5 * su, q.a5, ((16.0 / 30.0) * u) * q.a4);
+        q.a7 = fma((11.0 / 7.0) * su, q.a6, ((25.0 / 42.0) * u) * q.a5);
+        q.a8 = fma(1.625 * su, q.a7, ((36.0 / 56.0) * u) * q.a6);
+        const double a9 = fma((15.0 / 9.0) * su, q.a8, ((49.0 / 72.0) * u) * q.a7);
+        const double w2 = wmax * wmax, w4 = w2 * w2;
+        ok = ok && (absd(a9) * (w4 * w4 * wmax) <= kLongTerm);
+    }
+    if (q.mode & kHigh) {
+        const double c = A.cp, sa = absd(A.sp);
+        const double inv_s = fast_rcp(sa);
+        const double cs = c * inv_s, kap = cs * cs;
+        const double sgn = (A.sp < 0.0) ? kRad2Deg : -kRad2Deg;   // -sign(z) * rad2deg
+        q.b1 = cs * sgn;
+        q.b2 = kap * (0.5 * q.b1);
+        q.b3 = kap * fma(1.0 / 6.0, q.b1, q.b2);
+        q.b4 = kap * fma(1.25, q.b3, (1.0 / 3.0) * q.b2);
+        q.b5 = kap * fma(1.4, q.b4, 0.45 * q.b3);
+        q.b6 = kap * fma(1.5, q.b5, (16.0 / 30.0) * q.b4);
+        q.b7 = kap * fma(11.0 / 7.0, q.b6, (25.0 / 42.0) * q.b5);
+        q.b8 = kap * fma(1.625, q.b7, (36.0 / 56.0) * q.b6);
+        const double b9 = kap * fma(15.0 / 9.0, q.b8, (49.0 / 72.0) * q.b7);
+        const double vmax = 1.1 * horiz;                      // v = h + g (sqrt(1 + t^2) - 1)
+        const double v2 = vmax * vmax, v4 = v2 * v2;
+        ok = ok && (absd(b9) * (v4 * v4 * vmax) <= kLongTerm);
+    }
+    if (!ok) q.mode = kSlow;
+}
+
+// One fine pixel of a 5 km quad.  MODE = kLow | kHigh | kBoth (kBoth also does the +-180 wrap).
+template <int MODE>
+GTP_FD void pixel_eval_long(const Quad& q, const RowCoef& r, double a_col, double& lon, double& lat)
+{
+    const double e = fma(a_col, r.Ue, r.Ve);
+    const double h = fma(a_col, r.Uh, r.Vh);
+    const double g = 1.0 + h;
+    const double t = e * fast_rcp(g);
+    const double t2 = t * t;
+    double p = fma(t2, kLonC13, kLonC11);
+    p = fma(t2, p, kLonC9);
+    p = fma(t2, p, kLonC7);
+    p = fma(t2, p, kLonC5);
+    p = fma(t2, p, -kLonC3);
+    double lo = fma(t, fma(t2, p, 1.0), q.lon0);
+    if (MODE == kBoth) {
+        if (lo > 180.0) lo -= 360.0;
+        else if (lo < -180.0) lo += 360.0;
+    }
+    lon = lo;
+    double la_low = 0.0, la_high = 0.0, w = 0.0;
+    if (MODE & kLow) {
+        w = fma(a_col, r.Uw, r.Vw);
+        double a = fma(w, q.a8, q.a7);
+        a = fma(w, a, q.a6);
+        a = fma(w, a, q.a5);
+        a = fma(w, a, q.a4);
+        a = fma(w, a, q.a3);
+        a = fma(w, a, q.a2);
+        a = fma(w, a, q.a1);
+        la_low = fma(w, a, q.lat0);
+    }
+    if (MODE & kHigh) {
+        double sq = fma(t2, kV6, kV5);
+        sq = fma(t2, sq, kV4);
+        sq = fma(t2, sq, kV3);
+        sq = fma(t2, sq, kV2);
+        sq = fma(t2, sq, kV1);
+        const double v = fma(g, t2 * sq, h);
+        double b = fma(v, q.b8, q.b7);
+        b = fma(v, b, q.b6);
+        b = fma(v, b, q.b5);
+        b = fma(v, b, q.b4);
+        b = fma(v, b, q.b3);
+        b = fma(v, b, q.b2);
+        b = fma(v, b, q.b1);
+        la_high = fma(v, b, q.lat0);
+    }
+    if (MODE == kLow) lat = la_low;
+    else if (MODE == kHigh) lat = la_high;
+    else {
+        const double zr = q.s0 + w;
+        lat = (zr < kLatSwitch && zr > -kLatSwitch) ? la_low : la_high;
+    }
+}
+
+// sub-pixel coordinate x[i] of _get_coords_5km (a5) for fine column i of a 5 km -> 1 km scan and
+// the quad column it belongs to (a7): F5 = 2 partial columns left, 2 (W = 271) or 7 (W = 270) right
+GTP_FD int quad_col_5km(int i, int W) { const int c = (i >= 2) ? (i - 2) / 5 : 0; return c > W - 2 ? W - 2 : c; }
+GTP_FD int coord_x_5km(int i, int W) { return i - 2 - 5 * quad_col_5km(i, W); }
 
 // One fine pixel of a kWide quad (always wrap-checked: these quads sit next to a pole).
 GTP_FD void pixel_eval_wide(const Quad& q, const RowCoef& r, double a_col, double& lon, double& lat)

@@ -20,6 +20,12 @@ cudaError_t gtp_launch_simple_fast_f64(const double* lon, const double* lat, dou
                                        long long n_scans, int res, cudaStream_t stream);
 bool gtp_simple_fast_f64_supported(int width, int res);
 
+// gtp_fast5.cu: float64 5 km -> 1 km fast path (271 or 270 tie columns)
+cudaError_t gtp_launch_cviirs_fast5_f64(const double* lon, const double* lat, const double* satz,
+                                        double* out_lon, double* out_lat,
+                                        long long n_scans, const CviirsCfg& cfg, cudaStream_t stream);
+bool gtp_cviirs_fast5_f64_supported(const CviirsCfg& cfg);
+
 // gtp_fast_f32.cu: float32 CVIIRS 1 km fast path (rounding-faithful blend, anchor-relative back-transform)
 cudaError_t gtp_launch_cviirs_fast_f32(const float* lon, const float* lat, const float* satz,
                                        float* out_lon, float* out_lat,

@@ -95,6 +95,54 @@ extern "C" int gtp_emul_cviirs_fast_f64(const double* lon, const double* lat, co
 }
 
 
+// ---- float64 5 km -> 1 km fast path (csrc/gtp_fast5.cu) ------------------------------------------
+extern "C" int gtp_emul_cviirs_fast5_f64(const double* lon, const double* lat, const double* satz, long n_scans,
+                                         int W, double* out_lon, double* out_lat, long* mode_counts)
+{
+    for (int k = 0; k < 6; ++k) mode_counts[k] = 0;
+    if (W != 270 && W != 271) return 1;
+    const int Wf = 1354, nq = W - 1;
+    for (long s = 0; s < n_scans; ++s) {
+        for (int qc = 0; qc < nq; ++qc) {
+            TieGeo top[2], bot[2];
+            TieZen zen[2], unused = {0.0, 0.0, 1.0, 0.0, 1.0};
+            for (int k = 0; k < 2; ++k) {
+                const long o = (s * 2) * W + qc + k;
+                top[k] = TieGeo{0.0, 1.0, 0.0, 1.0, 0.0, 0.0};
+                zen[k] = TieZen{0.0, 0.0, 1.0, 0.0, 1.0};
+                tie_first<true>(top[k], zen[k], lon[o], lat[o], satz[o]);
+                bot[k] = top[k];
+                tie_next<false>(bot[k], unused, lon[o + W], lat[o + W], 0.0);
+            }
+            const Vec3 A = tie_xyz(top[0]), B = tie_xyz(top[1]), D = tie_xyz(bot[0]), C = tie_xyz(bot[1]);
+            double ce, cal;
+            quad_coefficients(zen[0], zen[1].za, zen[1].sphi, zen[1].cphi, 5, ce, cal);
+            const double a_max = (qc != nq - 1) ? 1.0 : (W == 271 ? 1.4 : 3.0);
+            Quad q;
+            const QuadSize sz = quad_project(q, top[0], A, B, C, D, a_max);
+            quad_classify_long(q, top[0], sz, ce, cal);
+            mode_counts[q.mode]++;
+            const int i0 = (qc == 0) ? 0 : 2 + 5 * qc, i1 = (qc == nq - 1) ? Wf : 2 + 5 * qc + 5;
+            for (int j = 0; j < 10; ++j) {
+                const double s_t = (double)(j - 2) / 5.0;
+                const RowCoef rc = (q.mode != kSlow) ? row_setup(q, s_t, s_t * (1.0 - s_t)) : RowCoef();
+                for (int i = i0; i < i1; ++i) {
+                    const double s_s = (double)coord_x_5km(i, W) / 5.0;
+                    const double a_col = fma(s_s * (1.0 - s_s), q.ce, s_s);
+                    double lo, la;
+                    if (q.mode == kSlow) { const LonLat ll = pixel_eval_slow(A, B, C, D, q.ce, q.ca, s_s, s_t); lo = ll.lon; la = ll.lat; }
+                    else if (!q.wrap && q.mode == kLow) pixel_eval_long<kLow>(q, rc, a_col, lo, la);
+                    else if (!q.wrap && q.mode == kHigh) pixel_eval_long<kHigh>(q, rc, a_col, lo, la);
+                    else pixel_eval_long<kBoth>(q, rc, a_col, lo, la);
+                    const long o = (s * 10 + j) * (long)Wf + i;
+                    out_lon[o] = lo; out_lat[o] = la;
+                }
+            }
+        }
+    }
+    return 0;
+}
+
 // ---- float32 fast path (gtp_fast_f32_math.cuh) -------------------------------------------------
 template <int P>
 static void run_f32(const float* lon, const float* lat, const float* satz, long n_scans,

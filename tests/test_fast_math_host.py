@@ -50,6 +50,18 @@ def emul():
         assert rc == 0
         return out_lon, out_lat, dict(zip(("slow", "low", "high", "both", "small", "wide"), modes))
     run.simple = run_simple
+
+    def run_5km(lon, lat, satz):
+        ns, w = lon.shape[0] // 2, lon.shape[1]
+        out_lon = np.full((ns * 10, 1354), np.nan)
+        out_lat = np.full_like(out_lon, np.nan)
+        modes = (ctypes.c_long * 6)()
+        rc = lib.gtp_emul_cviirs_fast5_f64(lon.ctypes.data_as(dp), lat.ctypes.data_as(dp), satz.ctypes.data_as(dp),
+                                           ctypes.c_long(ns), w, out_lon.ctypes.data_as(dp),
+                                           out_lat.ctypes.data_as(dp), modes)
+        assert rc == 0
+        return out_lon, out_lat, dict(zip(("slow", "low", "high", "both", "small", "wide"), modes))
+    run.five_km = run_5km
     fp = ctypes.POINTER(ctypes.c_float)
 
     def run_f32(lon, lat, satz, fine):
@@ -94,6 +106,30 @@ def test_fast_math_stress_inputs(emul, golden_inputs, name):
         with np.errstate(all="ignore"):
             exp = gtp_oracle.cviirs(lon, lat, satz, 1000, fine)
         assert_parity(got_lon, got_lat, *exp, what=f"host emulation {name} -> {fine} m, modes {modes}")
+
+
+@pytest.mark.parametrize("width", [271, 270])
+@pytest.mark.parametrize("granule", [0, 3, 4, 5, 14, 34, 287])
+def test_5km_fast_math_matches_oracle(emul, granule, width):
+    """5 km -> 1 km: the 8-term series of csrc/gtp_fast5.cu against the oracle, whole granules (406 tie
+    rows) incl. the ones that sweep over a pole."""
+    lon, lat, satz = testing.subsample_5km(*testing.modis_granule(granule), width=width)
+    got_lon, got_lat, modes = emul.five_km(lon, lat, satz)
+    with np.errstate(all="ignore"):
+        exp = gtp_oracle.cviirs(lon, lat, satz, 5000, 1000, width, n_threads=8)
+    assert_parity(got_lon, got_lat, *exp, what=f"host emulation 5km({width}) granule {granule}, modes {modes}")
+
+
+@pytest.mark.parametrize("name", ["antimeridian", "pole", "south_pole", "prime_meridian", "lat_switch",
+                                  "symmetric_satz", "zeros", "nan_holes"])
+def test_5km_fast_math_stress_inputs(emul, golden_inputs, name):
+    from cases import cviirs_inputs
+    for width in (271, 270):
+        lon, lat, satz = cviirs_inputs(golden_inputs[name], 5000, width, np.float64)
+        got_lon, got_lat, modes = emul.five_km(lon, lat, satz)
+        with np.errstate(all="ignore"):
+            exp = gtp_oracle.cviirs(lon, lat, satz, 5000, 1000, width)
+        assert_parity(got_lon, got_lat, *exp, what=f"host emulation 5km({width}) {name}, modes {modes}")
 
 
 def test_unphysical_inputs_fall_back(emul):
