@@ -44,6 +44,8 @@ CONFIGS = {
     "cviirs_5km_1km_270": dict(kind="cviirs", coarse=5000, fine=1000, width=270, n_in=3, tie_rows=406, tie_cols=270, f=5, out_cols=1354),
     "simple_1km_250m": dict(kind="simple", coarse=1000, fine=250, width=0, n_in=2, tie_rows=2030, tie_cols=1354, f=4, out_cols=5416),
     "simple_1km_500m": dict(kind="simple", coarse=1000, fine=500, width=0, n_in=2, tie_rows=2030, tie_cols=1354, f=2, out_cols=2708),
+    # extension: float32 lon/lat + int16 zenith in, float64 math, float32 out (--dtype is ignored)
+    "mod03_1km_250m": dict(kind="mixed", coarse=1000, fine=250, width=0, n_in=3, tie_rows=2030, tie_cols=1354, f=4, out_cols=5416),
 }
 TIE_ROWS, TIE_COLS = 2030, 1354
 OUT_ROWS, OUT_COLS = 8120, 5416
@@ -58,6 +60,8 @@ def algorithmic_bytes_per_px(itemsize, cfg=None):
     """Each input element read once, each output written once: 17.5 B/px for
     CVIIRS 1 km -> 250 m float64."""
     cfg = cfg or CONFIGS["cviirs_1km_250m"]
+    if cfg["kind"] == "mixed":      # 2 x float32 out; float32 + float32 + int16 in
+        return 2 * 4 + (4 + 4 + 2) * (cfg["tie_rows"] * cfg["tie_cols"]) / px_per_granule(cfg)
     return 2 * itemsize + cfg["n_in"] * itemsize * (cfg["tie_rows"] * cfg["tie_cols"]) / px_per_granule(cfg)
 
 
@@ -303,12 +307,17 @@ def run_b200_arm(args, dtype):
 
     cfg = CONFIGS[args.config]
     headline = args.config == "cviirs_1km_250m"
+    mixed = cfg["kind"] == "mixed"
+    if mixed:
+        dtype, args.dtype = np.float32, "f32"
     tdtype = torch.float64 if dtype == np.float64 else torch.float32
     itemsize = np.dtype(dtype).itemsize
     G = args.granules_per_gpu
     # rank r owns the contiguous scan range of granules [r*G, (r+1)*G) of the day
     g_lo, g_hi = sharding.granule_range(rank, world, G * world)
     host_in = make_granules(g_lo, g_hi - g_lo, dtype, cfg)
+    if mixed:       # MOD03 layout: SensorZenith as int16 * 0.01
+        host_in = (host_in[0], host_in[1], np.round(host_in[2].astype(np.float64) / 0.01).astype(np.int16))
     lon, lat = host_in[0], host_in[1]
     rows_per_scan = 10 if cfg["coarse"] == 1000 else 2
     n_scans = lon.shape[0] // rows_per_scan
@@ -318,8 +327,9 @@ def run_b200_arm(args, dtype):
     out_lat = torch.empty_like(out_lon)
     lib = _capi.lib()
     suffix = "f64" if dtype == np.float64 else "f32"
-    generic = args.kernel == "generic" and (suffix == "f64" or cfg["kind"] == "cviirs")
-    fn = getattr(lib, f"gtp_{cfg['kind']}_interp_" + (("generic_" + suffix) if generic else suffix))
+    generic = args.kernel == "generic" and (suffix == "f64" or cfg["kind"] == "cviirs") and not mixed
+    fn = lib.gtp_cviirs_interp_mixed if mixed else \
+        getattr(lib, f"gtp_{cfg['kind']}_interp_" + (("generic_" + suffix) if generic else suffix))
     stream = torch.cuda.current_stream(device)
     if cfg["kind"] == "cviirs":
         scalars = (cfg["coarse"], cfg["fine"], cfg["width"])
@@ -327,8 +337,12 @@ def run_b200_arm(args, dtype):
         scalars = (cfg["tie_cols"], cfg["coarse"] // cfg["fine"])
 
     def step():
-        rc = fn(*[t.data_ptr() for t in d_in], n_scans, *scalars,
-                out_lon.data_ptr(), out_lat.data_ptr(), local_rank, ctypes.c_void_p(stream.cuda_stream))
+        if mixed:
+            rc = fn(*[t.data_ptr() for t in d_in], 1, 0.01, 0.0, n_scans, cfg["fine"],
+                    out_lon.data_ptr(), out_lat.data_ptr(), 0, local_rank, ctypes.c_void_p(stream.cuda_stream))
+        else:
+            rc = fn(*[t.data_ptr() for t in d_in], n_scans, *scalars,
+                    out_lon.data_ptr(), out_lat.data_ptr(), local_rank, ctypes.c_void_p(stream.cuda_stream))
         _capi.check(rc)
 
     def barrier():
@@ -405,7 +419,11 @@ def run_b200_arm(args, dtype):
             out_rows = np.concatenate([np.arange(s * out_rows_per_scan, (s + 1) * out_rows_per_scan) for s in picks])
             sub = [np.ascontiguousarray(a[in_rows]) for a in host_in]
             with np.errstate(all="ignore"):
-                if cfg["kind"] == "cviirs":
+                if mixed:       # the float64 reference on the widened inputs, rounded once
+                    exp = gtp_oracle.cviirs(sub[0].astype(np.float64), sub[1].astype(np.float64),
+                                            sub[2].astype(np.float64) * 0.01, 1000, cfg["fine"], 0, n_threads=8)
+                    exp = tuple(a.astype(np.float32) for a in exp)
+                elif cfg["kind"] == "cviirs":
                     exp = gtp_oracle.cviirs(*sub, cfg["coarse"], cfg["fine"], cfg["width"], n_threads=8)
                 else:
                     exp = gtp_oracle.simple(*sub, cfg["coarse"], cfg["fine"], n_threads=8)
@@ -420,7 +438,12 @@ def run_b200_arm(args, dtype):
     if not args.no_e2e:
         from geotiepoints_b200 import simple_modis_interpolator
         from geotiepoints_b200._modis_interpolator import interpolate as cviirs_interpolate
-        if cfg["kind"] == "cviirs":
+        if mixed:
+            from geotiepoints_b200 import mod03
+
+            def public_api(*arrs):
+                return mod03.modis_1km_to_250m(*arrs, zenith_scale=0.01)
+        elif cfg["kind"] == "cviirs":
             def public_api(*arrs):
                 return cviirs_interpolate(*arrs, coarse_resolution=cfg["coarse"], fine_resolution=cfg["fine"],
                                           coarse_scan_width=cfg["width"])
@@ -434,7 +457,7 @@ def run_b200_arm(args, dtype):
         rows = ge * cfg["tie_rows"]
         h_in = []
         for a in host_in:
-            pinned = _capi.pinned_pool.empty((rows, cfg["tie_cols"]), dtype)
+            pinned = _capi.pinned_pool.empty((rows, cfg["tie_cols"]), a.dtype)
             pinned[...] = a[:rows]
             h_in.append(pinned)
         res = public_api(*h_in)      # warm-up (pinned pool, stream pool)
@@ -451,7 +474,7 @@ def run_b200_arm(args, dtype):
         dt = sharding.max_over_ranks(dt, dist if world > 1 else None)
         e2e_px = ge * px_per_granule(cfg)
         e2e = {"value": e2e_px * world * e2e_steps / dt, "unit": UNIT,
-               "h2d_bytes_per_step": int(cfg["n_in"] * rows * cfg["tie_cols"] * itemsize),
+               "h2d_bytes_per_step": int(sum(a.dtype.itemsize for a in host_in) * rows * cfg["tie_cols"]),
                "d2h_bytes_per_step": int(2 * e2e_px * itemsize),
                "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
                "host_cpus_bound_to_gpu": len(bound_cpus) if bound_cpus else None,

@@ -100,6 +100,28 @@ int gtp_simple_interp_host_f32(const float* lon, const float* lat, int64_t n_sca
 int gtp_simple_interp_host_f64(const double* lon, const double* lat, int64_t n_scans, int64_t width, int res_factor,
                                double* out_lon, double* out_lat, int device);
 
+/* ---- on-disk types in, float64 math (extension) --------- */
+/* MOD03 stores Longitude / Latitude as float32 and SensorZenith as int16 * 0.01
+ * (reference: testdata/create_modis_test_data.py:85-99).  These entry points take
+ * those arrays as they are - float32 lon / lat, zenith angles as float32 (GTP_ZEN_F32) or int16
+ * (GTP_ZEN_I16), decoded in the kernel as value * zen_scale + zen_offset degrees - run the float64
+ * algorithm of gtp_cviirs_interp_f64 on the widened values and write float32 (GTP_OUT_F32, rounded
+ * once at the store) or float64 (GTP_OUT_F64) results.  The result equals the reference's float64
+ * path on `lon.astype(float64), lat.astype(float64), zenith * scale + offset` (to the float64
+ * parity of this library), NOT its float32 path, whose fine Cartesian coordinates are float32
+ * (0.25-0.5 m of rounding noise).  1 km tie points only (fine_res 250 | 500).  Inputs must be
+ * 4-byte aligned, outputs p * sizeof(out) aligned (p = 1000 / fine_res). */
+#define GTP_ZEN_F32 0
+#define GTP_ZEN_I16 1
+#define GTP_OUT_F32 0
+#define GTP_OUT_F64 1
+int gtp_cviirs_interp_mixed(const float* lon, const float* lat, const void* satz, int zen_kind,
+                            double zen_scale, double zen_offset, int64_t n_scans, int fine_res,
+                            void* out_lon, void* out_lat, int out_kind, int device, void* stream);
+int gtp_cviirs_interp_mixed_host(const float* lon, const float* lat, const void* satz, int zen_kind,
+                                 double zen_scale, double zen_offset, int64_t n_scans, int fine_res,
+                                 void* out_lon, void* out_lat, int out_kind, int device);
+
 /* The host entry points keep up to 4 idle sets of (3 streams + chunk scratch, ~300 MB of
  * device memory each) per process for the next call; gtp_trim() frees them. */
 int gtp_trim(void);

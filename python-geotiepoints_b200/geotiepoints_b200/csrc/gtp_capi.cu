@@ -199,9 +199,13 @@ size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
         if (_e != cudaSuccess) { status = cuda_fail(_e, where); goto done; } \
     } while (0)
 
-template <typename T, int N_IN, typename Launch>
-int host_pipeline(const T* const (&in)[N_IN], T* out_lon, T* out_lat, int64_t n_scans,
-                  int64_t in_elems_per_scan, int64_t out_elems_per_scan, int device, Launch launch)
+// Byte-level core: `in` are n_in host arrays of in_bytes[a] bytes per scan each; both outputs have
+// out_bytes bytes per scan.  launch(d_in, d_lon, d_lat, n_scans_of_chunk, stream) enqueues the kernel.
+constexpr int kMaxInputs = 3;
+
+template <typename Launch>
+int host_pipeline_bytes(const void* const* in, const size_t* in_bytes, int n_in, void* out_lon, void* out_lat,
+                        size_t out_bytes, int64_t n_scans, int device, Launch launch)
 {
     if (n_scans == 0) return GTP_OK;
     DeviceGuard guard(device);
@@ -209,32 +213,33 @@ int host_pipeline(const T* const (&in)[N_IN], T* out_lon, T* out_lat, int64_t n_
     int current = -1;
     if (cudaGetDevice(&current) != cudaSuccess) { cudaGetLastError(); return fail(GTP_E_NO_DEVICE, "no usable CUDA device%s"); }
     int status = GTP_OK;
-    int64_t chunk = std::max<int64_t>(1, chunk_out_bytes() / (int64_t)(out_elems_per_scan * sizeof(T)));
+    int64_t chunk = std::max<int64_t>(1, chunk_out_bytes() / (int64_t)out_bytes);
     chunk = std::min(chunk, n_scans);
     const int64_t n_chunks = (n_scans + chunk - 1) / chunk;
     const int n_streams = (int)std::min<int64_t>(kStreams, n_chunks);
-    const size_t in_bytes = align_up((size_t)chunk * in_elems_per_scan * sizeof(T));
-    const size_t out_bytes = align_up((size_t)chunk * out_elems_per_scan * sizeof(T));
+    size_t in_off[kMaxInputs + 1] = {0};
+    for (int a = 0; a < n_in; ++a) in_off[a + 1] = in_off[a] + align_up((size_t)chunk * in_bytes[a]);
+    const size_t out_chunk = align_up((size_t)chunk * out_bytes);
     HostPipe* pipe = acquire_pipe(current);
-    T* d_in[kStreams][N_IN] = {};
-    T* d_out[kStreams][2] = {};
+    void* d_in[kStreams][kMaxInputs] = {};
+    char* d_out[kStreams][2] = {};
     for (int s = 0; s < n_streams; ++s) {
-        GTP_CUDA_TRY(pipe->reserve(s, N_IN * in_bytes + 2 * out_bytes), "scratch alloc");
-        for (int a = 0; a < N_IN; ++a) d_in[s][a] = (T*)(pipe->scratch[s] + a * in_bytes);
-        for (int a = 0; a < 2; ++a) d_out[s][a] = (T*)(pipe->scratch[s] + N_IN * in_bytes + a * out_bytes);
+        GTP_CUDA_TRY(pipe->reserve(s, in_off[n_in] + 2 * out_chunk), "scratch alloc");
+        for (int a = 0; a < n_in; ++a) d_in[s][a] = pipe->scratch[s] + in_off[a];
+        for (int a = 0; a < 2; ++a) d_out[s][a] = pipe->scratch[s] + in_off[n_in] + a * out_chunk;
     }
     for (int64_t k = 0; k < n_chunks; ++k) {
         const int s = (int)(k % n_streams);
         const cudaStream_t st = pipe->streams[s];
         const int64_t s0 = k * chunk, ns = std::min(chunk, n_scans - s0);
-        for (int a = 0; a < N_IN; ++a)
-            GTP_CUDA_TRY(cudaMemcpyAsync(d_in[s][a], in[a] + s0 * in_elems_per_scan, ns * in_elems_per_scan * sizeof(T),
+        for (int a = 0; a < n_in; ++a)
+            GTP_CUDA_TRY(cudaMemcpyAsync(d_in[s][a], (const char*)in[a] + (size_t)s0 * in_bytes[a], (size_t)ns * in_bytes[a],
                                          cudaMemcpyHostToDevice, st), "H2D");
-        status = launch(d_in[s], d_out[s][0], d_out[s][1], ns, st);
+        status = launch(d_in[s], (void*)d_out[s][0], (void*)d_out[s][1], ns, st);
         if (status != GTP_OK) goto done;
-        GTP_CUDA_TRY(cudaMemcpyAsync(out_lon + s0 * out_elems_per_scan, d_out[s][0], ns * out_elems_per_scan * sizeof(T),
+        GTP_CUDA_TRY(cudaMemcpyAsync((char*)out_lon + (size_t)s0 * out_bytes, d_out[s][0], (size_t)ns * out_bytes,
                                      cudaMemcpyDeviceToHost, st), "D2H");
-        GTP_CUDA_TRY(cudaMemcpyAsync(out_lat + s0 * out_elems_per_scan, d_out[s][1], ns * out_elems_per_scan * sizeof(T),
+        GTP_CUDA_TRY(cudaMemcpyAsync((char*)out_lat + (size_t)s0 * out_bytes, d_out[s][1], (size_t)ns * out_bytes,
                                      cudaMemcpyDeviceToHost, st), "D2H");
     }
 done:
@@ -249,6 +254,49 @@ done:
     }
     release_pipe(pipe, healthy && status == GTP_OK);
     return status;
+}
+
+template <typename T, int N_IN, typename Launch>
+int host_pipeline(const T* const (&in)[N_IN], T* out_lon, T* out_lat, int64_t n_scans,
+                  int64_t in_elems_per_scan, int64_t out_elems_per_scan, int device, Launch launch)
+{
+    static_assert(N_IN <= kMaxInputs, "at most three input arrays");
+    const void* in_v[N_IN];
+    size_t in_bytes[N_IN];
+    for (int a = 0; a < N_IN; ++a) { in_v[a] = in[a]; in_bytes[a] = (size_t)in_elems_per_scan * sizeof(T); }
+    return host_pipeline_bytes(in_v, in_bytes, N_IN, out_lon, out_lat, (size_t)out_elems_per_scan * sizeof(T), n_scans, device,
+        [&](void* const* d_in, void* d_lon, void* d_lat, int64_t ns, cudaStream_t st) {
+            T* typed[N_IN];
+            for (int a = 0; a < N_IN; ++a) typed[a] = (T*)d_in[a];
+            return launch(typed, (T*)d_lon, (T*)d_lat, ns, st);
+        });
+}
+
+// ---- mixed-type operator: on-disk types in, float64 math, float32 | float64 out ----
+int mixed_check(const void* lon, const void* lat, const void* satz, int zen_kind, int64_t n_scans, int fine_res,
+                const void* out_lon, const void* out_lat, int out_kind)
+{
+    if (fine_res != 250 && fine_res != 500) return fail(GTP_E_RESOLUTION, "mixed operator: fine_res must be 250 or 500 (1 km tie points)%s");
+    if (zen_kind != GTP_ZEN_F32 && zen_kind != GTP_ZEN_I16) return fail(GTP_E_RESOLUTION, "mixed operator: unknown zenith type%s");
+    if (out_kind != GTP_OUT_F32 && out_kind != GTP_OUT_F64) return fail(GTP_E_RESOLUTION, "mixed operator: unknown output type%s");
+    if (n_scans < 0) return fail(GTP_E_SHAPE, "n_scans must be >= 0%s");
+    if (n_scans > 0 && (!lon || !lat || !satz || !out_lon || !out_lat)) return fail(GTP_E_NULL, "null buffer%s");
+    return GTP_OK;
+}
+
+int mixed_device(const float* lon, const float* lat, const void* satz, int zen_kind, double zen_scale, double zen_offset,
+                 int64_t n_scans, int fine_res, void* out_lon, void* out_lat, int out_kind, int device, void* stream)
+{
+    int rc = mixed_check(lon, lat, satz, zen_kind, n_scans, fine_res, out_lon, out_lat, out_kind);
+    if (rc != GTP_OK || n_scans == 0) return rc;
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) { cudaGetLastError(); return fail(GTP_E_NO_DEVICE, "no usable CUDA device: %s", cudaGetErrorString(guard.err)); }
+    cudaError_t e = gtp_launch_cviirs_mixed(lon, lat, satz, zen_kind == GTP_ZEN_I16, zen_scale, zen_offset, out_lon, out_lat,
+                                            out_kind == GTP_OUT_F64, n_scans, 1000 / fine_res, (cudaStream_t)stream);
+    if (e == cudaErrorMisalignedAddress) { cudaGetLastError(); return fail(GTP_E_SHAPE, "mixed operator: inputs must be 4-byte and outputs 16-byte (float64: 32-byte) aligned%s"); }
+    if (e != cudaSuccess) return cuda_fail(e, "mixed launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return GTP_OK;
 }
 
 template <typename T>
@@ -359,6 +407,29 @@ int gtp_simple_interp_host_f32(const float* lon, const float* lat, int64_t n_sca
 int gtp_simple_interp_host_f64(const double* lon, const double* lat, int64_t n_scans, int64_t width, int res_factor,
                                double* out_lon, double* out_lat, int device)
 { return simple_host<double>(lon, lat, n_scans, width, res_factor, out_lon, out_lat, device); }
+
+int gtp_cviirs_interp_mixed(const float* lon, const float* lat, const void* satz, int zen_kind,
+                            double zen_scale, double zen_offset, int64_t n_scans, int fine_res,
+                            void* out_lon, void* out_lat, int out_kind, int device, void* stream)
+{ return mixed_device(lon, lat, satz, zen_kind, zen_scale, zen_offset, n_scans, fine_res, out_lon, out_lat, out_kind, device, stream); }
+
+int gtp_cviirs_interp_mixed_host(const float* lon, const float* lat, const void* satz, int zen_kind,
+                                 double zen_scale, double zen_offset, int64_t n_scans, int fine_res,
+                                 void* out_lon, void* out_lat, int out_kind, int device)
+{
+    int rc = mixed_check(lon, lat, satz, zen_kind, n_scans, fine_res, out_lon, out_lat, out_kind);
+    if (rc != GTP_OK || n_scans == 0) return rc;
+    const int p = 1000 / fine_res;
+    const void* in[3] = {lon, lat, satz};
+    const size_t tie = 10 * 1354;
+    const size_t in_bytes[3] = {tie * 4, tie * 4, tie * (zen_kind == GTP_ZEN_I16 ? 2 : 4)};
+    const size_t out_bytes = tie * p * p * (out_kind == GTP_OUT_F64 ? 8 : 4);
+    return host_pipeline_bytes(in, in_bytes, 3, out_lon, out_lat, out_bytes, n_scans, device,
+        [&](void* const* d_in, void* d_lon, void* d_lat, int64_t ns, cudaStream_t st) {
+            return mixed_device((const float*)d_in[0], (const float*)d_in[1], d_in[2], zen_kind, zen_scale, zen_offset,
+                                ns, fine_res, d_lon, d_lat, out_kind, -1, (void*)st);
+        });
+}
 
 int gtp_trim(void)
 {

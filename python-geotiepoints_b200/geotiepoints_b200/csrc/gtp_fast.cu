@@ -13,6 +13,7 @@
 // is an L2 hit.  Warps cover 31 quad columns (lane 31 only provides the right
 // neighbour's tie points), 44 warps per scan; the thread of tie column 1353 produces
 // the P extra pixels right of the last quad (x = P .. 2P-1, extrapolation).
+#include <type_traits>
 #include <cuda_runtime.h>
 #include "gtp_kernels.h"
 #include "gtp_fast_math.cuh"
@@ -52,6 +53,23 @@ __device__ __forceinline__ void store_px<2>(double* p, const double (&v)[2])
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v[0]), "d"(v[1]) : "memory");
 }
 
+// float32 outputs of the float64 math (gtp_cviirs_interp_mixed): rounded once, at the store
+template <int P>
+__device__ __forceinline__ void store_px(float* p, const double (&v)[P]);
+
+template <>
+__device__ __forceinline__ void store_px<4>(float* p, const double (&v)[4])
+{
+    asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"((float)v[0]), "f"((float)v[1]),
+                 "f"((float)v[2]), "f"((float)v[3]) : "memory");
+}
+
+template <>
+__device__ __forceinline__ void store_px<2>(float* p, const double (&v)[2])
+{
+    asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"((float)v[0]), "f"((float)v[1]) : "memory");
+}
+
 // 8-byte asynchronous global -> shared copy (LDGSTS): the next tie row is fetched while the
 // current quad row is computed without holding the values in registers (with ~165 live
 // registers ptxas otherwise parks a register prefetch in local memory and stalls on it).
@@ -60,13 +78,37 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_s
     const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src)
+{
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+
+// One tie-point input element -> its 8-byte staging slot, and back as a double.  float64 is the
+// reference's layout; float32 and int16 (MOD03 stores SensorZenith as int16 * 0.01,
+// testdata/create_modis_test_data.py:95-97) are the on-disk types, widened here instead of on the
+// host.  An int16 travels as the aligned 4-byte pair that holds it (cp.async moves >= 4 bytes).
+__device__ __forceinline__ void stage_fetch(double* slot, const double* src, long long idx) { cp_async8(slot, src + idx); }
+__device__ __forceinline__ void stage_fetch(double* slot, const float* src, long long idx) { cp_async4(slot, src + idx); }
+__device__ __forceinline__ void stage_fetch(double* slot, const short* src, long long idx) { cp_async4(slot, src + (idx & ~1LL)); }
+__device__ __forceinline__ double stage_value(const double* slot, const double*, long long) { return *slot; }
+__device__ __forceinline__ double stage_value(const double* slot, const float*, long long)
+{
+    return (double)*reinterpret_cast<const float*>(slot);
+}
+__device__ __forceinline__ double stage_value(const double* slot, const short*, long long idx)
+{
+    const int pair = *reinterpret_cast<const int*>(slot);
+    return (double)(short)((idx & 1) ? (pair >> 16) : (pair & 0xffff));
+}
+
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // the fine rows [0, nrows) of one quad, first row at a_track = s_t0, branch-free per pixel
-template <int P, int MODE, bool WRAP>
+template <int P, int MODE, bool WRAP, typename TOut>
 __device__ __forceinline__ void quad_rows(const Quad& q, const double (&a_col)[P], double s_t0, int nrows,
-                                          double* out_lon, double* out_lat, long long out_idx)
+                                          TOut* out_lon, TOut* out_lat, long long out_idx)
 {
     // one element index for both outputs (2 registers) instead of two running pointers (4)
     constexpr long long kPitch = (long long)kW * P;
@@ -96,9 +138,9 @@ __device__ __forceinline__ void quad_rows(const Quad& q, const double (&a_col)[P
 // on granules that never call it (the caller's register allocation around the call), and ptxas 12.9
 // turned the 256-bit vector store inside the non-entry function into a single 64-bit store - only
 // pixel 0 of 4 was written, caught by the antimeridian parity test (gpurun_out/per_granule.txt, ab10.txt).
-template <int P>
+template <int P, typename TOut>
 __device__ __forceinline__ void quad_rows_cold(const Quad* qp, const double* a_colp, double s_t0, int nrows,
-                                            double* out_lon, double* out_lat, long long out_idx)
+                                            TOut* out_lon, TOut* out_lat, long long out_idx)
 {
     const Quad q = *qp;
     double a_col[P];
@@ -115,12 +157,18 @@ __device__ __forceinline__ void quad_rows_cold(const Quad* qp, const double* a_c
 // columns and first/last 2 (1) rows (_simple_modis_interpolator.pyx:85-225) IS that bilinear
 // form evaluated at t_y = j/res - (res/16 + 1/8) - r, t_x = i/res - c: the
 // fine-row / column fractions coincide with the CVIIRS ones of the same resolution.
-template <int P, bool SIMPLE>
+//
+// TIn / TZen / TOut: the element types of lon & lat, of the zenith angle and of the outputs.  The
+// reference's interface is all-float64 (double, double, double); the other instantiations serve
+// gtp_cviirs_interp_mixed: float32 lon/lat, float32 or int16 * zen_scale + zen_offset
+// zenith angles, float64 MATH throughout, results rounded once to float32 or kept in float64.
+template <int P, bool SIMPLE, typename TIn, typename TZen, typename TOut>
 __global__ void __launch_bounds__(kThreads, GTP_FAST_MIN_BLOCKS)
-modis_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restrict__ lat,
-                          const double* __restrict__ satz, double* __restrict__ out_lon,
-                          double* __restrict__ out_lat, long long n_scans)
+modis_fast_1km_f64_kernel(const TIn* __restrict__ lon, const TIn* __restrict__ lat,
+                          const TZen* __restrict__ satz, TOut* __restrict__ out_lon,
+                          TOut* __restrict__ out_lat, long long n_scans, double zen_scale, double zen_offset)
 {
+    constexpr bool kZenDecode = !std::is_same<TZen, double>::value;      // float64 zenith angles are taken as they are
     constexpr int kWf = kW * P;          // fine columns
     constexpr int kN = kL * P;           // fine rows per scan
     constexpr int kHalf = P / 2;
@@ -151,21 +199,23 @@ modis_fast_1km_f64_kernel(const double* __restrict__ lon, const double* __restri
     Vec3 topB = {0.0, 0.0, 0.0};
     double top_ce = 0.0, top_ca = 0.0;
     __shared__ double stage[2][3][kThreads];     // double-buffered next-row inputs, one slot per thread
-    cp_async8(&stage[0][0][threadIdx.x], lon + tie_idx);
-    cp_async8(&stage[0][1][threadIdx.x], lat + tie_idx);
-    if (!SIMPLE) cp_async8(&stage[0][2][threadIdx.x], satz + tie_idx);
+    stage_fetch(&stage[0][0][threadIdx.x], lon, tie_idx);
+    stage_fetch(&stage[0][1][threadIdx.x], lat, tie_idx);
+    if (!SIMPLE) stage_fetch(&stage[0][2][threadIdx.x], satz, tie_idx);
     cp_async_commit();
 
 #pragma unroll 1
     for (int r = 0; r < kL; ++r) {
         cp_async_wait_all();
-        const double clon = stage[r & 1][0][threadIdx.x], clat = stage[r & 1][1][threadIdx.x];
-        const double csatz = SIMPLE ? 0.0 : stage[r & 1][2][threadIdx.x];
+        const double clon = stage_value(&stage[r & 1][0][threadIdx.x], lon, tie_idx);
+        const double clat = stage_value(&stage[r & 1][1][threadIdx.x], lat, tie_idx);
+        double csatz = SIMPLE ? 0.0 : stage_value(&stage[r & 1][2][threadIdx.x], satz, tie_idx);
+        if (!SIMPLE && kZenDecode) csatz = fma(csatz, zen_scale, zen_offset);
         if (r + 1 < kL) {            // fetch the next tie row while this one is worked on
-            tie_idx += kW;
-            cp_async8(&stage[(r + 1) & 1][0][threadIdx.x], lon + tie_idx);
-            cp_async8(&stage[(r + 1) & 1][1][threadIdx.x], lat + tie_idx);
-            if (!SIMPLE) cp_async8(&stage[(r + 1) & 1][2][threadIdx.x], satz + tie_idx);
+            tie_idx += kW;           // even: an int16's half of its staged pair is the same in every row
+            stage_fetch(&stage[(r + 1) & 1][0][threadIdx.x], lon, tie_idx);
+            stage_fetch(&stage[(r + 1) & 1][1][threadIdx.x], lat, tie_idx);
+            if (!SIMPLE) stage_fetch(&stage[(r + 1) & 1][2][threadIdx.x], satz, tie_idx);
             cp_async_commit();
         }
         // this lane's tie point of row r; corner B of the lane's quad column comes from lane + 1
@@ -274,22 +324,36 @@ bool gtp_simple_fast_f64_supported(int width, int res)
 
 namespace {
 
-// 256-bit (P = 4) / 128-bit (P = 2) stores need aligned outputs; the row pitch already is
-bool outputs_aligned(const double* out_lon, const double* out_lat, int p)
+// 256-bit (P = 4, float64), 128-bit (P = 2 float64 | P = 4 float32) or 64-bit (P = 2 float32) stores
+// need aligned outputs; the row pitch already is
+template <typename TOut>
+bool outputs_aligned(const TOut* out_lon, const TOut* out_lat, int p)
 {
-    const uintptr_t align = (p == 4) ? 32 : 16;
+    const uintptr_t align = (uintptr_t)p * sizeof(TOut);
     return (((uintptr_t)out_lon | (uintptr_t)out_lat) & (align - 1)) == 0;
 }
 
-template <int P, bool SIMPLE>
-cudaError_t launch_fast(const double* lon, const double* lat, const double* satz, double* out_lon, double* out_lat,
-                        long long n_scans, cudaStream_t stream)
+template <int P, bool SIMPLE, typename TIn, typename TZen, typename TOut>
+cudaError_t launch_fast(const TIn* lon, const TIn* lat, const TZen* satz, TOut* out_lon, TOut* out_lat,
+                        long long n_scans, double zen_scale, double zen_offset, cudaStream_t stream)
 {
     const long long warps = n_scans * kWarpsPerScan;
     const long long blocks = (warps * 32 + kThreads - 1) / kThreads;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    modis_fast_1km_f64_kernel<P, SIMPLE><<<(unsigned)blocks, kThreads, 0, stream>>>(lon, lat, satz, out_lon, out_lat, n_scans);
+    modis_fast_1km_f64_kernel<P, SIMPLE, TIn, TZen, TOut><<<(unsigned)blocks, kThreads, 0, stream>>>(
+        lon, lat, satz, out_lon, out_lat, n_scans, zen_scale, zen_offset);
     return cudaGetLastError();
+}
+
+template <typename TZen, typename TOut>
+cudaError_t launch_mixed(const float* lon, const float* lat, const TZen* satz, double zen_scale, double zen_offset,
+                         TOut* out_lon, TOut* out_lat, long long n_scans, int p, cudaStream_t stream)
+{
+    if (!outputs_aligned(out_lon, out_lat, p)) return cudaErrorMisalignedAddress;
+    // an int16 zenith angle is fetched as the aligned 4-byte pair that holds it
+    if (((uintptr_t)lon | (uintptr_t)lat | (uintptr_t)satz) & 3) return cudaErrorMisalignedAddress;
+    return p == 4 ? launch_fast<4, false>(lon, lat, satz, out_lon, out_lat, n_scans, zen_scale, zen_offset, stream)
+                  : launch_fast<2, false>(lon, lat, satz, out_lon, out_lat, n_scans, zen_scale, zen_offset, stream);
 }
 
 }  // namespace
@@ -301,8 +365,8 @@ cudaError_t gtp_launch_cviirs_fast_f64(const double* lon, const double* lat, con
     if (n_scans <= 0) return cudaSuccess;
     if (!outputs_aligned(out_lon, out_lat, cfg.p))
         return gtp_launch_cviirs_generic<double>(lon, lat, satz, out_lon, out_lat, n_scans, cfg, stream);
-    return cfg.p == 4 ? launch_fast<4, false>(lon, lat, satz, out_lon, out_lat, n_scans, stream)
-                      : launch_fast<2, false>(lon, lat, satz, out_lon, out_lat, n_scans, stream);
+    return cfg.p == 4 ? launch_fast<4, false>(lon, lat, satz, out_lon, out_lat, n_scans, 1.0, 0.0, stream)
+                      : launch_fast<2, false>(lon, lat, satz, out_lon, out_lat, n_scans, 1.0, 0.0, stream);
 }
 
 cudaError_t gtp_launch_simple_fast_f64(const double* lon, const double* lat, double* out_lon, double* out_lat,
@@ -311,6 +375,24 @@ cudaError_t gtp_launch_simple_fast_f64(const double* lon, const double* lat, dou
     if (n_scans <= 0) return cudaSuccess;
     if (!outputs_aligned(out_lon, out_lat, res))
         return gtp_launch_simple_generic<double>(lon, lat, out_lon, out_lat, n_scans, kW, res, stream);
-    return res == 4 ? launch_fast<4, true>(lon, lat, nullptr, out_lon, out_lat, n_scans, stream)
-                    : launch_fast<2, true>(lon, lat, nullptr, out_lon, out_lat, n_scans, stream);
+    return res == 4 ? launch_fast<4, true>(lon, lat, (const double*)nullptr, out_lon, out_lat, n_scans, 1.0, 0.0, stream)
+                    : launch_fast<2, true>(lon, lat, (const double*)nullptr, out_lon, out_lat, n_scans, 1.0, 0.0, stream);
+}
+
+// float32 lon / lat, float32 (zen_is_i16 == 0) or int16 zenith angles decoded as v * zen_scale +
+// zen_offset, float64 math, float32 (out_is_f64 == 0) or float64 results; 1 km tie points only
+cudaError_t gtp_launch_cviirs_mixed(const float* lon, const float* lat, const void* satz, int zen_is_i16,
+                                    double zen_scale, double zen_offset, void* out_lon, void* out_lat, int out_is_f64,
+                                    long long n_scans, int p, cudaStream_t stream)
+{
+    if (n_scans <= 0) return cudaSuccess;
+    if (p != 4 && p != 2) return cudaErrorInvalidValue;
+    if (zen_is_i16) {
+        const short* z = (const short*)satz;
+        return out_is_f64 ? launch_mixed(lon, lat, z, zen_scale, zen_offset, (double*)out_lon, (double*)out_lat, n_scans, p, stream)
+                          : launch_mixed(lon, lat, z, zen_scale, zen_offset, (float*)out_lon, (float*)out_lat, n_scans, p, stream);
+    }
+    const float* z = (const float*)satz;
+    return out_is_f64 ? launch_mixed(lon, lat, z, zen_scale, zen_offset, (double*)out_lon, (double*)out_lat, n_scans, p, stream)
+                      : launch_mixed(lon, lat, z, zen_scale, zen_offset, (float*)out_lon, (float*)out_lat, n_scans, p, stream);
 }

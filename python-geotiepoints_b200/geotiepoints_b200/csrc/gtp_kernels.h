@@ -19,6 +19,10 @@ bool gtp_cviirs_fast_f64_supported(const CviirsCfg& cfg);
 cudaError_t gtp_launch_simple_fast_f64(const double* lon, const double* lat, double* out_lon, double* out_lat,
                                        long long n_scans, int res, cudaStream_t stream);
 bool gtp_simple_fast_f64_supported(int width, int res);
+// the same kernel on the on-disk types: float32 lon/lat, float32 | int16 zenith, float32 | float64 out
+cudaError_t gtp_launch_cviirs_mixed(const float* lon, const float* lat, const void* satz, int zen_is_i16,
+                                    double zen_scale, double zen_offset, void* out_lon, void* out_lat, int out_is_f64,
+                                    long long n_scans, int p, cudaStream_t stream);
 
 // gtp_fast5.cu: float64 5 km -> 1 km fast path (271 or 270 tie columns)
 cudaError_t gtp_launch_cviirs_fast5_f64(const double* lon, const double* lat, const double* satz,

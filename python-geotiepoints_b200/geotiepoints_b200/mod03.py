@@ -1,0 +1,85 @@
+"""MODIS geolocation interpolation straight from the MOD03 on-disk types (extension).
+
+Not part of the reference's API.  MOD03 stores ``Longitude`` /
+``Latitude`` as float32 and ``SensorZenith`` as int16 with ``scale_factor = 0.01``
+(``/root/reference/testdata/create_modis_test_data.py:85-99``); a caller of the reference widens
+them on the host and gets the reference's float32 arithmetic, whose fine Cartesian coordinates are
+float32 (0.25 - 0.5 m of rounding noise, up to 4e-5 deg of longitude at high latitudes).  The
+functions here hand the arrays to the GPU as they are, decode the zenith angle in the kernel, run
+the **float64** algorithm (the kernel behind ``modisinterpolator.modis_1km_to_250m`` for float64
+input) and round once, to float32 by default.  The result is the reference's *float64* result for
+``lon.astype(float64), lat.astype(float64), zenith * scale + offset`` - less input and half the
+output traffic of the float64 path, three times the pixel rate of the float32-faithful one.
+
+    lons, lats = mod03.modis_1km_to_250m(lon_f32, lat_f32, sensor_zenith_i16, zenith_scale=0.01)
+
+Inputs are numpy arrays or torch CUDA tensors (zero copy), C-contiguous, whole scans of 10 rows and
+1354 columns; ``sensor_zenith`` is float32 (degrees, or scaled) or int16.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _capi
+from ._operator import _is_torch_tensor
+
+_ZEN_KIND = {"float32": 0, "int16": 1}
+_OUT_KIND = {"float32": 0, "float64": 1}
+
+
+def modis_1km_to_250m(lon1, lat1, sensor_zenith, *, zenith_scale=1.0, zenith_offset=0.0, out_dtype=np.float32):
+    """1 km -> 250 m from float32 lon / lat and float32 | int16 zenith angles, float64 math."""
+    return _interpolate(lon1, lat1, sensor_zenith, 250, zenith_scale, zenith_offset, out_dtype)
+
+
+def modis_1km_to_500m(lon1, lat1, sensor_zenith, *, zenith_scale=1.0, zenith_offset=0.0, out_dtype=np.float32):
+    """1 km -> 500 m from float32 lon / lat and float32 | int16 zenith angles, float64 math."""
+    return _interpolate(lon1, lat1, sensor_zenith, 500, zenith_scale, zenith_offset, out_dtype)
+
+
+def _dtype_name(a):
+    return str(a.dtype).replace("torch.", "")
+
+
+def _interpolate(lon1, lat1, zen, fine_resolution, zenith_scale, zenith_offset, out_dtype):
+    arrays = [lon1, lat1, zen]
+    for a in arrays:
+        if a.ndim != 2:
+            raise ValueError("Expected 2D input arrays.")
+    if _dtype_name(lon1) != "float32" or _dtype_name(lat1) != "float32":
+        raise TypeError("mod03: longitude and latitude must be float32 (use modisinterpolator for float64)")
+    if _dtype_name(zen) not in _ZEN_KIND:
+        raise TypeError("mod03: sensor_zenith must be float32 or int16")
+    out_name = np.dtype(out_dtype).name
+    if out_name not in _OUT_KIND:
+        raise TypeError("mod03: out_dtype must be float32 or float64")
+    shape = tuple(lon1.shape)
+    if tuple(lat1.shape) != shape or tuple(zen.shape) != shape:
+        raise ValueError("input arrays must have the same shape")
+    rows, cols = shape
+    if rows % 10:
+        raise ValueError(f"Input data does not consist of whole scans (10 rows per scan), got {rows} rows.")
+    if cols != 1354:
+        raise ValueError(f"Expected 1354 tie-point columns, got {cols}.")
+    p = 1000 // fine_resolution
+    out_shape = (rows * p, cols * p)
+    scalars = (_ZEN_KIND[_dtype_name(zen)], float(zenith_scale), float(zenith_offset), rows // 10, fine_resolution)
+    lib = _capi.lib()
+    if all(_is_torch_tensor(a) for a in arrays):
+        import torch
+        if not lon1.is_cuda:
+            raise TypeError("torch inputs must be CUDA tensors (numpy arrays take the host path)")
+        arrays = [a.contiguous() for a in arrays]
+        tdtype = torch.float32 if out_name == "float32" else torch.float64
+        out = [torch.empty(out_shape, dtype=tdtype, device=lon1.device) for _ in range(2)]
+        stream = torch.cuda.current_stream(lon1.device).cuda_stream
+        rc = lib.gtp_cviirs_interp_mixed(*[a.data_ptr() for a in arrays], *scalars, out[0].data_ptr(), out[1].data_ptr(),
+                                         _OUT_KIND[out_name], lon1.device.index, ctypes.c_void_p(stream))
+        _capi.check(rc)
+        return out[0], out[1]
+    arrays = [np.ascontiguousarray(a) for a in arrays]
+    out = [_capi.pinned_pool.empty(out_shape, np.dtype(out_dtype)) for _ in range(2)]
+    rc = lib.gtp_cviirs_interp_mixed_host(*[a.ctypes.data for a in arrays], *scalars, out[0].ctypes.data,
+                                          out[1].ctypes.data, _OUT_KIND[out_name], -1)
+    _capi.check(rc)
+    return out[0], out[1]

@@ -186,3 +186,37 @@ def test_launch_counter_moves():
     before = _capi.launch_count()
     modisinterpolator.modis_1km_to_250m(lon, lat, satz)
     assert _capi.launch_count() == before + 1
+
+
+# ---- mixed-type extension (mod03): on-disk types in, float64 math ---------------------------------
+def _mod03_inputs(granule, n_scans, zen_kind):
+    lon, lat, satz = testing.modis_granule(granule, n_scans=n_scans, dtype=np.float32)
+    if zen_kind == "int16":
+        zen = np.round(satz.astype(np.float64) / 0.01).astype(np.int16)
+        return lon, lat, zen, 0.01, zen.astype(np.float64) * 0.01
+    return lon, lat, satz, 1.0, satz.astype(np.float64)
+
+
+@pytest.mark.parametrize("fine", [250, 500])
+@pytest.mark.parametrize("zen_kind", ["float32", "int16"])
+@pytest.mark.parametrize("granule", [0, 5, 14])
+def test_mod03_mixed_types_match_float64_reference(granule, zen_kind, fine):
+    """float32 lon/lat + float32|int16 zenith -> float64 math: equals the oracle's float64 path on the
+    widened inputs (1e-10 deg for float64 output; the float32 output is that result rounded once)."""
+    import torch
+    from geotiepoints_b200 import mod03
+    lon, lat, zen, scale, satz64 = _mod03_inputs(granule, 12, zen_kind)
+    fn = mod03.modis_1km_to_250m if fine == 250 else mod03.modis_1km_to_500m
+    exp = _oracle_cviirs((lon.astype(np.float64), lat.astype(np.float64), satz64), 1000, fine, 0)
+    got64 = fn(lon, lat, zen, zenith_scale=scale, out_dtype=np.float64)
+    assert got64[0].dtype == np.float64 and got64[0].shape == exp[0].shape
+    assert_parity(*got64, *exp, what=f"mod03 {zen_kind} granule {granule} ->{fine} float64 out")
+    got32 = fn(lon, lat, zen, zenith_scale=scale)
+    assert got32[0].dtype == np.float32
+    for g32, g64, name in ((got32[0], got64[0], "lon"), (got32[1], got64[1], "lat")):
+        assert np.array_equal(g32, g64.astype(np.float32)), f"float32 {name} is not the rounded float64 result"
+    # torch CUDA tensors: zero copy, same numbers
+    dev = [torch.from_numpy(a).cuda() for a in (lon, lat, zen)]
+    tor = fn(*dev, zenith_scale=scale)
+    assert tor[0].is_cuda and tor[0].dtype == torch.float32
+    assert np.array_equal(tor[0].cpu().numpy(), got32[0]) and np.array_equal(tor[1].cpu().numpy(), got32[1])

@@ -86,6 +86,25 @@ def test_mixed_dtypes_is_a_value_error():
         modisinterpolator.modis_1km_to_250m(a, a.astype(np.float64), a)
 
 
+def test_mod03_argument_checks():
+    """The mixed-type extension validates before it touches the device."""
+    from geotiepoints_b200 import mod03
+    lon = np.zeros((20, 1354), np.float32)
+    zen = np.zeros((20, 1354), np.int16)
+    with pytest.raises(TypeError):
+        mod03.modis_1km_to_250m(lon.astype(np.float64), lon, zen)
+    with pytest.raises(TypeError):
+        mod03.modis_1km_to_250m(lon, lon, zen.astype(np.int32))
+    with pytest.raises(TypeError):
+        mod03.modis_1km_to_250m(lon, lon, zen, out_dtype=np.float16)
+    with pytest.raises(ValueError):
+        mod03.modis_1km_to_250m(lon[:15], lon[:15], zen[:15])
+    with pytest.raises(ValueError):
+        mod03.modis_1km_to_500m(lon[:, :1000], lon[:, :1000], zen[:, :1000])
+    with pytest.raises(ValueError):
+        mod03.modis_1km_to_250m(lon, lon[:10], zen)
+
+
 def test_partial_scan_and_wrong_width_are_refused():
     a = np.zeros((15, 1354), np.float32)
     with pytest.raises(ValueError, match="whole scans"):
