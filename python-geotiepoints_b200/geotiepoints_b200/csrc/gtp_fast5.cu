@@ -164,6 +164,8 @@ modis_fast_5km_f64_kernel(const double* __restrict__ lon, const double* __restri
         if (!(MASKED_) || ((kmask >> k) & 1u)) { my_lon[k] = lo_; my_lat[k] = la_; }       \
     }
     const bool edge = first_warp || last_warp;                       // warp-uniform
+    double2* dst_lon = reinterpret_cast<double2*>(out_lon + row0);
+    double2* dst_lat = reinterpret_cast<double2*>(out_lat + row0);
 #pragma unroll 1
     for (int j = 0; j < kRows; ++j) {
         const double s_t = kTrack5[j];
@@ -187,17 +189,17 @@ modis_fast_5km_f64_kernel(const double* __restrict__ lon, const double* __restri
             }
         }
         __syncwarp();
-        double2* const dst_lon = reinterpret_cast<double2*>(out_lon + row0 + (long long)j * kFineCols);
-        double2* const dst_lat = reinterpret_cast<double2*>(out_lat + row0 + (long long)j * kFineCols);
-#pragma unroll
-        for (int m = 0; m < (kSpanMax / 2 + 31) / 32; ++m) {
-            const int e = lane + 32 * m;
-            if (e < span2) {
-                __stcs(dst_lon + e, span_lon[e]);
-                __stcs(dst_lat + e, span_lat[e]);
-            }
+        // 150 | 152 columns = 75 | 76 pairs: two full rounds of 32 lanes and one of 11 | 12
+        __stcs(dst_lon + lane, span_lon[lane]);
+        __stcs(dst_lat + lane, span_lat[lane]);
+        __stcs(dst_lon + lane + 32, span_lon[lane + 32]);
+        __stcs(dst_lat + lane + 32, span_lat[lane + 32]);
+        if (lane + 64 < span2) {
+            __stcs(dst_lon + lane + 64, span_lon[lane + 64]);
+            __stcs(dst_lat + lane + 64, span_lat[lane + 64]);
         }
         __syncwarp();
+        dst_lon += kFineCols / 2; dst_lat += kFineCols / 2;
     }
 #undef GTP_STAGE
 }
