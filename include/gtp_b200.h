@@ -122,6 +122,13 @@ int gtp_cviirs_interp_mixed_host(const float* lon, const float* lat, const void*
                                  double zen_scale, double zen_offset, int64_t n_scans, int fine_res,
                                  void* out_lon, void* out_lat, int out_kind, int device);
 
+/* simple_modis_interpolator (gtp_simple_interp_f64) on float32 lon / lat of width 1354: float64 math,
+ * float32 | float64 results */
+int gtp_simple_interp_mixed(const float* lon, const float* lat, int64_t n_scans, int res_factor,
+                            void* out_lon, void* out_lat, int out_kind, int device, void* stream);
+int gtp_simple_interp_mixed_host(const float* lon, const float* lat, int64_t n_scans, int res_factor,
+                                 void* out_lon, void* out_lat, int out_kind, int device);
+
 /* The host entry points keep up to 4 idle sets of (3 streams + chunk scratch, ~300 MB of
  * device memory each) per process for the next call; gtp_trim() frees them. */
 int gtp_trim(void);

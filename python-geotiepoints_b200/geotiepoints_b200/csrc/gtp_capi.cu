@@ -284,6 +284,30 @@ int mixed_check(const void* lon, const void* lat, const void* satz, int zen_kind
     return GTP_OK;
 }
 
+int simple_mixed_check(const void* lon, const void* lat, int64_t n_scans, int res, const void* out_lon, const void* out_lat,
+                       int out_kind)
+{
+    if (res != 2 && res != 4) return fail(GTP_E_RESOLUTION, "simple interpolator: res_factor must be 2 or 4%s");
+    if (out_kind != GTP_OUT_F32 && out_kind != GTP_OUT_F64) return fail(GTP_E_RESOLUTION, "mixed operator: unknown output type%s");
+    if (n_scans < 0) return fail(GTP_E_SHAPE, "n_scans must be >= 0%s");
+    if (n_scans > 0 && (!lon || !lat || !out_lon || !out_lat)) return fail(GTP_E_NULL, "null buffer%s");
+    return GTP_OK;
+}
+
+int simple_mixed_device(const float* lon, const float* lat, int64_t n_scans, int res, void* out_lon, void* out_lat,
+                        int out_kind, int device, void* stream)
+{
+    int rc = simple_mixed_check(lon, lat, n_scans, res, out_lon, out_lat, out_kind);
+    if (rc != GTP_OK || n_scans == 0) return rc;
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) { cudaGetLastError(); return fail(GTP_E_NO_DEVICE, "no usable CUDA device: %s", cudaGetErrorString(guard.err)); }
+    cudaError_t e = gtp_launch_simple_mixed(lon, lat, out_lon, out_lat, out_kind == GTP_OUT_F64, n_scans, res, (cudaStream_t)stream);
+    if (e == cudaErrorMisalignedAddress) { cudaGetLastError(); return fail(GTP_E_SHAPE, "mixed operator: inputs must be 4-byte and outputs 16-byte (float64: 32-byte) aligned%s"); }
+    if (e != cudaSuccess) return cuda_fail(e, "simple mixed launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return GTP_OK;
+}
+
 int mixed_device(const float* lon, const float* lat, const void* satz, int zen_kind, double zen_scale, double zen_offset,
                  int64_t n_scans, int fine_res, void* out_lon, void* out_lat, int out_kind, int device, void* stream)
 {
@@ -407,6 +431,26 @@ int gtp_simple_interp_host_f32(const float* lon, const float* lat, int64_t n_sca
 int gtp_simple_interp_host_f64(const double* lon, const double* lat, int64_t n_scans, int64_t width, int res_factor,
                                double* out_lon, double* out_lat, int device)
 { return simple_host<double>(lon, lat, n_scans, width, res_factor, out_lon, out_lat, device); }
+
+int gtp_simple_interp_mixed(const float* lon, const float* lat, int64_t n_scans, int res_factor,
+                            void* out_lon, void* out_lat, int out_kind, int device, void* stream)
+{ return simple_mixed_device(lon, lat, n_scans, res_factor, out_lon, out_lat, out_kind, device, stream); }
+
+int gtp_simple_interp_mixed_host(const float* lon, const float* lat, int64_t n_scans, int res_factor,
+                                 void* out_lon, void* out_lat, int out_kind, int device)
+{
+    int rc = simple_mixed_check(lon, lat, n_scans, res_factor, out_lon, out_lat, out_kind);
+    if (rc != GTP_OK || n_scans == 0) return rc;
+    const void* in[2] = {lon, lat};
+    const size_t tie = 10 * 1354;
+    const size_t in_bytes[2] = {tie * 4, tie * 4};
+    const size_t out_bytes = tie * res_factor * res_factor * (out_kind == GTP_OUT_F64 ? 8 : 4);
+    return host_pipeline_bytes(in, in_bytes, 2, out_lon, out_lat, out_bytes, n_scans, device,
+        [&](void* const* d_in, void* d_lon, void* d_lat, int64_t ns, cudaStream_t st) {
+            return simple_mixed_device((const float*)d_in[0], (const float*)d_in[1], ns, res_factor, d_lon, d_lat,
+                                       out_kind, -1, (void*)st);
+        });
+}
 
 int gtp_cviirs_interp_mixed(const float* lon, const float* lat, const void* satz, int zen_kind,
                             double zen_scale, double zen_offset, int64_t n_scans, int fine_res,

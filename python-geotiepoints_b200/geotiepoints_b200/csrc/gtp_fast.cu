@@ -379,6 +379,26 @@ cudaError_t gtp_launch_simple_fast_f64(const double* lon, const double* lat, dou
                     : launch_fast<2, true>(lon, lat, (const double*)nullptr, out_lon, out_lat, n_scans, 1.0, 0.0, stream);
 }
 
+// simple_modis_interpolator on float32 lon / lat: float64 math, float32 | float64 results (width 1354)
+cudaError_t gtp_launch_simple_mixed(const float* lon, const float* lat, void* out_lon, void* out_lat, int out_is_f64,
+                                    long long n_scans, int res, cudaStream_t stream)
+{
+    if (n_scans <= 0) return cudaSuccess;
+    if (res != 4 && res != 2) return cudaErrorInvalidValue;
+    if (((uintptr_t)lon | (uintptr_t)lat) & 3) return cudaErrorMisalignedAddress;
+    const double* none = nullptr;
+    if (out_is_f64) {
+        double* olon = (double*)out_lon; double* olat = (double*)out_lat;
+        if (!outputs_aligned(olon, olat, res)) return cudaErrorMisalignedAddress;
+        return res == 4 ? launch_fast<4, true>(lon, lat, none, olon, olat, n_scans, 1.0, 0.0, stream)
+                        : launch_fast<2, true>(lon, lat, none, olon, olat, n_scans, 1.0, 0.0, stream);
+    }
+    float* olon = (float*)out_lon; float* olat = (float*)out_lat;
+    if (!outputs_aligned(olon, olat, res)) return cudaErrorMisalignedAddress;
+    return res == 4 ? launch_fast<4, true>(lon, lat, none, olon, olat, n_scans, 1.0, 0.0, stream)
+                    : launch_fast<2, true>(lon, lat, none, olon, olat, n_scans, 1.0, 0.0, stream);
+}
+
 // float32 lon / lat, float32 (zen_is_i16 == 0) or int16 zenith angles decoded as v * zen_scale +
 // zen_offset, float64 math, float32 (out_is_f64 == 0) or float64 results; 1 km tie points only
 cudaError_t gtp_launch_cviirs_mixed(const float* lon, const float* lat, const void* satz, int zen_is_i16,

@@ -24,6 +24,9 @@ cudaError_t gtp_launch_cviirs_mixed(const float* lon, const float* lat, const vo
                                     double zen_scale, double zen_offset, void* out_lon, void* out_lat, int out_is_f64,
                                     long long n_scans, int p, cudaStream_t stream);
 
+cudaError_t gtp_launch_simple_mixed(const float* lon, const float* lat, void* out_lon, void* out_lat, int out_is_f64,
+                                    long long n_scans, int res, cudaStream_t stream);
+
 // gtp_fast5.cu: float64 5 km -> 1 km fast path (271 or 270 tie columns)
 cudaError_t gtp_launch_cviirs_fast5_f64(const double* lon, const double* lat, const double* satz,
                                         double* out_lon, double* out_lat,

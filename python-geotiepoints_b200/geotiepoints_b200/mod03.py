@@ -37,6 +37,16 @@ def modis_1km_to_500m(lon1, lat1, sensor_zenith, *, zenith_scale=1.0, zenith_off
     return _interpolate(lon1, lat1, sensor_zenith, 500, zenith_scale, zenith_offset, out_dtype)
 
 
+def simple_modis_1km_to_250m(lon1, lat1, *, out_dtype=np.float32):
+    """``simple_modis_interpolator.modis_1km_to_250m`` on float32 lon / lat with float64 math."""
+    return _interpolate_simple(lon1, lat1, 4, out_dtype)
+
+
+def simple_modis_1km_to_500m(lon1, lat1, *, out_dtype=np.float32):
+    """``simple_modis_interpolator.modis_1km_to_500m`` on float32 lon / lat with float64 math."""
+    return _interpolate_simple(lon1, lat1, 2, out_dtype)
+
+
 def _dtype_name(a):
     return str(a.dtype).replace("torch.", "")
 
@@ -80,6 +90,45 @@ def _interpolate(lon1, lat1, zen, fine_resolution, zenith_scale, zenith_offset, 
     arrays = [np.ascontiguousarray(a) for a in arrays]
     out = [_capi.pinned_pool.empty(out_shape, np.dtype(out_dtype)) for _ in range(2)]
     rc = lib.gtp_cviirs_interp_mixed_host(*[a.ctypes.data for a in arrays], *scalars, out[0].ctypes.data,
+                                          out[1].ctypes.data, _OUT_KIND[out_name], -1)
+    _capi.check(rc)
+    return out[0], out[1]
+
+
+def _interpolate_simple(lon1, lat1, res, out_dtype):
+    arrays = [lon1, lat1]
+    for a in arrays:
+        if a.ndim != 2:
+            raise ValueError("Expected 2D input arrays.")
+    if _dtype_name(lon1) != "float32" or _dtype_name(lat1) != "float32":
+        raise TypeError("mod03: longitude and latitude must be float32 (use simple_modis_interpolator for float64)")
+    out_name = np.dtype(out_dtype).name
+    if out_name not in _OUT_KIND:
+        raise TypeError("mod03: out_dtype must be float32 or float64")
+    rows, cols = tuple(lon1.shape)
+    if tuple(lat1.shape) != (rows, cols):
+        raise ValueError("input arrays must have the same shape")
+    if rows % 10:
+        raise ValueError(f"Input data does not consist of whole scans (10 rows per scan), got {rows} rows.")
+    if cols != 1354:
+        raise ValueError(f"Expected 1354 tie-point columns, got {cols}.")
+    out_shape = (rows * res, cols * res)
+    lib = _capi.lib()
+    if all(_is_torch_tensor(a) for a in arrays):
+        import torch
+        if not lon1.is_cuda:
+            raise TypeError("torch inputs must be CUDA tensors (numpy arrays take the host path)")
+        arrays = [a.contiguous() for a in arrays]
+        tdtype = torch.float32 if out_name == "float32" else torch.float64
+        out = [torch.empty(out_shape, dtype=tdtype, device=lon1.device) for _ in range(2)]
+        stream = torch.cuda.current_stream(lon1.device).cuda_stream
+        rc = lib.gtp_simple_interp_mixed(*[a.data_ptr() for a in arrays], rows // 10, res, out[0].data_ptr(),
+                                         out[1].data_ptr(), _OUT_KIND[out_name], lon1.device.index, ctypes.c_void_p(stream))
+        _capi.check(rc)
+        return out[0], out[1]
+    arrays = [np.ascontiguousarray(a) for a in arrays]
+    out = [_capi.pinned_pool.empty(out_shape, np.dtype(out_dtype)) for _ in range(2)]
+    rc = lib.gtp_simple_interp_mixed_host(*[a.ctypes.data for a in arrays], rows // 10, res, out[0].ctypes.data,
                                           out[1].ctypes.data, _OUT_KIND[out_name], -1)
     _capi.check(rc)
     return out[0], out[1]

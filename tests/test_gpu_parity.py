@@ -220,3 +220,18 @@ def test_mod03_mixed_types_match_float64_reference(granule, zen_kind, fine):
     tor = fn(*dev, zenith_scale=scale)
     assert tor[0].is_cuda and tor[0].dtype == torch.float32
     assert np.array_equal(tor[0].cpu().numpy(), got32[0]) and np.array_equal(tor[1].cpu().numpy(), got32[1])
+
+
+@pytest.mark.parametrize("fine", [250, 500])
+@pytest.mark.parametrize("granule", [0, 5, 14])
+def test_mod03_simple_matches_float64_reference(granule, fine):
+    from geotiepoints_b200 import mod03
+    lon, lat, _ = testing.modis_granule(granule, n_scans=12, dtype=np.float32)
+    fn = mod03.simple_modis_1km_to_250m if fine == 250 else mod03.simple_modis_1km_to_500m
+    with np.errstate(all="ignore"):
+        exp = gtp_oracle.simple(lon.astype(np.float64), lat.astype(np.float64), 1000, fine, n_threads=8)
+    got64 = fn(lon, lat, out_dtype=np.float64)
+    assert_parity(*got64, *exp, what=f"mod03 simple granule {granule} ->{fine} float64 out")
+    got32 = fn(lon, lat)
+    assert got32[0].dtype == np.float32
+    assert np.array_equal(got32[0], got64[0].astype(np.float32)) and np.array_equal(got32[1], got64[1].astype(np.float32))
