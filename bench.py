@@ -338,7 +338,7 @@ def run_b200_arm(args, dtype):
 
     def step():
         if mixed:
-            rc = fn(*[t.data_ptr() for t in d_in], 1, 0.01, 0.0, n_scans, cfg["fine"],
+            rc = fn(*[t.data_ptr() for t in d_in], 1, 0.01, 0.0, n_scans, cfg["coarse"], cfg["fine"], 0,
                     out_lon.data_ptr(), out_lat.data_ptr(), 0, local_rank, ctypes.c_void_p(stream.cuda_stream))
         else:
             rc = fn(*[t.data_ptr() for t in d_in], n_scans, *scalars,

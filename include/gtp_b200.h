@@ -109,18 +109,20 @@ int gtp_simple_interp_host_f64(const double* lon, const double* lat, int64_t n_s
  * once at the store) or float64 (GTP_OUT_F64) results.  The result equals the reference's float64
  * path on `lon.astype(float64), lat.astype(float64), zenith * scale + offset` (to the float64
  * parity of this library), NOT its float32 path, whose fine Cartesian coordinates are float32
- * (0.25-0.5 m of rounding noise).  1 km tie points only (fine_res 250 | 500).  Inputs must be
- * 4-byte aligned, outputs p * sizeof(out) aligned (p = 1000 / fine_res). */
+ * (0.25-0.5 m of rounding noise).  coarse_res 1000 with fine_res 250 | 500, or coarse_res 5000
+ * (coarse_width 270 | 271, 0 = 271) with fine_res 1000.  Inputs must be 4-byte aligned (int16: each
+ * chunk of scans starts on an even element, which whole scans do), outputs 16-byte (float64 at
+ * 250 m: 32-byte) aligned. */
 #define GTP_ZEN_F32 0
 #define GTP_ZEN_I16 1
 #define GTP_OUT_F32 0
 #define GTP_OUT_F64 1
 int gtp_cviirs_interp_mixed(const float* lon, const float* lat, const void* satz, int zen_kind,
-                            double zen_scale, double zen_offset, int64_t n_scans, int fine_res,
-                            void* out_lon, void* out_lat, int out_kind, int device, void* stream);
+                            double zen_scale, double zen_offset, int64_t n_scans, int coarse_res, int fine_res,
+                            int coarse_width, void* out_lon, void* out_lat, int out_kind, int device, void* stream);
 int gtp_cviirs_interp_mixed_host(const float* lon, const float* lat, const void* satz, int zen_kind,
-                                 double zen_scale, double zen_offset, int64_t n_scans, int fine_res,
-                                 void* out_lon, void* out_lat, int out_kind, int device);
+                                 double zen_scale, double zen_offset, int64_t n_scans, int coarse_res, int fine_res,
+                                 int coarse_width, void* out_lon, void* out_lat, int out_kind, int device);
 
 /* simple_modis_interpolator (gtp_simple_interp_f64) on float32 lon / lat of width 1354: float64 math,
  * float32 | float64 results */

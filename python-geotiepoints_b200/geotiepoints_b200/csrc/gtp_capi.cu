@@ -273,10 +273,22 @@ int host_pipeline(const T* const (&in)[N_IN], T* out_lon, T* out_lat, int64_t n_
 }
 
 // ---- mixed-type operator: on-disk types in, float64 math, float32 | float64 out ----
-int mixed_check(const void* lon, const void* lat, const void* satz, int zen_kind, int64_t n_scans, int fine_res,
-                const void* out_lon, const void* out_lat, int out_kind)
+// geometry of the mixed operator: 1 km -> 250 | 500 m or 5 km (270 | 271 columns) -> 1 km
+struct MixedCfg { int rows_per_scan, width, out_rows_per_scan, out_cols; };
+
+int mixed_check(const void* lon, const void* lat, const void* satz, int zen_kind, int64_t n_scans, int coarse_res,
+                int fine_res, int coarse_width, const void* out_lon, const void* out_lat, int out_kind, MixedCfg* mc)
 {
-    if (fine_res != 250 && fine_res != 500) return fail(GTP_E_RESOLUTION, "mixed operator: fine_res must be 250 or 500 (1 km tie points)%s");
+    if (coarse_res == 1000 && (fine_res == 250 || fine_res == 500)) {
+        const int p = 1000 / fine_res;
+        *mc = MixedCfg{10, 1354, 10 * p, 1354 * p};
+    } else if (coarse_res == 5000 && fine_res == 1000) {
+        const int w = coarse_width ? coarse_width : 271;
+        if (w != 270 && w != 271) return fail(GTP_E_WIDTH_5KM, "Can't interpolate if 5km tiepoints have less than 270 columns.%s");
+        *mc = MixedCfg{2, w, 10, 1354};
+    } else {
+        return fail(GTP_E_RESOLUTION, "mixed operator: 1000 -> 250 | 500 or 5000 -> 1000 only%s");
+    }
     if (zen_kind != GTP_ZEN_F32 && zen_kind != GTP_ZEN_I16) return fail(GTP_E_RESOLUTION, "mixed operator: unknown zenith type%s");
     if (out_kind != GTP_OUT_F32 && out_kind != GTP_OUT_F64) return fail(GTP_E_RESOLUTION, "mixed operator: unknown output type%s");
     if (n_scans < 0) return fail(GTP_E_SHAPE, "n_scans must be >= 0%s");
@@ -309,14 +321,19 @@ int simple_mixed_device(const float* lon, const float* lat, int64_t n_scans, int
 }
 
 int mixed_device(const float* lon, const float* lat, const void* satz, int zen_kind, double zen_scale, double zen_offset,
-                 int64_t n_scans, int fine_res, void* out_lon, void* out_lat, int out_kind, int device, void* stream)
+                 int64_t n_scans, int coarse_res, int fine_res, int coarse_width, void* out_lon, void* out_lat, int out_kind,
+                 int device, void* stream)
 {
-    int rc = mixed_check(lon, lat, satz, zen_kind, n_scans, fine_res, out_lon, out_lat, out_kind);
+    MixedCfg mc;
+    int rc = mixed_check(lon, lat, satz, zen_kind, n_scans, coarse_res, fine_res, coarse_width, out_lon, out_lat, out_kind, &mc);
     if (rc != GTP_OK || n_scans == 0) return rc;
     DeviceGuard guard(device);
     if (guard.err != cudaSuccess) { cudaGetLastError(); return fail(GTP_E_NO_DEVICE, "no usable CUDA device: %s", cudaGetErrorString(guard.err)); }
-    cudaError_t e = gtp_launch_cviirs_mixed(lon, lat, satz, zen_kind == GTP_ZEN_I16, zen_scale, zen_offset, out_lon, out_lat,
-                                            out_kind == GTP_OUT_F64, n_scans, 1000 / fine_res, (cudaStream_t)stream);
+    cudaError_t e = (coarse_res == 1000)
+        ? gtp_launch_cviirs_mixed(lon, lat, satz, zen_kind == GTP_ZEN_I16, zen_scale, zen_offset, out_lon, out_lat,
+                                  out_kind == GTP_OUT_F64, n_scans, 1000 / fine_res, (cudaStream_t)stream)
+        : gtp_launch_cviirs5_mixed(lon, lat, satz, zen_kind == GTP_ZEN_I16, zen_scale, zen_offset, out_lon, out_lat,
+                                   out_kind == GTP_OUT_F64, n_scans, mc.width, (cudaStream_t)stream);
     if (e == cudaErrorMisalignedAddress) { cudaGetLastError(); return fail(GTP_E_SHAPE, "mixed operator: inputs must be 4-byte and outputs 16-byte (float64: 32-byte) aligned%s"); }
     if (e != cudaSuccess) return cuda_fail(e, "mixed launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -453,25 +470,28 @@ int gtp_simple_interp_mixed_host(const float* lon, const float* lat, int64_t n_s
 }
 
 int gtp_cviirs_interp_mixed(const float* lon, const float* lat, const void* satz, int zen_kind,
-                            double zen_scale, double zen_offset, int64_t n_scans, int fine_res,
-                            void* out_lon, void* out_lat, int out_kind, int device, void* stream)
-{ return mixed_device(lon, lat, satz, zen_kind, zen_scale, zen_offset, n_scans, fine_res, out_lon, out_lat, out_kind, device, stream); }
+                            double zen_scale, double zen_offset, int64_t n_scans, int coarse_res, int fine_res,
+                            int coarse_width, void* out_lon, void* out_lat, int out_kind, int device, void* stream)
+{
+    return mixed_device(lon, lat, satz, zen_kind, zen_scale, zen_offset, n_scans, coarse_res, fine_res, coarse_width,
+                        out_lon, out_lat, out_kind, device, stream);
+}
 
 int gtp_cviirs_interp_mixed_host(const float* lon, const float* lat, const void* satz, int zen_kind,
-                                 double zen_scale, double zen_offset, int64_t n_scans, int fine_res,
-                                 void* out_lon, void* out_lat, int out_kind, int device)
+                                 double zen_scale, double zen_offset, int64_t n_scans, int coarse_res, int fine_res,
+                                 int coarse_width, void* out_lon, void* out_lat, int out_kind, int device)
 {
-    int rc = mixed_check(lon, lat, satz, zen_kind, n_scans, fine_res, out_lon, out_lat, out_kind);
+    MixedCfg mc;
+    int rc = mixed_check(lon, lat, satz, zen_kind, n_scans, coarse_res, fine_res, coarse_width, out_lon, out_lat, out_kind, &mc);
     if (rc != GTP_OK || n_scans == 0) return rc;
-    const int p = 1000 / fine_res;
     const void* in[3] = {lon, lat, satz};
-    const size_t tie = 10 * 1354;
+    const size_t tie = (size_t)mc.rows_per_scan * mc.width;
     const size_t in_bytes[3] = {tie * 4, tie * 4, tie * (zen_kind == GTP_ZEN_I16 ? 2 : 4)};
-    const size_t out_bytes = tie * p * p * (out_kind == GTP_OUT_F64 ? 8 : 4);
+    const size_t out_bytes = (size_t)mc.out_rows_per_scan * mc.out_cols * (out_kind == GTP_OUT_F64 ? 8 : 4);
     return host_pipeline_bytes(in, in_bytes, 3, out_lon, out_lat, out_bytes, n_scans, device,
         [&](void* const* d_in, void* d_lon, void* d_lat, int64_t ns, cudaStream_t st) {
             return mixed_device((const float*)d_in[0], (const float*)d_in[1], d_in[2], zen_kind, zen_scale, zen_offset,
-                                ns, fine_res, d_lon, d_lat, out_kind, -1, (void*)st);
+                                ns, coarse_res, fine_res, coarse_width, d_lon, d_lat, out_kind, -1, (void*)st);
         });
 }
 

@@ -2,7 +2,8 @@
 //
 // One THREAD owns one tie-point quad column of one scan and walks down the ten tie
 // rows of the scan; the neighbouring column's tie-point data comes from the next lane
-// by warp shuffle, so nothing is staged in shared memory and there is no barrier.
+// by warp shuffle; shared memory only holds one private slot per thread for the next tie
+// row's inputs (cp.async double buffering), so there is no barrier.
 // For every quad the thread projects the quad on the local frame of its corner A once
 // (gtp_fast_math.cuh) and then produces the quad's P x (P | P + P/2) fine pixels with
 // ~16 FP64 FMAs each; a warp therefore writes 31 x 32 B = 992 contiguous bytes per

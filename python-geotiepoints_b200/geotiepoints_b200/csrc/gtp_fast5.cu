@@ -17,6 +17,7 @@
 //
 // HBM traffic: 16 B written per pixel + 3 x 8 B per tie point = 16.96 B/px.
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 #include "gtp_kernels.h"
 #include "gtp_fast_math.cuh"
@@ -63,10 +64,21 @@ __device__ __forceinline__ void take_quad_from(Quad& q, QuadCorners& x, int src,
 
 constexpr int kSpanMax = 152;        // fine columns one warp produces per row: 30 x 5 (+ 2 at either swath edge)
 
+// store two adjacent pixels of the float64 result: as they are, or rounded once to float32
+__device__ __forceinline__ void store_pair(double* dst, int pair, double2 v) { __stcs(reinterpret_cast<double2*>(dst) + pair, v); }
+__device__ __forceinline__ void store_pair(float* dst, int pair, double2 v)
+{
+    __stcs(reinterpret_cast<float2*>(dst) + pair, make_float2((float)v.x, (float)v.y));
+}
+
+// TIn / TZen / TOut as in gtp_fast.cu: all-double is the reference's interface; float lon/lat, float
+// or int16 * zen_scale + zen_offset zenith angles and float | double results serve gtp_cviirs_interp_mixed.
+template <typename TIn, typename TZen, typename TOut>
 __global__ void __launch_bounds__(kThreads5, 4)
-modis_fast_5km_f64_kernel(const double* __restrict__ lon, const double* __restrict__ lat,
-                          const double* __restrict__ satz, double* __restrict__ out_lon,
-                          double* __restrict__ out_lat, long long n_scans, int W, int warps_per_scan)
+modis_fast_5km_f64_kernel(const TIn* __restrict__ lon, const TIn* __restrict__ lat,
+                          const TZen* __restrict__ satz, TOut* __restrict__ out_lon,
+                          TOut* __restrict__ out_lat, long long n_scans, int W, int warps_per_scan,
+                          double zen_scale, double zen_offset)
 {
     const long long warp_global = (blockIdx.x * (long long)kThreads5 + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -81,8 +93,10 @@ modis_fast_5km_f64_kernel(const double* __restrict__ lon, const double* __restri
 
     // ---- the two tie points of this lane's column -------------------------------------------
     const long long base = scan * 2 * (long long)W + tc;
-    const double lon0 = __ldg(lon + base), lat0 = __ldg(lat + base), satz0 = __ldg(satz + base);
-    const double lon1 = __ldg(lon + base + W), lat1 = __ldg(lat + base + W);
+    const double lon0 = (double)__ldg(lon + base), lat0 = (double)__ldg(lat + base);
+    const double lon1 = (double)__ldg(lon + base + W), lat1 = (double)__ldg(lat + base + W);
+    double satz0 = (double)__ldg(satz + base);
+    if (!std::is_same<TZen, double>::value) satz0 = fma(satz0, zen_scale, zen_offset);
     TieGeo top = {0.0, 1.0, 0.0, 1.0, 0.0, 0.0};
     TieZen zen = {0.0, 0.0, 1.0, 0.0, 1.0}, unused = zen;
     tie_first<true>(top, zen, lon0, lat0, satz0);
@@ -164,8 +178,8 @@ modis_fast_5km_f64_kernel(const double* __restrict__ lon, const double* __restri
         if (!(MASKED_) || ((kmask >> k) & 1u)) { my_lon[k] = lo_; my_lat[k] = la_; }       \
     }
     const bool edge = first_warp || last_warp;                       // warp-uniform
-    double2* dst_lon = reinterpret_cast<double2*>(out_lon + row0);
-    double2* dst_lat = reinterpret_cast<double2*>(out_lat + row0);
+    TOut* dst_lon = out_lon + row0;
+    TOut* dst_lat = out_lat + row0;
 #pragma unroll 1
     for (int j = 0; j < kRows; ++j) {
         const double s_t = kTrack5[j];
@@ -190,16 +204,16 @@ modis_fast_5km_f64_kernel(const double* __restrict__ lon, const double* __restri
         }
         __syncwarp();
         // 150 | 152 columns = 75 | 76 pairs: two full rounds of 32 lanes and one of 11 | 12
-        __stcs(dst_lon + lane, span_lon[lane]);
-        __stcs(dst_lat + lane, span_lat[lane]);
-        __stcs(dst_lon + lane + 32, span_lon[lane + 32]);
-        __stcs(dst_lat + lane + 32, span_lat[lane + 32]);
+        store_pair(dst_lon, lane, span_lon[lane]);
+        store_pair(dst_lat, lane, span_lat[lane]);
+        store_pair(dst_lon, lane + 32, span_lon[lane + 32]);
+        store_pair(dst_lat, lane + 32, span_lat[lane + 32]);
         if (lane + 64 < span2) {
-            __stcs(dst_lon + lane + 64, span_lon[lane + 64]);
-            __stcs(dst_lat + lane + 64, span_lat[lane + 64]);
+            store_pair(dst_lon, lane + 64, span_lon[lane + 64]);
+            store_pair(dst_lat, lane + 64, span_lat[lane + 64]);
         }
         __syncwarp();
-        dst_lon += kFineCols / 2; dst_lat += kFineCols / 2;
+        dst_lon += kFineCols; dst_lat += kFineCols;
     }
 #undef GTP_STAGE
 }
@@ -211,6 +225,25 @@ bool gtp_cviirs_fast5_f64_supported(const CviirsCfg& cfg)
     return cfg.km == 5 && cfg.p == 1 && (cfg.W == 271 || cfg.W == 270);
 }
 
+namespace {
+
+template <typename TIn, typename TZen, typename TOut>
+cudaError_t launch_fast5(const TIn* lon, const TIn* lat, const TZen* satz, TOut* out_lon, TOut* out_lat,
+                         long long n_scans, int W, double zen_scale, double zen_offset, cudaStream_t stream)
+{
+    // 9 warps of 30 quads: 270 (W = 271) or 269 (W = 270) quads; the last warp has lanes to spare for
+    // the columns right of the last quad (lane 30 | lanes 29, 30), warp 0 uses lane 31 for the left ones
+    const int warps_per_scan = (W - 1 + kQuadsPerWarp - 1) / kQuadsPerWarp;
+    const long long warps = n_scans * warps_per_scan;
+    const long long blocks = (warps * 32 + kThreads5 - 1) / kThreads5;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    modis_fast_5km_f64_kernel<TIn, TZen, TOut><<<(unsigned)blocks, kThreads5, 0, stream>>>(
+        lon, lat, satz, out_lon, out_lat, n_scans, W, warps_per_scan, zen_scale, zen_offset);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
 cudaError_t gtp_launch_cviirs_fast5_f64(const double* lon, const double* lat, const double* satz,
                                         double* out_lon, double* out_lat,
                                         long long n_scans, const CviirsCfg& cfg, cudaStream_t stream)
@@ -219,13 +252,26 @@ cudaError_t gtp_launch_cviirs_fast5_f64(const double* lon, const double* lat, co
     // 128-bit stores need 16-byte aligned outputs (the row pitch and every span start already are)
     if ((((uintptr_t)out_lon | (uintptr_t)out_lat) & 15) != 0)
         return gtp_launch_cviirs_generic<double>(lon, lat, satz, out_lon, out_lat, n_scans, cfg, stream);
-    // 9 warps of 30 quads: 270 (W = 271) or 269 (W = 270) quads; the last warp has lanes to spare for
-    // the columns right of the last quad (lane 30 | lanes 29, 30), warp 0 uses lane 31 for the left ones
-    const int warps_per_scan = (cfg.W - 1 + kQuadsPerWarp - 1) / kQuadsPerWarp;
-    const long long warps = n_scans * warps_per_scan;
-    const long long blocks = (warps * 32 + kThreads5 - 1) / kThreads5;
-    if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    modis_fast_5km_f64_kernel<<<(unsigned)blocks, kThreads5, 0, stream>>>(lon, lat, satz, out_lon, out_lat, n_scans,
-                                                                         cfg.W, warps_per_scan);
-    return cudaGetLastError();
+    return launch_fast5(lon, lat, satz, out_lon, out_lat, n_scans, cfg.W, 1.0, 0.0, stream);
+}
+
+// float32 lon / lat, float32 | int16 zenith angles, float64 math, float32 | float64 results (5 km -> 1 km)
+cudaError_t gtp_launch_cviirs5_mixed(const float* lon, const float* lat, const void* satz, int zen_is_i16,
+                                     double zen_scale, double zen_offset, void* out_lon, void* out_lat, int out_is_f64,
+                                     long long n_scans, int W, cudaStream_t stream)
+{
+    if (n_scans <= 0) return cudaSuccess;
+    if (W != 270 && W != 271) return cudaErrorInvalidValue;
+    const uintptr_t out_align = out_is_f64 ? 15 : 7;
+    if ((((uintptr_t)out_lon | (uintptr_t)out_lat) & out_align) || (((uintptr_t)lon | (uintptr_t)lat) & 3)
+        || ((uintptr_t)satz & (zen_is_i16 ? 1 : 3)))
+        return cudaErrorMisalignedAddress;
+    if (zen_is_i16) {
+        const short* z = (const short*)satz;
+        return out_is_f64 ? launch_fast5(lon, lat, z, (double*)out_lon, (double*)out_lat, n_scans, W, zen_scale, zen_offset, stream)
+                          : launch_fast5(lon, lat, z, (float*)out_lon, (float*)out_lat, n_scans, W, zen_scale, zen_offset, stream);
+    }
+    const float* z = (const float*)satz;
+    return out_is_f64 ? launch_fast5(lon, lat, z, (double*)out_lon, (double*)out_lat, n_scans, W, zen_scale, zen_offset, stream)
+                      : launch_fast5(lon, lat, z, (float*)out_lon, (float*)out_lat, n_scans, W, zen_scale, zen_offset, stream);
 }

@@ -32,6 +32,9 @@ cudaError_t gtp_launch_cviirs_fast5_f64(const double* lon, const double* lat, co
                                         double* out_lon, double* out_lat,
                                         long long n_scans, const CviirsCfg& cfg, cudaStream_t stream);
 bool gtp_cviirs_fast5_f64_supported(const CviirsCfg& cfg);
+cudaError_t gtp_launch_cviirs5_mixed(const float* lon, const float* lat, const void* satz, int zen_is_i16,
+                                     double zen_scale, double zen_offset, void* out_lon, void* out_lat, int out_is_f64,
+                                     long long n_scans, int W, cudaStream_t stream);
 
 // gtp_fast_f32.cu: float32 CVIIRS 1 km fast path (rounding-faithful blend, anchor-relative back-transform)
 cudaError_t gtp_launch_cviirs_fast_f32(const float* lon, const float* lat, const float* satz,

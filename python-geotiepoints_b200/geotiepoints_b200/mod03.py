@@ -37,6 +37,11 @@ def modis_1km_to_500m(lon1, lat1, sensor_zenith, *, zenith_scale=1.0, zenith_off
     return _interpolate(lon1, lat1, sensor_zenith, 500, zenith_scale, zenith_offset, out_dtype)
 
 
+def modis_5km_to_1km(lon1, lat1, sensor_zenith, *, zenith_scale=1.0, zenith_offset=0.0, out_dtype=np.float32):
+    """5 km (270 or 271 columns) -> 1 km from float32 lon / lat and float32 | int16 zenith angles, float64 math."""
+    return _interpolate(lon1, lat1, sensor_zenith, 1000, zenith_scale, zenith_offset, out_dtype, coarse_resolution=5000)
+
+
 def simple_modis_1km_to_250m(lon1, lat1, *, out_dtype=np.float32):
     """``simple_modis_interpolator.modis_1km_to_250m`` on float32 lon / lat with float64 math."""
     return _interpolate_simple(lon1, lat1, 4, out_dtype)
@@ -51,7 +56,7 @@ def _dtype_name(a):
     return str(a.dtype).replace("torch.", "")
 
 
-def _interpolate(lon1, lat1, zen, fine_resolution, zenith_scale, zenith_offset, out_dtype):
+def _interpolate(lon1, lat1, zen, fine_resolution, zenith_scale, zenith_offset, out_dtype, coarse_resolution=1000):
     arrays = [lon1, lat1, zen]
     for a in arrays:
         if a.ndim != 2:
@@ -67,13 +72,20 @@ def _interpolate(lon1, lat1, zen, fine_resolution, zenith_scale, zenith_offset, 
     if tuple(lat1.shape) != shape or tuple(zen.shape) != shape:
         raise ValueError("input arrays must have the same shape")
     rows, cols = shape
-    if rows % 10:
-        raise ValueError(f"Input data does not consist of whole scans (10 rows per scan), got {rows} rows.")
-    if cols != 1354:
-        raise ValueError(f"Expected 1354 tie-point columns, got {cols}.")
-    p = 1000 // fine_resolution
-    out_shape = (rows * p, cols * p)
-    scalars = (_ZEN_KIND[_dtype_name(zen)], float(zenith_scale), float(zenith_offset), rows // 10, fine_resolution)
+    rows_per_scan = 10 if coarse_resolution == 1000 else 2
+    if rows % rows_per_scan:
+        raise ValueError(f"Input data does not consist of whole scans ({rows_per_scan} rows per scan), got {rows} rows.")
+    if coarse_resolution == 1000:
+        if cols != 1354:
+            raise ValueError(f"Expected 1354 tie-point columns, got {cols}.")
+        p = 1000 // fine_resolution
+        out_shape = (rows * p, cols * p)
+    else:
+        if cols not in (270, 271):
+            raise NotImplementedError("Can't interpolate if 5km tiepoints have less than 270 columns.")
+        out_shape = (rows * 5, 1354)
+    scalars = (_ZEN_KIND[_dtype_name(zen)], float(zenith_scale), float(zenith_offset), rows // rows_per_scan,
+               coarse_resolution, fine_resolution, cols if coarse_resolution == 5000 else 0)
     lib = _capi.lib()
     if all(_is_torch_tensor(a) for a in arrays):
         import torch

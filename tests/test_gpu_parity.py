@@ -222,6 +222,22 @@ def test_mod03_mixed_types_match_float64_reference(granule, zen_kind, fine):
     assert np.array_equal(tor[0].cpu().numpy(), got32[0]) and np.array_equal(tor[1].cpu().numpy(), got32[1])
 
 
+@pytest.mark.parametrize("width", [271, 270])
+@pytest.mark.parametrize("zen_kind", ["float32", "int16"])
+@pytest.mark.parametrize("granule", [0, 14])
+def test_mod03_5km_matches_float64_reference(granule, zen_kind, width):
+    from geotiepoints_b200 import mod03
+    lon, lat, zen, scale, satz64 = _mod03_inputs(granule, 203, zen_kind)
+    lon5, lat5, zen5 = testing.subsample_5km(lon, lat, zen, width)
+    _, _, satz5 = testing.subsample_5km(lon, lat, satz64, width)
+    exp = _oracle_cviirs((lon5.astype(np.float64), lat5.astype(np.float64), satz5), 5000, 1000, width)
+    got64 = mod03.modis_5km_to_1km(lon5, lat5, zen5, zenith_scale=scale, out_dtype=np.float64)
+    assert_parity(*got64, *exp, what=f"mod03 5km({width}) {zen_kind} granule {granule} float64 out")
+    got32 = mod03.modis_5km_to_1km(lon5, lat5, zen5, zenith_scale=scale)
+    assert got32[0].dtype == np.float32 and got32[0].shape == (2030, 1354)
+    assert np.array_equal(got32[0], got64[0].astype(np.float32)) and np.array_equal(got32[1], got64[1].astype(np.float32))
+
+
 @pytest.mark.parametrize("fine", [250, 500])
 @pytest.mark.parametrize("granule", [0, 5, 14])
 def test_mod03_simple_matches_float64_reference(granule, fine):
@@ -235,3 +251,18 @@ def test_mod03_simple_matches_float64_reference(granule, fine):
     got32 = fn(lon, lat)
     assert got32[0].dtype == np.float32
     assert np.array_equal(got32[0], got64[0].astype(np.float32)) and np.array_equal(got32[1], got64[1].astype(np.float32))
+
+
+def test_concurrent_host_calls_from_threads():
+    """dask's threaded scheduler calls the operator from several threads at once: every call checks out
+    its own streams + scratch (csrc/gtp_capi.cu HostPipe), results must equal the serial ones bit for bit."""
+    from concurrent.futures import ThreadPoolExecutor
+    inputs = [testing.modis_granule(g, n_scans=30 + 7 * g) for g in range(6)]
+    serial = [modisinterpolator.modis_1km_to_250m(*a) for a in inputs]
+    serial = [(np.array(lo), np.array(la)) for lo, la in serial]
+    with ThreadPoolExecutor(6) as pool:
+        for _ in range(3):
+            got = list(pool.map(lambda a: modisinterpolator.modis_1km_to_250m(*a), inputs))
+            for (lo, la), (slo, sla) in zip(got, serial):
+                assert np.array_equal(lo, slo, equal_nan=True) and np.array_equal(la, sla, equal_nan=True)
+    assert _capi.lib().gtp_trim() == 0
