@@ -266,3 +266,55 @@ def test_concurrent_host_calls_from_threads():
             for (lo, la), (slo, sla) in zip(got, serial):
                 assert np.array_equal(lo, slo, equal_nan=True) and np.array_equal(la, sla, equal_nan=True)
     assert _capi.lib().gtp_trim() == 0
+
+
+@pytest.mark.parametrize("config", ["1km_250m", "1km_500m", "5km_271", "5km_270", "simple_250m", "mixed_250m_f32", "mixed_5km_f32"])
+def test_kernels_stay_inside_their_output_buffers(config):
+    """compute-sanitizer is not available on the GPU pool, so: outputs are carved out of the middle of a
+    sentinel-filled allocation; after the launch everything outside them must still be the sentinel and
+    everything inside must have been written.  A polar granule tail exercises every evaluation mode."""
+    import ctypes
+    import torch
+    lib = _capi.lib()
+    lon, lat, satz = (np.ascontiguousarray(a[-40:]) for a in testing.modis_granule(4))
+    pad, sentinel = 4096, -12345.0
+    tdt, npdt, out_dt = torch.float64, np.float64, torch.float64
+    if config.startswith("mixed"):
+        tdt, npdt, out_dt = torch.float32, np.float32, torch.float32
+    arrs = [a.astype(npdt) for a in (lon, lat, satz)]
+    n_scans, out_shape = 4, None
+    if "5km" in config:
+        width = 270 if config.endswith("270") else 271
+        arrs = list(testing.subsample_5km(*arrs, width=width))
+        n_scans, out_shape = arrs[0].shape[0] // 2, (arrs[0].shape[0] * 5, 1354)
+    else:
+        p = 2 if "500m" in config else 4
+        out_shape = (arrs[0].shape[0] * p, 1354 * p)
+    dev = [torch.from_numpy(a).cuda() for a in arrs]
+    n_out = out_shape[0] * out_shape[1]
+    bufs = [torch.full((n_out + 2 * pad,), sentinel, dtype=out_dt, device="cuda") for _ in range(2)]
+    outs = [b[pad:pad + n_out] for b in bufs]
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ptr = [t.data_ptr() for t in dev]
+    optr = [o.data_ptr() for o in outs]
+    if config in ("1km_250m", "1km_500m"):
+        rc = lib.gtp_cviirs_interp_f64(*ptr, n_scans, 1000, 250 if config == "1km_250m" else 500, 0, *optr, 0, st)
+    elif config.startswith("5km"):
+        rc = lib.gtp_cviirs_interp_f64(*ptr, n_scans, 5000, 1000, arrs[0].shape[1], *optr, 0, st)
+    elif config == "simple_250m":
+        rc = lib.gtp_simple_interp_f64(ptr[0], ptr[1], n_scans, 1354, 4, *optr, 0, st)
+    elif config == "mixed_250m_f32":
+        rc = lib.gtp_cviirs_interp_mixed(*ptr, 0, 1.0, 0.0, n_scans, 1000, 250, 0, *optr, 0, 0, st)
+    else:
+        sub = testing.subsample_5km(*arrs, width=271)
+        dev = [torch.from_numpy(a).cuda() for a in sub]
+        n_scans = sub[0].shape[0] // 2
+        n_out = n_scans * 10 * 1354
+        outs = [b[pad:pad + n_out] for b in bufs]
+        rc = lib.gtp_cviirs_interp_mixed(*[t.data_ptr() for t in dev], 0, 1.0, 0.0, n_scans, 5000, 1000, 271,
+                                         *[o.data_ptr() for o in outs], 0, 0, st)
+    _capi.check(rc)
+    torch.cuda.synchronize()
+    for b in bufs:
+        assert bool((b[:pad] == sentinel).all()) and bool((b[pad + n_out:] == sentinel).all()), "wrote outside the output"
+        assert not bool((b[pad:pad + n_out] == sentinel).any()), "left output pixels unwritten"
