@@ -180,20 +180,57 @@ modis_fast_5km_f64_kernel(const TIn* __restrict__ lon, const TIn* __restrict__ l
     const bool edge = first_warp || last_warp;                       // warp-uniform
     TOut* dst_lon = out_lon + row0;
     TOut* dst_lat = out_lat + row0;
+    // the warp's staged row -> global memory: 150 | 152 columns = 75 | 76 pairs, two full rounds of 32
+    // lanes and one of 11 | 12
+#define GTP_COPY_OUT()                                                                     \
+    __syncwarp();                                                                          \
+    store_pair(dst_lon, lane, span_lon[lane]);                                             \
+    store_pair(dst_lat, lane, span_lat[lane]);                                             \
+    store_pair(dst_lon, lane + 32, span_lon[lane + 32]);                                   \
+    store_pair(dst_lat, lane + 32, span_lat[lane + 32]);                                   \
+    if (lane + 64 < span2) {                                                               \
+        store_pair(dst_lon, lane + 64, span_lon[lane + 64]);                               \
+        store_pair(dst_lat, lane + 64, span_lat[lane + 64]);                               \
+    }                                                                                      \
+    __syncwarp();                                                                          \
+    dst_lon += kFineCols; dst_lat += kFineCols;
+
+    // Inner warps whose quads all evaluate the same way - nearly all of them - run a row loop without
+    // the per-row dispatch (lanes 30 and 31 own no quad there and only help with the copy).
+    const bool all_low = !edge && __all_sync(kFull, mode == kLow || mode < 0);
+    const bool all_high = !edge && __all_sync(kFull, mode == kHigh || mode < 0);
+    if (all_low) {
+#pragma unroll 1
+        for (int j = 0; j < kRows; ++j) {
+            if (mode >= 0) {
+                const double s_t = kTrack5[j];
+                const RowCoef rc = row_setup(q, s_t, s_t * (1.0 - s_t));
+                GTP_STAGE(kLow, false)
+            }
+            GTP_COPY_OUT()
+        }
+        return;
+    }
+    if (all_high) {
+#pragma unroll 1
+        for (int j = 0; j < kRows; ++j) {
+            if (mode >= 0) {
+                const double s_t = kTrack5[j];
+                const RowCoef rc = row_setup(q, s_t, s_t * (1.0 - s_t));
+                GTP_STAGE(kHigh, false)
+            }
+            GTP_COPY_OUT()
+        }
+        return;
+    }
 #pragma unroll 1
     for (int j = 0; j < kRows; ++j) {
         const double s_t = kTrack5[j];
         if (mode == kLow || mode == kHigh || mode == kBoth) {
             const RowCoef rc = row_setup(q, s_t, s_t * (1.0 - s_t));
-            if (!edge) {
-                if (mode == kLow) { GTP_STAGE(kLow, false) }
-                else if (mode == kHigh) { GTP_STAGE(kHigh, false) }
-                else { GTP_STAGE(kBoth, false) }
-            } else {
-                if (mode == kLow) { GTP_STAGE(kLow, true) }
-                else if (mode == kHigh) { GTP_STAGE(kHigh, true) }
-                else { GTP_STAGE(kBoth, true) }
-            }
+            if (mode == kLow) { GTP_STAGE(kLow, true) }
+            else if (mode == kHigh) { GTP_STAGE(kHigh, true) }
+            else { GTP_STAGE(kBoth, true) }
         } else if (mode == kSlow) {
 #pragma unroll 1
             for (int k = 0; k < kF; ++k) {
@@ -202,19 +239,9 @@ modis_fast_5km_f64_kernel(const TIn* __restrict__ lon, const TIn* __restrict__ l
                 my_lon[k] = ll.lon; my_lat[k] = ll.lat;
             }
         }
-        __syncwarp();
-        // 150 | 152 columns = 75 | 76 pairs: two full rounds of 32 lanes and one of 11 | 12
-        store_pair(dst_lon, lane, span_lon[lane]);
-        store_pair(dst_lat, lane, span_lat[lane]);
-        store_pair(dst_lon, lane + 32, span_lon[lane + 32]);
-        store_pair(dst_lat, lane + 32, span_lat[lane + 32]);
-        if (lane + 64 < span2) {
-            store_pair(dst_lon, lane + 64, span_lon[lane + 64]);
-            store_pair(dst_lat, lane + 64, span_lat[lane + 64]);
-        }
-        __syncwarp();
-        dst_lon += kFineCols; dst_lat += kFineCols;
+        GTP_COPY_OUT()
     }
+#undef GTP_COPY_OUT
 #undef GTP_STAGE
 }
 
