@@ -244,15 +244,31 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return None
+
+
 def cpu_baseline(dtype, reps=3):
+    """The reference on this box's host cores: all threads on one granule (the reported value) and one
+    thread on 40 scans of it (SURVEY.md 8d asks for both)."""
     kind, run = load_reference()
     lon, lat, satz = make_granules(0, 1, dtype)
     threads = host_threads()
     time_reference_step(run, lon[:200], lat[:200], satz[:200], min(threads, 4))      # warm-up
     best = min(time_reference_step(run, lon, lat, satz, threads) for _ in range(reps))
+    rows1 = 400
+    best1 = min(time_reference_step(run, lon[:rows1], lat[:rows1], satz[:rows1], 1) for _ in range(reps))
     return {"value": PX_PER_GRANULE / best, "unit": UNIT, "cores": threads, "kind": kind,
+            "single_thread_value": (rows1 * 4 * OUT_COLS) / best1, "cpu_model": cpu_model(),
             "sample": f"1 synthetic granule 2030x1354 {np.dtype(dtype).name} 1km->250m, best of {reps}, "
-                      f"scans split over {threads} threads" + (" (f64 = reference + 2-line dtype patch)" if kind == "reference" and dtype == np.float64 else "")}
+                      f"scans split over {threads} threads" + (" (f64 = reference + 2-line dtype patch)" if kind == "reference" and dtype == np.float64 else "")
+                      + f"; single_thread_value: {rows1 // 10} scans on 1 thread"}
 
 
 def run_reference_arm(args, dtype):
