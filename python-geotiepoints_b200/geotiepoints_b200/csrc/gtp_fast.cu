@@ -200,6 +200,12 @@ modis_fast_1km_f64_kernel(const TIn* __restrict__ lon, const TIn* __restrict__ l
     Vec3 topB = {0.0, 0.0, 0.0};
     double top_ce = 0.0, top_ca = 0.0;
     __shared__ double stage[2][3][kThreads];     // double-buffered next-row inputs, one slot per thread
+#ifdef GTP_FAST_NO_PARK
+    constexpr bool kPark = false;
+#else
+    constexpr bool kPark = (P == 4);
+#endif
+    __shared__ double park[kPark ? 14 : 1][kThreads];      // per-thread parking slots (see the row loops)
     stage_fetch(&stage[0][0][threadIdx.x], lon, tie_idx);
     stage_fetch(&stage[0][1][threadIdx.x], lat, tie_idx);
     if (!SIMPLE) stage_fetch(&stage[0][2][threadIdx.x], satz, tie_idx);
@@ -251,6 +257,21 @@ modis_fast_1km_f64_kernel(const TIn* __restrict__ lon, const TIn* __restrict__ l
             Quad q;
             quad_setup(q, A, A_xyz, topB, curB, D, top_ce, top_ca, extra ? (double)kABoundExtra : 1.0);
             if (q.mode != kSlow) {
+                // State that is only needed again after the row loops (this tie row's frame, corner B, the
+                // zenith chain: 14 doubles) waits in shared memory meanwhile: with those 28 registers the
+                // compiler interleaves the 4 pixel chains of a fine row instead of evaluating them one
+                // after the other (ncu: "wait" was 47 % of the stall samples in the row loops; +2..6 % at
+                // 250 m).  Not at 500 m: 28 shared-memory accesses per quad cost more than they buy there.
+                volatile double* const pk = &park[0][threadIdx.x];
+                if (kPark) {
+                    pk[0 * kThreads] = own.sl; pk[1 * kThreads] = own.cl; pk[2 * kThreads] = own.sp; pk[3 * kThreads] = own.cp;
+                    pk[4 * kThreads] = own.lon; pk[5 * kThreads] = own.lat;
+                    pk[6 * kThreads] = curB.x; pk[7 * kThreads] = curB.y; pk[8 * kThreads] = curB.z;
+                    if (!SIMPLE) {
+                        pk[9 * kThreads] = zen.za; pk[10 * kThreads] = zen.sz; pk[11 * kThreads] = zen.cz;
+                        pk[12 * kThreads] = zen.sphi; pk[13 * kThreads] = zen.cphi;
+                    }
+                }
                 // s_s + s_s (1 - s_s) c_exp  (:341, :344); s_s = k / P inside the quad, 1 + k / P right of it
                 double a_col[P];
                 double s_base = extra ? 1.0 : 0.0;
@@ -271,6 +292,15 @@ modis_fast_1km_f64_kernel(const TIn* __restrict__ lon, const TIn* __restrict__ l
 #pragma unroll
                     for (int k = 0; k < P; ++k) a_colc[k] = a_col[k];
                     quad_rows_cold<P>(&qc, a_colc, s_t0, nrows, out_lon, out_lat, out_idx);
+                }
+                if (kPark) {
+                    own.sl = pk[0 * kThreads]; own.cl = pk[1 * kThreads]; own.sp = pk[2 * kThreads]; own.cp = pk[3 * kThreads];
+                    own.lon = pk[4 * kThreads]; own.lat = pk[5 * kThreads];
+                    curB.x = pk[6 * kThreads]; curB.y = pk[7 * kThreads]; curB.z = pk[8 * kThreads];
+                    if (!SIMPLE) {
+                        zen.za = pk[9 * kThreads]; zen.sz = pk[10 * kThreads]; zen.cz = pk[11 * kThreads];
+                        zen.sphi = pk[12 * kThreads]; zen.cphi = pk[13 * kThreads];
+                    }
                 }
             } else {
 #pragma unroll 1
