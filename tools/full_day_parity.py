@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""Parity over the whole synthetic day: 3 scans out of every one of the 288 granules (864 scans, 1.9e8
+pixels at 250 m) through the CUDA path and through the oracle, per configuration.
+
+    python tools/full_day_parity.py            # needs a GPU; prints one line per configuration
+
+The oracle (oracle/, test infrastructure) is the checker here, exactly as in tests/."""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in ("python-geotiepoints_b200", "oracle", "tests"):
+    sys.path.insert(0, os.path.join(ROOT, p))
+import numpy as np
+import gtp_oracle
+from geotiepoints_b200 import mod03, modisinterpolator, simple_modis_interpolator, testing
+from parity import compare
+
+scans = (0, 101, 202)
+parts = []
+t0 = time.time()
+for g in range(288):
+    lon, lat, satz = testing.modis_granule(g)
+    rows = np.concatenate([np.arange(s * 10, s * 10 + 10) for s in scans])
+    parts.append((lon[rows], lat[rows], satz[rows]))
+lon, lat, satz = (np.ascontiguousarray(np.concatenate([p[k] for p in parts])) for k in range(3))
+print(f"# {lon.shape[0] // 10} scans of 288 granules, |lat| max {np.abs(lat).max():.2f}, built in {time.time() - t0:.0f} s", flush=True)
+
+
+def report(name, got, exp):
+    s = compare(got[0], got[1], exp[0], exp[1])
+    keys = ("n", "nan_pattern_equal", "max_dlat", "max_dlon_outside_band", "max_dlon_in_band",
+            "n_in_band_over_conditioning_bound", "bit_exact_fraction", "n_over_tol_and_ulp")
+    print(f"{name:34s} " + " ".join(f"{k}={s[k]:.3g}" if isinstance(s[k], float) else f"{k}={s[k]}" for k in keys if k in s), flush=True)
+
+
+with np.errstate(all="ignore"):
+    for fine, fn in ((250, modisinterpolator.modis_1km_to_250m), (500, modisinterpolator.modis_1km_to_500m)):
+        for dt in (np.float64, np.float32):
+            a = [x.astype(dt) for x in (lon, lat, satz)]
+            report(f"cviirs 1km->{fine}m {np.dtype(dt).name}", fn(*a), gtp_oracle.cviirs(*a, 1000, fine, 0, n_threads=16))
+    for fine, fn in ((250, simple_modis_interpolator.modis_1km_to_250m), (500, simple_modis_interpolator.modis_1km_to_500m)):
+        for dt in (np.float64, np.float32):
+            a = [x.astype(dt) for x in (lon, lat)]
+            report(f"simple 1km->{fine}m {np.dtype(dt).name}", fn(*a), gtp_oracle.simple(*a, 1000, fine, n_threads=16))
+    # 5 km: every scan of 12 granules spread over the day (a 5 km scan is 2 tie rows of its own)
+    for width in (271, 270):
+        for dt in (np.float64, np.float32):
+            subs = [testing.subsample_5km(*[x.astype(dt) for x in testing.modis_granule(g)], width=width) for g in range(0, 288, 24)]
+            a = [np.ascontiguousarray(np.concatenate([s[k] for s in subs])) for k in range(3)]
+            report(f"cviirs 5km({width})->1km {np.dtype(dt).name}", modisinterpolator.modis_5km_to_1km(*a),
+                   gtp_oracle.cviirs(*a, 5000, 1000, width, n_threads=16))
+    # extension: float32 lon/lat + int16 zenith, float64 math -> float32
+    f = [x.astype(np.float32) for x in (lon, lat)]
+    zen = np.round(satz / 0.01).astype(np.int16)
+    exp = gtp_oracle.cviirs(f[0].astype(np.float64), f[1].astype(np.float64), zen.astype(np.float64) * 0.01, 1000, 250, 0, n_threads=16)
+    report("mod03 1km->250m f32+i16 -> f64", mod03.modis_1km_to_250m(*f, zen, zenith_scale=0.01, out_dtype=np.float64), exp)
+    report("mod03 1km->250m f32+i16 -> f32", mod03.modis_1km_to_250m(*f, zen, zenith_scale=0.01),
+           tuple(x.astype(np.float32) for x in exp))
