@@ -57,10 +57,10 @@ __device__ __forceinline__ void quad_rows(const QuadF32& q, const float (&s_s)[P
         float vlon[P], vlat[P];
 #pragma unroll
         for (int k = 0; k < P; ++k) {
-            float v[3];
+            double v[3];
             blend_f32(q, rc, s_s[k], k1d[k], v);
             if (MODE == kSlow) {
-                const LonLatF ll = backtransform_f32_slow(v[0], v[1], v[2]);
+                const LonLatF ll = backtransform_f32_slow((float)v[0], (float)v[1], (float)v[2]);
                 vlon[k] = ll.lon; vlat[k] = ll.lat;
             } else {
                 backtransform_f32<MODE, WRAP>(q, v, vlon[k], vlat[k]);

@@ -14,7 +14,8 @@
 //     _modis_utils.pyx:51-57) with the anchor-relative series of gtp_fast_math.cuh around the
 //     FLOAT32-ROUNDED corner A of the quad: two inverse-trig calls, a sqrt and two divisions per
 //     pixel become ~25 FMAs, accurate to ~1e-13 deg before the final rounding to float32.
-// Per pixel that is ~28 float<->double conversions (16/clk/SM on B200) and ~45 FP64 instructions,
+// Per pixel that is ~22 float<->double conversions (16/clk/SM on B200; the last rounding of the fine
+// xyz is done on the FP64 pipe, round_to_f32) and ~55 FP64 instructions,
 // against ~370 FP64-pipe slots of the rounding-faithful kernel in gtp_generic.cu.
 #pragma once
 #include "gtp_fast_math.cuh"
@@ -39,6 +40,20 @@ GTP_FD float fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 GTP_FD float fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 GTP_FD float fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 #endif
+
+// x rounded to float32 precision, as a double: what `(double)(float)x` gives, but on the FP64 pipe
+// (Veltkamp's splitting with 2^29 + 1: 3 instructions) instead of two F2F conversions on the XU pipe,
+// which the kernel is bound by (ncu: XU 80 % busy, F2F = 21 % of the instructions).  Round to nearest;
+// a tie (the low 29 bits exactly 1000...0, one value in 5e8) may break either way.
+GTP_FD double round_to_f32(double x)
+{
+#ifdef __CUDA_ARCH__
+    const double c = mul_rn(x, 536870913.0);
+    return add_rn(c, -add_rn(c, -x));
+#else
+    return (double)(float)x;
+#endif
+}
 
 struct TieGeoF {           // geometry of one float32 tie point
     float x, y, z;         // lonlat2xyz, rounded to float (_modis_utils.pyx:38-40)
@@ -204,7 +219,8 @@ GTP_FD RowF32 row_setup_f32(const QuadF32& q, float s_t)
 
 // The float32 fine xyz of one pixel, with the reference's rounding points (:344, :396-398).
 // k1d = (double)s_s * (1.0 - (double)s_s)
-GTP_FD void blend_f32(const QuadF32& q, const RowF32& r, float s_s, double k1d, float (&v)[3])
+// v[k] are float32 values held in doubles (the reference promotes them to double next, :51-57)
+GTP_FD void blend_f32(const QuadF32& q, const RowF32& r, float s_s, double k1d, double (&v)[3])
 {
     const double a_d = add_rn(add_rn((double)s_s, mul_rn(k1d, (double)q.ce)), r.row_ca);
     const float a = (float)a_d;
@@ -213,16 +229,16 @@ GTP_FD void blend_f32(const QuadF32& q, const RowF32& r, float s_s, double k1d, 
     for (int k = 0; k < 3; ++k) {
         const float s1 = (float)add_rn(mul_rn(oma, q.A[k]), (double)fmul_rn(a, q.B[k]));
         const float s2 = (float)add_rn(mul_rn(oma, q.D[k]), (double)fmul_rn(a, q.C[k]));
-        v[k] = (float)add_rn(mul_rn(r.omt, (double)s1), (double)fmul_rn(r.s_t, s2));
+        v[k] = round_to_f32(add_rn(mul_rn(r.omt, (double)s1), (double)fmul_rn(r.s_t, s2)));
     }
 }
 
 // xyz2lonlat of the float32 xyz, anchor-relative in double, result rounded to float (:51-65)
 template <int MODE, bool WRAP>
-GTP_FD void backtransform_f32(const QuadF32& q, const float (&v)[3], float& lon, float& lat)
+GTP_FD void backtransform_f32(const QuadF32& q, const double (&v)[3], float& lon, float& lat)
 {
-    const double zd = (double)v[2];
-    const double dx = (double)v[0] - q.A[0], dy = (double)v[1] - q.A[1], dz = zd - q.A[2];
+    const double zd = v[2];
+    const double dx = v[0] - q.A[0], dy = v[1] - q.A[1], dz = zd - q.A[2];
     const double e = fma(q.ue0, dx, q.ue1 * dy);
     const double h = fma(q.uh0, dx, q.uh1 * dy);
     const double w = dz * kInvEarthR;

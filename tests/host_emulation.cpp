@@ -173,9 +173,10 @@ static void run_f32(const float* lon, const float* lat, const float* satz, long 
                     for (int k = 0; k < P; ++k) {
                         const float s_s = (float)(xoff + k) / (float)P;
                         const double k1d = mul_rn((double)s_s, add_rn(1.0, -(double)s_s));
-                        float v[3], lo, la;
+                        double v[3];
+                        float lo, la;
                         blend_f32(q, rc, s_s, k1d, v);
-                        if (q.mode == kSlow) { const LonLatF ll = backtransform_f32_slow(v[0], v[1], v[2]); lo = ll.lon; la = ll.lat; }
+                        if (q.mode == kSlow) { const LonLatF ll = backtransform_f32_slow((float)v[0], (float)v[1], (float)v[2]); lo = ll.lon; la = ll.lat; }
                         else if (q.wrap) backtransform_f32<kBoth, true>(q, v, lo, la);
                         else if (q.mode == kLow) backtransform_f32<kLow, false>(q, v, lo, la);
                         else if (q.mode == kHigh) backtransform_f32<kHigh, false>(q, v, lo, la);
