@@ -31,7 +31,7 @@ constexpr int kF = 5;                // fine pixels per coarse pixel (5 km -> 1 
 constexpr int kRows = 10;            // fine rows per scan
 constexpr int kQuadsPerWarp = 30;    // 150 fine columns: every warp's span starts on an even column (16 B);
                                      // lane 30 provides the right-hand corners of lane 29
-constexpr int kThreads5 = 128;
+constexpr int kThreads5 = 32;     // one warp = one strip: a CTA slot is free again as soon as its strip is done
 constexpr unsigned kFull = 0xffffffffu;
 
 // s_t = y / f, y = j - 2 (:231-249, :341-343) and s_s = x / f for x = -5 ... 11 (index x + 5)
@@ -43,10 +43,11 @@ __constant__ double kScan5[17] = {-5.0 / 5.0, -4.0 / 5.0, -3.0 / 5.0, -2.0 / 5.0
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(kFull, v, src); }
 
-// every field a virtual lane needs of the quad it helps with
+// the four Cartesian corners of a quad: only the rounding-faithful fallback needs them after the set-up,
+// so they wait in shared memory (12 doubles per lane) instead of in 24 registers through the row loops
 struct QuadCorners { Vec3 A, B, C, D; };
 
-__device__ __forceinline__ void take_quad_from(Quad& q, QuadCorners& x, int src, bool take)
+__device__ __forceinline__ void take_quad_from(Quad& q, int src, bool take)
 {
 #define GTP_TAKE(f) { const double v_ = shfl_d(f, src); if (take) f = v_; }
     { const int m_ = __shfl_sync(kFull, q.mode, src); if (take) q.mode = m_; }
@@ -57,8 +58,6 @@ __device__ __forceinline__ void take_quad_from(Quad& q, QuadCorners& x, int src,
     GTP_TAKE(q.lon0) GTP_TAKE(q.lat0) GTP_TAKE(q.s0)
     GTP_TAKE(q.a1) GTP_TAKE(q.a2) GTP_TAKE(q.a3) GTP_TAKE(q.a4) GTP_TAKE(q.a5) GTP_TAKE(q.a6) GTP_TAKE(q.a7) GTP_TAKE(q.a8)
     GTP_TAKE(q.b1) GTP_TAKE(q.b2) GTP_TAKE(q.b3) GTP_TAKE(q.b4) GTP_TAKE(q.b5) GTP_TAKE(q.b6) GTP_TAKE(q.b7) GTP_TAKE(q.b8)
-    GTP_TAKE(x.A.x) GTP_TAKE(x.A.y) GTP_TAKE(x.A.z) GTP_TAKE(x.B.x) GTP_TAKE(x.B.y) GTP_TAKE(x.B.z)
-    GTP_TAKE(x.C.x) GTP_TAKE(x.C.y) GTP_TAKE(x.C.z) GTP_TAKE(x.D.x) GTP_TAKE(x.D.y) GTP_TAKE(x.D.z)
 #undef GTP_TAKE
 }
 
@@ -74,7 +73,7 @@ __device__ __forceinline__ void store_pair(float* dst, int pair, double2 v)
 // TIn / TZen / TOut as in gtp_fast.cu: all-double is the reference's interface; float lon/lat, float
 // or int16 * zen_scale + zen_offset zenith angles and float | double results serve gtp_cviirs_interp_mixed.
 template <typename TIn, typename TZen, typename TOut>
-__global__ void __launch_bounds__(kThreads5, 4)
+__global__ void __launch_bounds__(kThreads5, 16)
 modis_fast_5km_f64_kernel(const TIn* __restrict__ lon, const TIn* __restrict__ lat,
                           const TZen* __restrict__ satz, TOut* __restrict__ out_lon,
                           TOut* __restrict__ out_lat, long long n_scans, int W, int warps_per_scan,
@@ -125,6 +124,16 @@ modis_fast_5km_f64_kernel(const TIn* __restrict__ lon, const TIn* __restrict__ l
         const QuadSize sz = quad_project(q, top, x.A, x.B, x.C, x.D, a_max);
         quad_classify_long(q, top, sz, ce, ca);
     }
+    __shared__ double corners[12][kThreads5];
+    {
+        double* const cs = &corners[0][threadIdx.x];
+        cs[0 * kThreads5] = x.A.x; cs[1 * kThreads5] = x.A.y; cs[2 * kThreads5] = x.A.z;
+        cs[3 * kThreads5] = x.B.x; cs[4 * kThreads5] = x.B.y; cs[5 * kThreads5] = x.B.z;
+        cs[6 * kThreads5] = x.C.x; cs[7 * kThreads5] = x.C.y; cs[8 * kThreads5] = x.C.z;
+        cs[9 * kThreads5] = x.D.x; cs[10 * kThreads5] = x.D.y; cs[11 * kThreads5] = x.D.z;
+    }
+    __syncwarp();                             // virtual lanes read another lane's slot
+    int corner_lane = threadIdx.x;            // whose corners this lane evaluates (virtual lanes: the source quad's)
 
     // ---- lane roles --------------------------------------------------------------------------
     // real lanes: columns x = 0..4 of their quad.  Virtual lanes (idle otherwise) take over the
@@ -138,8 +147,10 @@ modis_fast_5km_f64_kernel(const TIn* __restrict__ lon, const TIn* __restrict__ l
         const bool v_first = first_warp && (lane == 31);
         const bool v_last1 = last_warp && (lane == last_lane + 1);
         const bool v_last2 = last_warp && (lane == last_lane + 2) && (n_extra > kF);
-        if (first_warp) take_quad_from(q, x, 0, v_first);
-        if (last_warp) take_quad_from(q, x, last_lane, v_last1 || v_last2);
+        if (first_warp) take_quad_from(q, 0, v_first);
+        if (last_warp) take_quad_from(q, last_lane, v_last1 || v_last2);
+        if (v_first) corner_lane = (threadIdx.x & ~31);
+        if (v_last1 || v_last2) corner_lane = (threadIdx.x & ~31) + last_lane;
         if (v_first) { src_quad = 0; xoff = -kF; kmask = 0x18u; }                       // k = 3, 4 -> x = -2, -1
         if (v_last1) { src_quad = n_quads - 1; xoff = kF; kmask = (n_extra >= kF) ? 0x1fu : ((1u << n_extra) - 1u); }
         if (v_last2) { src_quad = n_quads - 1; xoff = 2 * kF; kmask = (1u << (n_extra - kF)) - 1u; }
@@ -235,7 +246,13 @@ modis_fast_5km_f64_kernel(const TIn* __restrict__ lon, const TIn* __restrict__ l
 #pragma unroll 1
             for (int k = 0; k < kF; ++k) {
                 if (!((kmask >> k) & 1u)) continue;
-                const LonLat ll = pixel_eval_slow(x.A, x.B, x.C, x.D, q.ce, q.ca, kScan5[xoff + k + 5], s_t);
+                const double* const cs = &corners[0][corner_lane];
+                Vec3 cA, cB, cC, cD;
+                cA.x = cs[0 * kThreads5]; cA.y = cs[1 * kThreads5]; cA.z = cs[2 * kThreads5];
+                cB.x = cs[3 * kThreads5]; cB.y = cs[4 * kThreads5]; cB.z = cs[5 * kThreads5];
+                cC.x = cs[6 * kThreads5]; cC.y = cs[7 * kThreads5]; cC.z = cs[8 * kThreads5];
+                cD.x = cs[9 * kThreads5]; cD.y = cs[10 * kThreads5]; cD.z = cs[11 * kThreads5];
+                const LonLat ll = pixel_eval_slow(cA, cB, cC, cD, q.ce, q.ca, kScan5[xoff + k + 5], s_t);
                 my_lon[k] = ll.lon; my_lat[k] = ll.lat;
             }
         }
