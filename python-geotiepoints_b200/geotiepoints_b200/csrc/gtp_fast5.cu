@@ -188,6 +188,13 @@ modis_fast_5km_f64_kernel(const TIn* __restrict__ lon, const TIn* __restrict__ l
         pixel_eval_long<MODE_>(q, rc, a_col[k], lo_, la_);                                 \
         if (!(MASKED_) || ((kmask >> k) & 1u)) { my_lon[k] = lo_; my_lat[k] = la_; }       \
     }
+    // the same with the 5-term forms of the 1 km path (Quad::small)
+#define GTP_STAGE_SHORT(MODE_)                                                             \
+    _Pragma("unroll") for (int k = 0; k < kF; ++k) {                                       \
+        double lo_, la_;                                                                   \
+        pixel_eval<MODE_, false>(q, rc, a_col[k], lo_, la_);                               \
+        my_lon[k] = lo_; my_lat[k] = la_;                                                  \
+    }
     const bool edge = first_warp || last_warp;                       // warp-uniform
     TOut* dst_lon = out_lon + row0;
     TOut* dst_lat = out_lat + row0;
@@ -210,6 +217,31 @@ modis_fast_5km_f64_kernel(const TIn* __restrict__ lon, const TIn* __restrict__ l
     // the per-row dispatch (lanes 30 and 31 own no quad there and only help with the copy).
     const bool all_low = !edge && __all_sync(kFull, mode == kLow || mode < 0);
     const bool all_high = !edge && __all_sync(kFull, mode == kHigh || mode < 0);
+    const bool all_short = __all_sync(kFull, q.small || mode < 0);
+    if (all_low && all_short) {
+#pragma unroll 1
+        for (int j = 0; j < kRows; ++j) {
+            if (mode >= 0) {
+                const double s_t = kTrack5[j];
+                const RowCoef rc = row_setup(q, s_t, s_t * (1.0 - s_t));
+                GTP_STAGE_SHORT(kLow)
+            }
+            GTP_COPY_OUT()
+        }
+        return;
+    }
+    if (all_high && all_short) {
+#pragma unroll 1
+        for (int j = 0; j < kRows; ++j) {
+            if (mode >= 0) {
+                const double s_t = kTrack5[j];
+                const RowCoef rc = row_setup(q, s_t, s_t * (1.0 - s_t));
+                GTP_STAGE_SHORT(kHigh)
+            }
+            GTP_COPY_OUT()
+        }
+        return;
+    }
     if (all_low) {
 #pragma unroll 1
         for (int j = 0; j < kRows; ++j) {
@@ -259,6 +291,7 @@ modis_fast_5km_f64_kernel(const TIn* __restrict__ lon, const TIn* __restrict__ l
         GTP_COPY_OUT()
     }
 #undef GTP_COPY_OUT
+#undef GTP_STAGE_SHORT
 #undef GTP_STAGE
 }
 

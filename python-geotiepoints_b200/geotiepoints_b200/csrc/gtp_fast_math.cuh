@@ -646,6 +646,9 @@ GTP_FD void quad_classify_long(Quad& q, const TieGeo& A, const QuadSize& sz, dou
         ok = ok && (absd(b9) * (v4 * v4 * vmax) <= kLongTerm);
     }
     if (!ok) q.mode = kSlow;
+    // most 5 km quads are still within the limits the 5-term forms of the 1 km path are good for
+    // (pixel_eval<kLow | kHigh>: atan to t^5, a Newton reciprocal, series to the 5th order)
+    q.small = (q.mode == kLow || q.mode == kHigh) && !q.wrap && (horiz <= kMaxRelHoriz) && (wmax <= kMaxRelZ);
 }
 
 // One fine pixel of a 5 km quad.  MODE = kLow | kHigh | kBoth (kBoth also does the +-180 wrap).

@@ -122,6 +122,7 @@ extern "C" int gtp_emul_cviirs_fast5_f64(const double* lon, const double* lat, c
             const QuadSize sz = quad_project(q, top[0], A, B, C, D, a_max);
             quad_classify_long(q, top[0], sz, ce, cal);
             mode_counts[q.mode]++;
+            if (q.mode != kSlow && q.small) mode_counts[4]++;
             const int i0 = (qc == 0) ? 0 : 2 + 5 * qc, i1 = (qc == nq - 1) ? Wf : 2 + 5 * qc + 5;
             for (int j = 0; j < 10; ++j) {
                 const double s_t = (double)(j - 2) / 5.0;
@@ -131,6 +132,8 @@ extern "C" int gtp_emul_cviirs_fast5_f64(const double* lon, const double* lat, c
                     const double a_col = fma(s_s * (1.0 - s_s), q.ce, s_s);
                     double lo, la;
                     if (q.mode == kSlow) { const LonLat ll = pixel_eval_slow(A, B, C, D, q.ce, q.ca, s_s, s_t); lo = ll.lon; la = ll.lat; }
+                    else if (q.small && q.mode == kLow) pixel_eval<kLow, false>(q, rc, a_col, lo, la);      // the kernel: whole warps only
+                    else if (q.small && q.mode == kHigh) pixel_eval<kHigh, false>(q, rc, a_col, lo, la);
                     else if (!q.wrap && q.mode == kLow) pixel_eval_long<kLow>(q, rc, a_col, lo, la);
                     else if (!q.wrap && q.mode == kHigh) pixel_eval_long<kHigh>(q, rc, a_col, lo, la);
                     else pixel_eval_long<kBoth>(q, rc, a_col, lo, la);
