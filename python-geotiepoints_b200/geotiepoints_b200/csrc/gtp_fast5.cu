@@ -52,6 +52,7 @@ __device__ __forceinline__ void take_quad_from(Quad& q, int src, bool take)
 #define GTP_TAKE(f) { const double v_ = shfl_d(f, src); if (take) f = v_; }
     { const int m_ = __shfl_sync(kFull, q.mode, src); if (take) q.mode = m_; }
     { const int w_ = __shfl_sync(kFull, (int)q.wrap, src); if (take) q.wrap = (w_ != 0); }
+    { const int s_ = __shfl_sync(kFull, (int)q.small, src); if (take) q.small = (s_ != 0); }
     GTP_TAKE(q.ce) GTP_TAKE(q.ca)
     GTP_TAKE(q.Pe) GTP_TAKE(q.Ph) GTP_TAKE(q.Pw) GTP_TAKE(q.Qe) GTP_TAKE(q.Qh) GTP_TAKE(q.Qw)
     GTP_TAKE(q.Se) GTP_TAKE(q.Sh) GTP_TAKE(q.Sw)
