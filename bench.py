@@ -46,6 +46,9 @@ CONFIGS = {
     "simple_1km_500m": dict(kind="simple", coarse=1000, fine=500, width=0, n_in=2, tie_rows=2030, tie_cols=1354, f=2, out_cols=2708),
     # extension: float32 lon/lat + int16 zenith in, float64 math, float32 out (--dtype is ignored)
     "mod03_1km_250m": dict(kind="mixed", coarse=1000, fine=250, width=0, n_in=3, tie_rows=2030, tie_cols=1354, f=4, out_cols=5416),
+    # extension: ECEF x / y / z instead of lon / lat (no back-transform, three outputs)
+    "ecef_1km_250m": dict(kind="cviirs", ecef=True, coarse=1000, fine=250, width=0, n_in=3, tie_rows=2030, tie_cols=1354, f=4, out_cols=5416),
+    "mod03_ecef_1km_250m": dict(kind="mixed", ecef=True, coarse=1000, fine=250, width=0, n_in=3, tie_rows=2030, tie_cols=1354, f=4, out_cols=5416),
 }
 TIE_ROWS, TIE_COLS = 2030, 1354
 OUT_ROWS, OUT_COLS = 8120, 5416
@@ -60,9 +63,10 @@ def algorithmic_bytes_per_px(itemsize, cfg=None):
     """Each input element read once, each output written once: 17.5 B/px for
     CVIIRS 1 km -> 250 m float64."""
     cfg = cfg or CONFIGS["cviirs_1km_250m"]
-    if cfg["kind"] == "mixed":      # 2 x float32 out; float32 + float32 + int16 in
-        return 2 * 4 + (4 + 4 + 2) * (cfg["tie_rows"] * cfg["tie_cols"]) / px_per_granule(cfg)
-    return 2 * itemsize + cfg["n_in"] * itemsize * (cfg["tie_rows"] * cfg["tie_cols"]) / px_per_granule(cfg)
+    n_out = 3 if cfg.get("ecef") else 2
+    if cfg["kind"] == "mixed":      # float32 out; float32 + float32 + int16 in
+        return n_out * 4 + (4 + 4 + 2) * (cfg["tie_rows"] * cfg["tie_cols"]) / px_per_granule(cfg)
+    return n_out * itemsize + cfg["n_in"] * itemsize * (cfg["tie_rows"] * cfg["tie_cols"]) / px_per_granule(cfg)
 
 
 def parse_args():
@@ -324,6 +328,8 @@ def run_b200_arm(args, dtype):
     cfg = CONFIGS[args.config]
     headline = args.config == "cviirs_1km_250m"
     mixed = cfg["kind"] == "mixed"
+    ecef = bool(cfg.get("ecef"))
+    n_out = 3 if ecef else 2
     if mixed:
         dtype, args.dtype = np.float32, "f32"
     tdtype = torch.float64 if dtype == np.float64 else torch.float32
@@ -339,13 +345,15 @@ def run_b200_arm(args, dtype):
     n_scans = lon.shape[0] // rows_per_scan
     out_rows_per_scan = rows_per_scan * cfg["f"]
     d_in = [torch.from_numpy(a).to(device) for a in host_in]
-    out_lon = torch.empty((n_scans * out_rows_per_scan, cfg["out_cols"]), dtype=tdtype, device=device)
-    out_lat = torch.empty_like(out_lon)
+    outs = [torch.empty((n_scans * out_rows_per_scan, cfg["out_cols"]), dtype=tdtype, device=device) for _ in range(n_out)]
+    out_lon, out_lat = outs[0], outs[1]
+    out_ptrs = [o.data_ptr() for o in outs]
     lib = _capi.lib()
     suffix = "f64" if dtype == np.float64 else "f32"
-    generic = args.kernel == "generic" and (suffix == "f64" or cfg["kind"] == "cviirs") and not mixed
-    fn = lib.gtp_cviirs_interp_mixed if mixed else \
-        getattr(lib, f"gtp_{cfg['kind']}_interp_" + (("generic_" + suffix) if generic else suffix))
+    generic = args.kernel == "generic" and (suffix == "f64" or (cfg["kind"] == "cviirs" and not ecef)) and not mixed
+    xyz = "xyz_" if ecef else ""
+    fn = getattr(lib, f"gtp_cviirs_interp_{xyz}mixed") if mixed else \
+        getattr(lib, f"gtp_{cfg['kind']}_interp_{xyz}" + (("generic_" + suffix) if generic else suffix))
     stream = torch.cuda.current_stream(device)
     if cfg["kind"] == "cviirs":
         scalars = (cfg["coarse"], cfg["fine"], cfg["width"])
@@ -353,12 +361,12 @@ def run_b200_arm(args, dtype):
         scalars = (cfg["tie_cols"], cfg["coarse"] // cfg["fine"])
 
     def step():
-        if mixed:
-            rc = fn(*[t.data_ptr() for t in d_in], 1, 0.01, 0.0, n_scans, cfg["coarse"], cfg["fine"], 0,
-                    out_lon.data_ptr(), out_lat.data_ptr(), 0, local_rank, ctypes.c_void_p(stream.cuda_stream))
+        if mixed:       # the ECEF form has no coarse_width argument
+            rc = fn(*[t.data_ptr() for t in d_in], 1, 0.01, 0.0, n_scans, cfg["coarse"], cfg["fine"], *(() if ecef else (0,)),
+                    *out_ptrs, 0, local_rank, ctypes.c_void_p(stream.cuda_stream))
         else:
             rc = fn(*[t.data_ptr() for t in d_in], n_scans, *scalars,
-                    out_lon.data_ptr(), out_lat.data_ptr(), local_rank, ctypes.c_void_p(stream.cuda_stream))
+                    *out_ptrs, local_rank, ctypes.c_void_p(stream.cuda_stream))
         _capi.check(rc)
 
     def barrier():
@@ -434,8 +442,18 @@ def run_b200_arm(args, dtype):
             in_rows = np.concatenate([np.arange(s * rows_per_scan, (s + 1) * rows_per_scan) for s in picks])
             out_rows = np.concatenate([np.arange(s * out_rows_per_scan, (s + 1) * out_rows_per_scan) for s in picks])
             sub = [np.ascontiguousarray(a[in_rows]) for a in host_in]
+            idx = torch.from_numpy(out_rows).to(device)
             with np.errstate(all="ignore"):
-                if mixed:       # the float64 reference on the widened inputs, rounded once
+                if ecef:
+                    from parity import compare_xyz
+                    if mixed:
+                        exp = gtp_oracle.cviirs_xyz(sub[0].astype(np.float64), sub[1].astype(np.float64),
+                                                    sub[2].astype(np.float64) * 0.01, 1000, cfg["fine"], 0, n_threads=8)
+                        exp = tuple(a.astype(np.float32) for a in exp)
+                    else:
+                        exp = gtp_oracle.cviirs_xyz(*sub, cfg["coarse"], cfg["fine"], cfg["width"], n_threads=8)
+                    parity = compare_xyz([o[idx].cpu().numpy() for o in outs], exp)
+                elif mixed:       # the float64 reference on the widened inputs, rounded once
                     exp = gtp_oracle.cviirs(sub[0].astype(np.float64), sub[1].astype(np.float64),
                                             sub[2].astype(np.float64) * 0.01, 1000, cfg["fine"], 0, n_threads=8)
                     exp = tuple(a.astype(np.float32) for a in exp)
@@ -443,8 +461,8 @@ def run_b200_arm(args, dtype):
                     exp = gtp_oracle.cviirs(*sub, cfg["coarse"], cfg["fine"], cfg["width"], n_threads=8)
                 else:
                     exp = gtp_oracle.simple(*sub, cfg["coarse"], cfg["fine"], n_threads=8)
-            idx = torch.from_numpy(out_rows).to(device)
-            parity = compare(out_lon[idx].cpu().numpy(), out_lat[idx].cpu().numpy(), *exp)
+            if not ecef:
+                parity = compare(out_lon[idx].cpu().numpy(), out_lat[idx].cpu().numpy(), *exp)
             parity["scans_checked"] = [int(s) for s in picks]
         except Exception as exc:  # the checker must never take the measurement down
             parity = {"error": repr(exc)}
@@ -458,7 +476,12 @@ def run_b200_arm(args, dtype):
             from geotiepoints_b200 import mod03
 
             def public_api(*arrs):
-                return mod03.modis_1km_to_250m(*arrs, zenith_scale=0.01)
+                return mod03.modis_1km_to_250m(*arrs, zenith_scale=0.01, ecef=ecef)
+        elif ecef:
+            from geotiepoints_b200 import ecef as ecef_api
+
+            def public_api(*arrs):
+                return ecef_api.interpolate(*arrs, cfg["coarse"], cfg["fine"], cfg["width"])
         elif cfg["kind"] == "cviirs":
             def public_api(*arrs):
                 return cviirs_interpolate(*arrs, coarse_resolution=cfg["coarse"], fine_resolution=cfg["fine"],
@@ -491,7 +514,7 @@ def run_b200_arm(args, dtype):
         e2e_px = ge * px_per_granule(cfg)
         e2e = {"value": e2e_px * world * e2e_steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(sum(a.dtype.itemsize for a in host_in) * rows * cfg["tie_cols"]),
-               "d2h_bytes_per_step": int(2 * e2e_px * itemsize),
+               "d2h_bytes_per_step": int(n_out * e2e_px * itemsize),
                "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
                "host_cpus_bound_to_gpu": len(bound_cpus) if bound_cpus else None,
                "sample": f"{ge} granules per GPU per call through the public numpy API "

@@ -131,6 +131,52 @@ int gtp_simple_interp_mixed(const float* lon, const float* lat, int64_t n_scans,
 int gtp_simple_interp_mixed_host(const float* lon, const float* lat, int64_t n_scans, int res_factor,
                                  void* out_lon, void* out_lat, int out_kind, int device);
 
+/* ---- ECEF output (extension) ---------------------------------- */
+/* The fine Cartesian coordinates x, y, z (metres; sphere of radius 6370997 m, _modis_utils.pyx:23) that
+ * the reference computes in MODISInterpolator._compute_fine_xyz (_modis_interpolator.pyx:346-398) -
+ * new_xyz in _simple_modis_interpolator.pyx:52-63 - and hands to xyz2lonlat (:293): the same operators
+ * stopped one step earlier, for consumers (resampling) that convert lon / lat straight back to ECEF.
+ * Three outputs of the shape of out_lon / out_lat above.  The _f32 / _f64 forms follow the reference's
+ * arithmetic in that type for every configuration (float64 1 km tie points of width 1354 with
+ * 4- | 2-element aligned outputs take gtp_fast_xyz.cu, everything else the rounding-faithful kernels;
+ * _generic_ forces the latter); the _mixed forms take MOD03's on-disk types like gtp_cviirs_interp_mixed
+ * (float64 math, float32 | float64 out; coarse_res 1000 with fine_res 250 | 500 only). */
+int gtp_cviirs_interp_xyz_f32(const float* lon, const float* lat, const float* satz, int64_t n_scans,
+                              int coarse_res, int fine_res, int coarse_width,
+                              float* out_x, float* out_y, float* out_z, int device, void* stream);
+int gtp_cviirs_interp_xyz_f64(const double* lon, const double* lat, const double* satz, int64_t n_scans,
+                              int coarse_res, int fine_res, int coarse_width,
+                              double* out_x, double* out_y, double* out_z, int device, void* stream);
+int gtp_cviirs_interp_xyz_generic_f64(const double* lon, const double* lat, const double* satz, int64_t n_scans,
+                                      int coarse_res, int fine_res, int coarse_width,
+                                      double* out_x, double* out_y, double* out_z, int device, void* stream);
+int gtp_simple_interp_xyz_f32(const float* lon, const float* lat, int64_t n_scans, int64_t width, int res_factor,
+                              float* out_x, float* out_y, float* out_z, int device, void* stream);
+int gtp_simple_interp_xyz_f64(const double* lon, const double* lat, int64_t n_scans, int64_t width, int res_factor,
+                              double* out_x, double* out_y, double* out_z, int device, void* stream);
+int gtp_simple_interp_xyz_generic_f64(const double* lon, const double* lat, int64_t n_scans, int64_t width, int res_factor,
+                                      double* out_x, double* out_y, double* out_z, int device, void* stream);
+int gtp_cviirs_interp_xyz_host_f32(const float* lon, const float* lat, const float* satz, int64_t n_scans,
+                                   int coarse_res, int fine_res, int coarse_width,
+                                   float* out_x, float* out_y, float* out_z, int device);
+int gtp_cviirs_interp_xyz_host_f64(const double* lon, const double* lat, const double* satz, int64_t n_scans,
+                                   int coarse_res, int fine_res, int coarse_width,
+                                   double* out_x, double* out_y, double* out_z, int device);
+int gtp_simple_interp_xyz_host_f32(const float* lon, const float* lat, int64_t n_scans, int64_t width, int res_factor,
+                                   float* out_x, float* out_y, float* out_z, int device);
+int gtp_simple_interp_xyz_host_f64(const double* lon, const double* lat, int64_t n_scans, int64_t width, int res_factor,
+                                   double* out_x, double* out_y, double* out_z, int device);
+int gtp_cviirs_interp_xyz_mixed(const float* lon, const float* lat, const void* satz, int zen_kind,
+                                double zen_scale, double zen_offset, int64_t n_scans, int coarse_res, int fine_res,
+                                void* out_x, void* out_y, void* out_z, int out_kind, int device, void* stream);
+int gtp_cviirs_interp_xyz_mixed_host(const float* lon, const float* lat, const void* satz, int zen_kind,
+                                     double zen_scale, double zen_offset, int64_t n_scans, int coarse_res, int fine_res,
+                                     void* out_x, void* out_y, void* out_z, int out_kind, int device);
+int gtp_simple_interp_xyz_mixed(const float* lon, const float* lat, int64_t n_scans, int res_factor,
+                                void* out_x, void* out_y, void* out_z, int out_kind, int device, void* stream);
+int gtp_simple_interp_xyz_mixed_host(const float* lon, const float* lat, int64_t n_scans, int res_factor,
+                                     void* out_x, void* out_y, void* out_z, int out_kind, int device);
+
 /* The host entry points keep up to 4 idle sets of (3 streams + chunk scratch, ~300 MB of
  * device memory each) per process for the next call; gtp_trim() frees them. */
 int gtp_trim(void);

@@ -36,6 +36,12 @@ def lib():
             fn = getattr(_lib, f"gtp_oracle_simple_{suf}")
             fn.restype = ctypes.c_int
             fn.argtypes = [p, p, ctypes.c_long, ctypes.c_long, ctypes.c_int, p, p, ctypes.c_int]
+            fn = getattr(_lib, f"gtp_oracle_cviirs_xyz_{suf}")
+            fn.restype = ctypes.c_int
+            fn.argtypes = [p, p, p, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_int, p, p, p, ctypes.c_int]
+            fn = getattr(_lib, f"gtp_oracle_simple_xyz_{suf}")
+            fn.restype = ctypes.c_int
+            fn.argtypes = [p, p, ctypes.c_long, ctypes.c_long, ctypes.c_int, p, p, p, ctypes.c_int]
     return _lib
 
 
@@ -86,3 +92,33 @@ def simple(lon, lat, coarse_resolution, fine_resolution, n_threads=1):
     if rc:
         raise ValueError(f"oracle simple rc={rc}")
     return out_lon, out_lat
+
+
+def cviirs_xyz(lon, lat, satz, coarse_resolution, fine_resolution, coarse_scan_width=0, n_threads=1):
+    """Fine ECEF coordinates (metres) of ``_compute_fine_xyz`` (``_modis_interpolator.pyx:346-398``)."""
+    lon, lat, satz = (np.ascontiguousarray(a) for a in (lon, lat, satz))
+    assert lon.dtype == lat.dtype == satz.dtype and lon.shape == lat.shape == satz.shape
+    L = 10 if coarse_resolution == 1000 else 2
+    f = (1000 // fine_resolution) * (coarse_resolution // 1000)
+    if coarse_resolution == 5000:
+        coarse_scan_width = coarse_scan_width or lon.shape[1]
+    out = [np.empty((lon.shape[0] * f, 1354 * (1000 // fine_resolution)), dtype=lon.dtype) for _ in range(3)]
+    fn = getattr(lib(), "gtp_oracle_cviirs_xyz_" + _suffix(lon.dtype))
+    rc = fn(_ptr(lon), _ptr(lat), _ptr(satz), lon.shape[0] // L, coarse_resolution, fine_resolution,
+            coarse_scan_width, *[_ptr(o) for o in out], n_threads)
+    if rc:
+        raise ValueError(f"oracle cviirs_xyz rc={rc}")
+    return tuple(out)
+
+
+def simple_xyz(lon, lat, coarse_resolution, fine_resolution, n_threads=1):
+    """Fine ECEF coordinates of the simple interpolator (``_simple_modis_interpolator.pyx:52-63``)."""
+    lon, lat = (np.ascontiguousarray(a) for a in (lon, lat))
+    assert lon.dtype == lat.dtype and lon.shape == lat.shape
+    res = coarse_resolution // fine_resolution
+    out = [np.empty((lon.shape[0] * res, lon.shape[1] * res), dtype=lon.dtype) for _ in range(3)]
+    fn = getattr(lib(), "gtp_oracle_simple_xyz_" + _suffix(lon.dtype))
+    rc = fn(_ptr(lon), _ptr(lat), lon.shape[0] // 10, lon.shape[1], res, *[_ptr(o) for o in out], n_threads)
+    if rc:
+        raise ValueError(f"oracle simple_xyz rc={rc}")
+    return tuple(out)

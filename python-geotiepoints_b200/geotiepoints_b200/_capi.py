@@ -41,7 +41,18 @@ for _suf in ("f32", "f64"):
     SIGNATURES[f"gtp_simple_interp_{_suf}"] = (_int, [_vp, _vp, _i64, _i64, _int, _vp, _vp, _int, _vp])
     SIGNATURES[f"gtp_cviirs_interp_host_{_suf}"] = (_int, [_vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _int])
     SIGNATURES[f"gtp_simple_interp_host_{_suf}"] = (_int, [_vp, _vp, _i64, _i64, _int, _vp, _vp, _int])
+    # ECEF output: three output pointers instead of two
+    SIGNATURES[f"gtp_cviirs_interp_xyz_{_suf}"] = (_int, [_vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _int, _vp])
+    SIGNATURES[f"gtp_simple_interp_xyz_{_suf}"] = (_int, [_vp, _vp, _i64, _i64, _int, _vp, _vp, _vp, _int, _vp])
+    SIGNATURES[f"gtp_cviirs_interp_xyz_host_{_suf}"] = (_int, [_vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _int])
+    SIGNATURES[f"gtp_simple_interp_xyz_host_{_suf}"] = (_int, [_vp, _vp, _i64, _i64, _int, _vp, _vp, _vp, _int])
 _dbl = ctypes.c_double
+SIGNATURES["gtp_cviirs_interp_xyz_generic_f64"] = SIGNATURES["gtp_cviirs_interp_xyz_f64"]
+SIGNATURES["gtp_simple_interp_xyz_generic_f64"] = SIGNATURES["gtp_simple_interp_xyz_f64"]
+SIGNATURES["gtp_cviirs_interp_xyz_mixed"] = (_int, [_vp, _vp, _vp, _int, _dbl, _dbl, _i64, _int, _int, _vp, _vp, _vp, _int, _int, _vp])
+SIGNATURES["gtp_cviirs_interp_xyz_mixed_host"] = (_int, [_vp, _vp, _vp, _int, _dbl, _dbl, _i64, _int, _int, _vp, _vp, _vp, _int, _int])
+SIGNATURES["gtp_simple_interp_xyz_mixed"] = (_int, [_vp, _vp, _i64, _int, _vp, _vp, _vp, _int, _int, _vp])
+SIGNATURES["gtp_simple_interp_xyz_mixed_host"] = (_int, [_vp, _vp, _i64, _int, _vp, _vp, _vp, _int, _int])
 SIGNATURES["gtp_cviirs_interp_mixed"] = (_int, [_vp, _vp, _vp, _int, _dbl, _dbl, _i64, _int, _int, _int, _vp, _vp, _int, _int, _vp])
 SIGNATURES["gtp_cviirs_interp_mixed_host"] = (_int, [_vp, _vp, _vp, _int, _dbl, _dbl, _i64, _int, _int, _int, _vp, _vp, _int, _int])
 SIGNATURES["gtp_simple_interp_mixed"] = (_int, [_vp, _vp, _i64, _int, _vp, _vp, _int, _int, _vp])

@@ -40,7 +40,11 @@ class MODISInterpolator:
         self._fine_pixels_per_coarse_pixel = fine_pixels_per_1km * (coarse_resolution // 1000)
         self._fine_scan_width = 1354 * fine_pixels_per_1km
 
-    def interpolate(self, lon1, lat1, satz1):
+    def interpolate_xyz(self, lon1, lat1, satz1):
+        """The fine Cartesian coordinates ``(x, y, z)`` of ``_compute_fine_xyz`` (``:346-398``), metres."""
+        return self.interpolate(lon1, lat1, satz1, ecef=True)
+
+    def interpolate(self, lon1, lat1, satz1, ecef=False):
         arrays = [lon1, lat1, satz1]
         rows, cols = _operator._check_2d_same_shape(arrays)
         # The reference silently leaves trailing rows uninitialised when the row count is
@@ -54,4 +58,4 @@ class MODISInterpolator:
         n_scans = rows // self._coarse_scan_length
         out_shape = (rows * self._fine_pixels_per_coarse_pixel, self._fine_scan_width)
         return _operator.run("cviirs", arrays, n_scans, out_shape,
-                             (self._coarse_resolution, self._fine_resolution, self._coarse_scan_width))
+                             (self._coarse_resolution, self._fine_resolution, self._coarse_scan_width), ecef=ecef)

@@ -33,29 +33,29 @@ def _check_2d_same_shape(arrays):
     return shape
 
 
-def run(kind, arrays, n_scans, out_shape, scalar_args):
+def run(kind, arrays, n_scans, out_shape, scalar_args, ecef=False):
     """Run one operator.
 
     ``kind`` is ``"cviirs"`` or ``"simple"``; ``arrays`` are the 2 or 3 inputs (all numpy
     or all torch CUDA tensors); ``scalar_args`` are the integer arguments between
     ``n_scans`` and the output pointers in the C signature.
-    Returns ``(lon, lat)`` of the same container type and dtype as the inputs.
+    Returns ``(lon, lat)`` - with ``ecef`` the Cartesian ``(x, y, z)`` the reference back-transforms
+    (``gtp_*_interp_xyz_*``) - of the same container type and dtype as the inputs.
     """
     lib = _capi.lib()
     if all(_is_torch_tensor(a) for a in arrays):
-        return _run_torch(lib, kind, arrays, n_scans, out_shape, scalar_args)
+        return _run_torch(lib, kind, arrays, n_scans, out_shape, scalar_args, ecef)
     arrays = [np.ascontiguousarray(a) for a in arrays]
     suffix = _check_same_dtype(arrays)
-    out_lon = _capi.pinned_pool.empty(out_shape, arrays[0].dtype)
-    out_lat = _capi.pinned_pool.empty(out_shape, arrays[0].dtype)
-    fn = getattr(lib, f"gtp_{kind}_interp_host_{suffix}")
+    out = [_capi.pinned_pool.empty(out_shape, arrays[0].dtype) for _ in range(3 if ecef else 2)]
+    fn = getattr(lib, f"gtp_{kind}_interp_{'xyz_' if ecef else ''}host_{suffix}")
     ptrs = [a.ctypes.data for a in arrays]
-    rc = fn(*ptrs, n_scans, *scalar_args, out_lon.ctypes.data, out_lat.ctypes.data, -1)
+    rc = fn(*ptrs, n_scans, *scalar_args, *[o.ctypes.data for o in out], -1)
     _capi.check(rc)
-    return out_lon, out_lat
+    return tuple(out)
 
 
-def _run_torch(lib, kind, arrays, n_scans, out_shape, scalar_args):
+def _run_torch(lib, kind, arrays, n_scans, out_shape, scalar_args, ecef=False):
     import torch
     first = arrays[0]
     if not first.is_cuda:
@@ -65,11 +65,10 @@ def _run_torch(lib, kind, arrays, n_scans, out_shape, scalar_args):
     for a in arrays[1:]:
         if a.device != first.device:
             raise ValueError("all input tensors must live on the same device")
-    out_lon = torch.empty(out_shape, dtype=first.dtype, device=first.device)
-    out_lat = torch.empty(out_shape, dtype=first.dtype, device=first.device)
+    out = [torch.empty(out_shape, dtype=first.dtype, device=first.device) for _ in range(3 if ecef else 2)]
     stream = torch.cuda.current_stream(first.device).cuda_stream
-    fn = getattr(lib, f"gtp_{kind}_interp_{suffix}")
+    fn = getattr(lib, f"gtp_{kind}_interp_{'xyz_' if ecef else ''}{suffix}")
     rc = fn(*[a.data_ptr() for a in arrays], n_scans, *scalar_args,
-            out_lon.data_ptr(), out_lat.data_ptr(), first.device.index, ctypes.c_void_p(stream))
+            *[o.data_ptr() for o in out], first.device.index, ctypes.c_void_p(stream))
     _capi.check(rc)
-    return out_lon, out_lat
+    return tuple(out)

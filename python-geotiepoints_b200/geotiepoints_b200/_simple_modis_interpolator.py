@@ -8,7 +8,7 @@ from . import _operator
 from ._modis_utils import rows_per_scan_for_resolution
 
 
-def interpolate_geolocation_cartesian(lon_array, lat_array, coarse_resolution, fine_resolution):
+def interpolate_geolocation_cartesian(lon_array, lat_array, coarse_resolution, fine_resolution, ecef=False):
     arrays = [lon_array, lat_array]
     rows, cols = _operator._check_2d_same_shape(arrays)
     rows_per_scan = rows_per_scan_for_resolution(coarse_resolution)
@@ -19,4 +19,5 @@ def interpolate_geolocation_cartesian(lon_array, lat_array, coarse_resolution, f
         raise ValueError("Input longitude/latitude data does not consist of "
                          "whole scans (10 rows per scan).")
     n_scans = rows // rows_per_scan
-    return _operator.run("simple", arrays, n_scans, (rows * res_factor, cols * res_factor), (cols, res_factor))
+    return _operator.run("simple", arrays, n_scans, (rows * res_factor, cols * res_factor), (cols, res_factor),
+                         ecef=ecef)

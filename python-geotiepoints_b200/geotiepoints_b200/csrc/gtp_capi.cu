@@ -199,13 +199,14 @@ size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
         if (_e != cudaSuccess) { status = cuda_fail(_e, where); goto done; } \
     } while (0)
 
-// Byte-level core: `in` are n_in host arrays of in_bytes[a] bytes per scan each; both outputs have
-// out_bytes bytes per scan.  launch(d_in, d_lon, d_lat, n_scans_of_chunk, stream) enqueues the kernel.
+// Byte-level core: `in` are n_in host arrays of in_bytes[a] bytes per scan each; the n_out outputs have
+// out_bytes bytes per scan each.  launch(d_in, d_out, n_scans_of_chunk, stream) enqueues the kernel.
 constexpr int kMaxInputs = 3;
+constexpr int kMaxOutputs = 3;
 
 template <typename Launch>
-int host_pipeline_bytes(const void* const* in, const size_t* in_bytes, int n_in, void* out_lon, void* out_lat,
-                        size_t out_bytes, int64_t n_scans, int device, Launch launch)
+int host_pipeline_n(const void* const* in, const size_t* in_bytes, int n_in, void* const* out, int n_out,
+                    size_t out_bytes, int64_t n_scans, int device, Launch launch)
 {
     if (n_scans == 0) return GTP_OK;
     DeviceGuard guard(device);
@@ -222,11 +223,11 @@ int host_pipeline_bytes(const void* const* in, const size_t* in_bytes, int n_in,
     const size_t out_chunk = align_up((size_t)chunk * out_bytes);
     HostPipe* pipe = acquire_pipe(current);
     void* d_in[kStreams][kMaxInputs] = {};
-    char* d_out[kStreams][2] = {};
+    void* d_out[kStreams][kMaxOutputs] = {};
     for (int s = 0; s < n_streams; ++s) {
-        GTP_CUDA_TRY(pipe->reserve(s, in_off[n_in] + 2 * out_chunk), "scratch alloc");
+        GTP_CUDA_TRY(pipe->reserve(s, in_off[n_in] + n_out * out_chunk), "scratch alloc");
         for (int a = 0; a < n_in; ++a) d_in[s][a] = pipe->scratch[s] + in_off[a];
-        for (int a = 0; a < 2; ++a) d_out[s][a] = pipe->scratch[s] + in_off[n_in] + a * out_chunk;
+        for (int a = 0; a < n_out; ++a) d_out[s][a] = pipe->scratch[s] + in_off[n_in] + a * out_chunk;
     }
     for (int64_t k = 0; k < n_chunks; ++k) {
         const int s = (int)(k % n_streams);
@@ -235,12 +236,11 @@ int host_pipeline_bytes(const void* const* in, const size_t* in_bytes, int n_in,
         for (int a = 0; a < n_in; ++a)
             GTP_CUDA_TRY(cudaMemcpyAsync(d_in[s][a], (const char*)in[a] + (size_t)s0 * in_bytes[a], (size_t)ns * in_bytes[a],
                                          cudaMemcpyHostToDevice, st), "H2D");
-        status = launch(d_in[s], (void*)d_out[s][0], (void*)d_out[s][1], ns, st);
+        status = launch(d_in[s], d_out[s], ns, st);
         if (status != GTP_OK) goto done;
-        GTP_CUDA_TRY(cudaMemcpyAsync((char*)out_lon + (size_t)s0 * out_bytes, d_out[s][0], (size_t)ns * out_bytes,
-                                     cudaMemcpyDeviceToHost, st), "D2H");
-        GTP_CUDA_TRY(cudaMemcpyAsync((char*)out_lat + (size_t)s0 * out_bytes, d_out[s][1], (size_t)ns * out_bytes,
-                                     cudaMemcpyDeviceToHost, st), "D2H");
+        for (int a = 0; a < n_out; ++a)
+            GTP_CUDA_TRY(cudaMemcpyAsync((char*)out[a] + (size_t)s0 * out_bytes, d_out[s][a], (size_t)ns * out_bytes,
+                                         cudaMemcpyDeviceToHost, st), "D2H");
     }
 done:
     bool healthy = true;
@@ -254,6 +254,16 @@ done:
     }
     release_pipe(pipe, healthy && status == GTP_OK);
     return status;
+}
+
+// the two-output (lon, lat) form
+template <typename Launch>
+int host_pipeline_bytes(const void* const* in, const size_t* in_bytes, int n_in, void* out_lon, void* out_lat,
+                        size_t out_bytes, int64_t n_scans, int device, Launch launch)
+{
+    void* const out[2] = {out_lon, out_lat};
+    return host_pipeline_n(in, in_bytes, n_in, out, 2, out_bytes, n_scans, device,
+        [&](void* const* d_in, void* const* d_out, int64_t ns, cudaStream_t st) { return launch(d_in, d_out[0], d_out[1], ns, st); });
 }
 
 template <typename T, int N_IN, typename Launch>
@@ -370,6 +380,145 @@ int simple_host(const T* lon, const T* lat, int64_t n_scans, int64_t width, int 
     return host_pipeline<T, 2>(in, out_lon, out_lat, n_scans, 10 * width, 10 * res * width * res, device,
         [&](T* const* d_in, T* d_lon, T* d_lat, int64_t ns, cudaStream_t st) {
             return simple_device<T>(d_in[0], d_in[1], ns, width, res, d_lon, d_lat, -1, (void*)st, true);
+        });
+}
+
+// ---- ECEF output: x / y / z of _compute_fine_xyz instead of their back-transform ----
+const char* const kMisaligned = "ECEF operator: inputs must be aligned to their element size (int16: 4 bytes) and outputs to 4 (250 m) | 2 (500 m) elements%s";
+
+template <typename T>
+int cviirs_xyz_device(const T* lon, const T* lat, const T* satz, int64_t n_scans, int coarse_res, int fine_res,
+                      int coarse_width, T* out_x, T* out_y, T* out_z, int device, void* stream, bool allow_fast)
+{
+    CviirsCfg cfg;
+    int rc = gtp_make_cfg(coarse_res, fine_res, coarse_width, &cfg);
+    if (rc) return cfg_error(rc);
+    if (n_scans < 0) return fail(GTP_E_SHAPE, "n_scans must be >= 0%s");
+    if (n_scans == 0) return GTP_OK;
+    if (!lon || !lat || !satz || !out_x || !out_y || !out_z) return fail(GTP_E_NULL, "null buffer%s");
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) { cudaGetLastError(); return fail(GTP_E_NO_DEVICE, "no usable CUDA device: %s", cudaGetErrorString(guard.err)); }
+    cudaError_t e = cudaErrorMisalignedAddress;
+    if constexpr (sizeof(T) == 8) {
+        if (allow_fast && gtp_cviirs_fast_f64_supported(cfg))
+            e = gtp_launch_xyz_fast(lon, lat, satz, 1, 0, 1.0, 0.0, out_x, out_y, out_z, 1, n_scans, cfg.p, (cudaStream_t)stream);
+    }
+    if (e == cudaErrorMisalignedAddress)       // not taken, or the vector stores do not fit: rounding-faithful kernel
+        e = gtp_launch_cviirs_generic_xyz<T>(lon, lat, satz, out_x, out_y, out_z, n_scans, cfg, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cviirs xyz launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return GTP_OK;
+}
+
+template <typename T>
+int simple_xyz_device(const T* lon, const T* lat, int64_t n_scans, int64_t width, int res, T* out_x, T* out_y, T* out_z,
+                      int device, void* stream, bool allow_fast)
+{
+    if (res != 2 && res != 4) return fail(GTP_E_RESOLUTION, "simple interpolator: res_factor must be 2 or 4%s");
+    if (n_scans < 0) return fail(GTP_E_SHAPE, "n_scans must be >= 0%s");
+    if (width < 4 || width > (1 << 24)) return fail(GTP_E_SHAPE, "simple interpolator: width must be in [4, 2^24]%s");
+    if (n_scans == 0) return GTP_OK;
+    if (!lon || !lat || !out_x || !out_y || !out_z) return fail(GTP_E_NULL, "null buffer%s");
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) { cudaGetLastError(); return fail(GTP_E_NO_DEVICE, "no usable CUDA device: %s", cudaGetErrorString(guard.err)); }
+    cudaError_t e = cudaErrorMisalignedAddress;
+    if constexpr (sizeof(T) == 8) {
+        if (allow_fast && gtp_simple_fast_f64_supported((int)width, res))
+            e = gtp_launch_xyz_fast(lon, lat, nullptr, 1, 0, 1.0, 0.0, out_x, out_y, out_z, 1, n_scans, res, (cudaStream_t)stream);
+    }
+    if (e == cudaErrorMisalignedAddress)
+        e = gtp_launch_simple_generic_xyz<T>(lon, lat, out_x, out_y, out_z, n_scans, (int)width, res, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "simple xyz launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return GTP_OK;
+}
+
+template <typename T>
+int cviirs_xyz_host(const T* lon, const T* lat, const T* satz, int64_t n_scans, int coarse_res, int fine_res,
+                    int coarse_width, T* out_x, T* out_y, T* out_z, int device)
+{
+    CviirsCfg cfg;
+    int rc = gtp_make_cfg(coarse_res, fine_res, coarse_width, &cfg);
+    if (rc) return cfg_error(rc);
+    if (n_scans < 0) return fail(GTP_E_SHAPE, "n_scans must be >= 0%s");
+    if (n_scans == 0) return GTP_OK;
+    if (!lon || !lat || !satz || !out_x || !out_y || !out_z) return fail(GTP_E_NULL, "null buffer%s");
+    const void* in[3] = {lon, lat, satz};
+    const size_t tie = (size_t)cfg.L * cfg.W * sizeof(T);
+    const size_t in_bytes[3] = {tie, tie, tie};
+    void* const out[3] = {out_x, out_y, out_z};
+    return host_pipeline_n(in, in_bytes, 3, out, 3, (size_t)cfg.n * cfg.Wf * sizeof(T), n_scans, device,
+        [&](void* const* d_in, void* const* d_out, int64_t ns, cudaStream_t st) {
+            return cviirs_xyz_device<T>((const T*)d_in[0], (const T*)d_in[1], (const T*)d_in[2], ns, coarse_res, fine_res,
+                                        coarse_width, (T*)d_out[0], (T*)d_out[1], (T*)d_out[2], -1, (void*)st, true);
+        });
+}
+
+template <typename T>
+int simple_xyz_host(const T* lon, const T* lat, int64_t n_scans, int64_t width, int res, T* out_x, T* out_y, T* out_z, int device)
+{
+    if (res != 2 && res != 4) return fail(GTP_E_RESOLUTION, "simple interpolator: res_factor must be 2 or 4%s");
+    if (n_scans < 0) return fail(GTP_E_SHAPE, "n_scans must be >= 0%s");
+    if (width < 4 || width > (1 << 24)) return fail(GTP_E_SHAPE, "simple interpolator: width must be in [4, 2^24]%s");
+    if (n_scans == 0) return GTP_OK;
+    if (!lon || !lat || !out_x || !out_y || !out_z) return fail(GTP_E_NULL, "null buffer%s");
+    const void* in[2] = {lon, lat};
+    const size_t tie = (size_t)10 * width * sizeof(T);
+    const size_t in_bytes[2] = {tie, tie};
+    void* const out[3] = {out_x, out_y, out_z};
+    return host_pipeline_n(in, in_bytes, 2, out, 3, tie * res * res, n_scans, device,
+        [&](void* const* d_in, void* const* d_out, int64_t ns, cudaStream_t st) {
+            return simple_xyz_device<T>((const T*)d_in[0], (const T*)d_in[1], ns, width, res,
+                                        (T*)d_out[0], (T*)d_out[1], (T*)d_out[2], -1, (void*)st, true);
+        });
+}
+
+// on-disk types in (float32 lon / lat, float32 | int16 zenith; satz == NULL: simple interpolator), float64
+// math, float32 | float64 ECEF out; 1 km tie points only
+int xyz_mixed_check(const void* lon, const void* lat, const void* satz, bool simple, int zen_kind, int64_t n_scans,
+                    int coarse_res, int fine_res, const void* out_x, const void* out_y, const void* out_z, int out_kind)
+{
+    if (coarse_res != 1000 || (fine_res != 250 && fine_res != 500))
+        return fail(GTP_E_RESOLUTION, "mixed ECEF operator: 1000 -> 250 | 500 only%s");
+    if (!simple && zen_kind != GTP_ZEN_F32 && zen_kind != GTP_ZEN_I16) return fail(GTP_E_RESOLUTION, "mixed operator: unknown zenith type%s");
+    if (out_kind != GTP_OUT_F32 && out_kind != GTP_OUT_F64) return fail(GTP_E_RESOLUTION, "mixed operator: unknown output type%s");
+    if (n_scans < 0) return fail(GTP_E_SHAPE, "n_scans must be >= 0%s");
+    if (n_scans > 0 && (!lon || !lat || (!simple && !satz) || !out_x || !out_y || !out_z)) return fail(GTP_E_NULL, "null buffer%s");
+    return GTP_OK;
+}
+
+int xyz_mixed_device(const float* lon, const float* lat, const void* satz, bool simple, int zen_kind, double zen_scale,
+                     double zen_offset, int64_t n_scans, int coarse_res, int fine_res, void* out_x, void* out_y, void* out_z,
+                     int out_kind, int device, void* stream)
+{
+    int rc = xyz_mixed_check(lon, lat, satz, simple, zen_kind, n_scans, coarse_res, fine_res, out_x, out_y, out_z, out_kind);
+    if (rc != GTP_OK || n_scans == 0) return rc;
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) { cudaGetLastError(); return fail(GTP_E_NO_DEVICE, "no usable CUDA device: %s", cudaGetErrorString(guard.err)); }
+    cudaError_t e = gtp_launch_xyz_fast(lon, lat, simple ? nullptr : satz, 0, zen_kind == GTP_ZEN_I16, zen_scale, zen_offset,
+                                        out_x, out_y, out_z, out_kind == GTP_OUT_F64, n_scans, 1000 / fine_res, (cudaStream_t)stream);
+    if (e == cudaErrorMisalignedAddress) { cudaGetLastError(); return fail(GTP_E_SHAPE, kMisaligned); }
+    if (e != cudaSuccess) return cuda_fail(e, "mixed xyz launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return GTP_OK;
+}
+
+int xyz_mixed_host(const float* lon, const float* lat, const void* satz, bool simple, int zen_kind, double zen_scale,
+                   double zen_offset, int64_t n_scans, int coarse_res, int fine_res, void* out_x, void* out_y, void* out_z,
+                   int out_kind, int device)
+{
+    int rc = xyz_mixed_check(lon, lat, satz, simple, zen_kind, n_scans, coarse_res, fine_res, out_x, out_y, out_z, out_kind);
+    if (rc != GTP_OK || n_scans == 0) return rc;
+    const void* in[3] = {lon, lat, satz};
+    const size_t tie = 10 * 1354;
+    const size_t in_bytes[3] = {tie * 4, tie * 4, tie * (zen_kind == GTP_ZEN_I16 ? 2 : 4)};
+    const int p = 1000 / fine_res;
+    void* const out[3] = {out_x, out_y, out_z};
+    return host_pipeline_n(in, in_bytes, simple ? 2 : 3, out, 3, tie * p * p * (out_kind == GTP_OUT_F64 ? 8 : 4), n_scans, device,
+        [&](void* const* d_in, void* const* d_out, int64_t ns, cudaStream_t st) {
+            return xyz_mixed_device((const float*)d_in[0], (const float*)d_in[1], simple ? nullptr : d_in[2], simple, zen_kind,
+                                    zen_scale, zen_offset, ns, coarse_res, fine_res, d_out[0], d_out[1], d_out[2], out_kind,
+                                    -1, (void*)st);
         });
 }
 
@@ -493,6 +642,84 @@ int gtp_cviirs_interp_mixed_host(const float* lon, const float* lat, const void*
             return mixed_device((const float*)d_in[0], (const float*)d_in[1], d_in[2], zen_kind, zen_scale, zen_offset,
                                 ns, coarse_res, fine_res, coarse_width, d_lon, d_lat, out_kind, -1, (void*)st);
         });
+}
+
+// ---- ECEF output ----
+int gtp_cviirs_interp_xyz_f32(const float* lon, const float* lat, const float* satz, int64_t n_scans,
+                              int coarse_res, int fine_res, int coarse_width,
+                              float* out_x, float* out_y, float* out_z, int device, void* stream)
+{ return cviirs_xyz_device<float>(lon, lat, satz, n_scans, coarse_res, fine_res, coarse_width, out_x, out_y, out_z, device, stream, true); }
+
+int gtp_cviirs_interp_xyz_f64(const double* lon, const double* lat, const double* satz, int64_t n_scans,
+                              int coarse_res, int fine_res, int coarse_width,
+                              double* out_x, double* out_y, double* out_z, int device, void* stream)
+{ return cviirs_xyz_device<double>(lon, lat, satz, n_scans, coarse_res, fine_res, coarse_width, out_x, out_y, out_z, device, stream, true); }
+
+int gtp_cviirs_interp_xyz_generic_f64(const double* lon, const double* lat, const double* satz, int64_t n_scans,
+                                      int coarse_res, int fine_res, int coarse_width,
+                                      double* out_x, double* out_y, double* out_z, int device, void* stream)
+{ return cviirs_xyz_device<double>(lon, lat, satz, n_scans, coarse_res, fine_res, coarse_width, out_x, out_y, out_z, device, stream, false); }
+
+int gtp_simple_interp_xyz_f32(const float* lon, const float* lat, int64_t n_scans, int64_t width, int res_factor,
+                              float* out_x, float* out_y, float* out_z, int device, void* stream)
+{ return simple_xyz_device<float>(lon, lat, n_scans, width, res_factor, out_x, out_y, out_z, device, stream, true); }
+
+int gtp_simple_interp_xyz_f64(const double* lon, const double* lat, int64_t n_scans, int64_t width, int res_factor,
+                              double* out_x, double* out_y, double* out_z, int device, void* stream)
+{ return simple_xyz_device<double>(lon, lat, n_scans, width, res_factor, out_x, out_y, out_z, device, stream, true); }
+
+int gtp_simple_interp_xyz_generic_f64(const double* lon, const double* lat, int64_t n_scans, int64_t width, int res_factor,
+                                      double* out_x, double* out_y, double* out_z, int device, void* stream)
+{ return simple_xyz_device<double>(lon, lat, n_scans, width, res_factor, out_x, out_y, out_z, device, stream, false); }
+
+int gtp_cviirs_interp_xyz_host_f32(const float* lon, const float* lat, const float* satz, int64_t n_scans,
+                                   int coarse_res, int fine_res, int coarse_width,
+                                   float* out_x, float* out_y, float* out_z, int device)
+{ return cviirs_xyz_host<float>(lon, lat, satz, n_scans, coarse_res, fine_res, coarse_width, out_x, out_y, out_z, device); }
+
+int gtp_cviirs_interp_xyz_host_f64(const double* lon, const double* lat, const double* satz, int64_t n_scans,
+                                   int coarse_res, int fine_res, int coarse_width,
+                                   double* out_x, double* out_y, double* out_z, int device)
+{ return cviirs_xyz_host<double>(lon, lat, satz, n_scans, coarse_res, fine_res, coarse_width, out_x, out_y, out_z, device); }
+
+int gtp_simple_interp_xyz_host_f32(const float* lon, const float* lat, int64_t n_scans, int64_t width, int res_factor,
+                                   float* out_x, float* out_y, float* out_z, int device)
+{ return simple_xyz_host<float>(lon, lat, n_scans, width, res_factor, out_x, out_y, out_z, device); }
+
+int gtp_simple_interp_xyz_host_f64(const double* lon, const double* lat, int64_t n_scans, int64_t width, int res_factor,
+                                   double* out_x, double* out_y, double* out_z, int device)
+{ return simple_xyz_host<double>(lon, lat, n_scans, width, res_factor, out_x, out_y, out_z, device); }
+
+int gtp_cviirs_interp_xyz_mixed(const float* lon, const float* lat, const void* satz, int zen_kind,
+                                double zen_scale, double zen_offset, int64_t n_scans, int coarse_res, int fine_res,
+                                void* out_x, void* out_y, void* out_z, int out_kind, int device, void* stream)
+{
+    return xyz_mixed_device(lon, lat, satz, false, zen_kind, zen_scale, zen_offset, n_scans, coarse_res, fine_res,
+                            out_x, out_y, out_z, out_kind, device, stream);
+}
+
+int gtp_cviirs_interp_xyz_mixed_host(const float* lon, const float* lat, const void* satz, int zen_kind,
+                                     double zen_scale, double zen_offset, int64_t n_scans, int coarse_res, int fine_res,
+                                     void* out_x, void* out_y, void* out_z, int out_kind, int device)
+{
+    return xyz_mixed_host(lon, lat, satz, false, zen_kind, zen_scale, zen_offset, n_scans, coarse_res, fine_res,
+                          out_x, out_y, out_z, out_kind, device);
+}
+
+int gtp_simple_interp_xyz_mixed(const float* lon, const float* lat, int64_t n_scans, int res_factor,
+                                void* out_x, void* out_y, void* out_z, int out_kind, int device, void* stream)
+{
+    if (res_factor != 2 && res_factor != 4) return fail(GTP_E_RESOLUTION, "simple interpolator: res_factor must be 2 or 4%s");
+    return xyz_mixed_device(lon, lat, nullptr, true, 0, 1.0, 0.0, n_scans, 1000, 1000 / res_factor,
+                            out_x, out_y, out_z, out_kind, device, stream);
+}
+
+int gtp_simple_interp_xyz_mixed_host(const float* lon, const float* lat, int64_t n_scans, int res_factor,
+                                     void* out_x, void* out_y, void* out_z, int out_kind, int device)
+{
+    if (res_factor != 2 && res_factor != 4) return fail(GTP_E_RESOLUTION, "simple interpolator: res_factor must be 2 or 4%s");
+    return xyz_mixed_host(lon, lat, nullptr, true, 0, 1.0, 0.0, n_scans, 1000, 1000 / res_factor,
+                          out_x, out_y, out_z, out_kind, device);
 }
 
 int gtp_trim(void)

@@ -791,4 +791,30 @@ GTP_FD double fine_row_y(int j)
          : (((j + kHalf) % P) + 0.5);
 }
 
+// ---- ECEF output (gtp_fast_xyz.cu): the bilinear form itself, v(a, t) = A + a P + t Q + a t S ----
+struct QuadXyz { Vec3 A, P, Q, S; };      // P = B - A, Q = D - A, S = (C - D) - P  (:360-363, :396-398)
+
+GTP_FD QuadXyz quadxyz_setup(const Vec3& A, const Vec3& B, const Vec3& C, const Vec3& D)
+{
+    QuadXyz q;
+    q.A = A;
+    q.P.x = B.x - A.x; q.P.y = B.y - A.y; q.P.z = B.z - A.z;
+    q.Q.x = D.x - A.x; q.Q.y = D.y - A.y; q.Q.z = D.z - A.z;
+    q.S.x = (C.x - D.x) - q.P.x; q.S.y = (C.y - D.y) - q.P.y; q.S.z = (C.z - D.z) - q.P.z;
+    return q;
+}
+
+// one fine row: v = V + a_col U with a_scan = a_col + a_row, a_row = s_t (1 - s_t) c_ali  (:344)
+struct RowXyz { Vec3 U, V; };
+
+GTP_FD RowXyz rowxyz_setup(const QuadXyz& q, double s_t, double a_row)
+{
+    RowXyz r;
+    r.U.x = fma(s_t, q.S.x, q.P.x); r.U.y = fma(s_t, q.S.y, q.P.y); r.U.z = fma(s_t, q.S.z, q.P.z);
+    r.V.x = fma(a_row, r.U.x, fma(s_t, q.Q.x, q.A.x));
+    r.V.y = fma(a_row, r.U.y, fma(s_t, q.Q.y, q.A.y));
+    r.V.z = fma(a_row, r.U.z, fma(s_t, q.Q.z, q.A.z));
+    return r;
+}
+
 }  // namespace gtpfast

@@ -89,10 +89,12 @@ __device__ __forceinline__ void quad_exp_ali(T satz_a, T satz_b, int km, T& c_ex
 // ---------------------------------------------------------------------------------
 // CVIIRS (satellite-zenith driven) interpolator, any configuration.
 // ---------------------------------------------------------------------------------
-template <typename T>
+// XYZ = true stores the fine Cartesian coordinates (_compute_fine_xyz, :346-398) in out_lon / out_lat /
+// out_z = x / y / z instead of their back-transform.
+template <typename T, bool XYZ>
 __global__ void __launch_bounds__(kThreads)
 cviirs_generic_kernel(const T* __restrict__ lon, const T* __restrict__ lat, const T* __restrict__ satz,
-                      T* __restrict__ out_lon, T* __restrict__ out_lat,
+                      T* __restrict__ out_lon, T* __restrict__ out_lat, T* __restrict__ out_z,
                       long long n_scans, int n_strips, CviirsCfg cfg)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -157,10 +159,16 @@ cviirs_generic_kernel(const T* __restrict__ lon, const T* __restrict__ lat, cons
             T scan2 = (T)(((1.0 - (double)a_scan) * (double)D) + (double)(T)(a_scan * C));
             fine[k] = (T)(((1.0 - (double)a_track) * (double)scan1) + (double)(T)(a_track * scan2));
         }
-        T lo, la;
-        xyz_to_lonlat(fine[0], fine[1], fine[2], lo, la);
-        olon[(long long)j * cfg.Wf + i] = lo;
-        olat[(long long)j * cfg.Wf + i] = la;
+        if (XYZ) {
+            olon[(long long)j * cfg.Wf + i] = fine[0];
+            olat[(long long)j * cfg.Wf + i] = fine[1];
+            out_z[(scan * cfg.n + j) * cfg.Wf + i] = fine[2];
+        } else {
+            T lo, la;
+            xyz_to_lonlat(fine[0], fine[1], fine[2], lo, la);
+            olon[(long long)j * cfg.Wf + i] = lo;
+            olat[(long long)j * cfg.Wf + i] = la;
+        }
     }
 }
 
@@ -238,10 +246,10 @@ __device__ __forceinline__ T simple_value(const SimpleTile<T>& t, int k, int j, 
     return m * yj + b;
 }
 
-template <typename T>
+template <typename T, bool XYZ>
 __global__ void __launch_bounds__(kThreads)
 simple_generic_kernel(const T* __restrict__ lon, const T* __restrict__ lat,
-                      T* __restrict__ out_lon, T* __restrict__ out_lat,
+                      T* __restrict__ out_lon, T* __restrict__ out_lat, T* __restrict__ out_z,
                       long long n_scans, int n_strips, int W, int res)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -286,10 +294,16 @@ simple_generic_kernel(const T* __restrict__ lon, const T* __restrict__ lat,
         T fx = simple_value(tile, 0, j, i);
         T fy = simple_value(tile, 1, j, i);
         T fz = simple_value(tile, 2, j, i);
-        T lo, la;
-        xyz_to_lonlat(fx, fy, fz, lo, la);
-        olon[(long long)j * Wf + i] = lo;
-        olat[(long long)j * Wf + i] = la;
+        if (XYZ) {
+            olon[(long long)j * Wf + i] = fx;
+            olat[(long long)j * Wf + i] = fy;
+            out_z[(scan * n + j) * Wf + i] = fz;
+        } else {
+            T lo, la;
+            xyz_to_lonlat(fx, fy, fz, lo, la);
+            olon[(long long)j * Wf + i] = lo;
+            olat[(long long)j * Wf + i] = la;
+        }
     }
 }
 
@@ -298,38 +312,78 @@ simple_generic_kernel(const T* __restrict__ lon, const T* __restrict__ lat,
 // ---------------------------------------------------------------------------------
 // launchers (declared in gtp_kernels.h)
 // ---------------------------------------------------------------------------------
-template <typename T>
-cudaError_t gtp_launch_cviirs_generic(const T* lon, const T* lat, const T* satz, T* out_lon, T* out_lat,
-                                      long long n_scans, const CviirsCfg& cfg, cudaStream_t stream)
+namespace {
+
+template <typename T, bool XYZ>
+cudaError_t launch_cviirs(const T* lon, const T* lat, const T* satz, T* out_a, T* out_b, T* out_c,
+                          long long n_scans, const CviirsCfg& cfg, cudaStream_t stream)
 {
     if (n_scans <= 0) return cudaSuccess;
     const int n_strips = (cfg.W - 1 + kStripQuads - 1) / kStripQuads;
     const size_t smem = sizeof(T) * (3 * cfg.L * (kStripQuads + 1) + 2 * (cfg.L - 1) * kStripQuads);
     const long long blocks = n_scans * n_strips;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    cviirs_generic_kernel<T><<<(unsigned)blocks, kThreads, smem, stream>>>(
-        lon, lat, satz, out_lon, out_lat, n_scans, n_strips, cfg);
+    cviirs_generic_kernel<T, XYZ><<<(unsigned)blocks, kThreads, smem, stream>>>(
+        lon, lat, satz, out_a, out_b, out_c, n_scans, n_strips, cfg);
     return cudaGetLastError();
 }
 
-template <typename T>
-cudaError_t gtp_launch_simple_generic(const T* lon, const T* lat, T* out_lon, T* out_lat,
-                                      long long n_scans, int width, int res, cudaStream_t stream)
+template <typename T, bool XYZ>
+cudaError_t launch_simple(const T* lon, const T* lat, T* out_a, T* out_b, T* out_c,
+                          long long n_scans, int width, int res, cudaStream_t stream)
 {
     if (n_scans <= 0) return cudaSuccess;
     const int n_strips = (width + kStripQuads - 1) / kStripQuads;
     const size_t smem = sizeof(T) * 3 * 10 * (kStripQuads + 4);
     const long long blocks = n_scans * n_strips;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    simple_generic_kernel<T><<<(unsigned)blocks, kThreads, smem, stream>>>(
-        lon, lat, out_lon, out_lat, n_scans, n_strips, width, res);
+    simple_generic_kernel<T, XYZ><<<(unsigned)blocks, kThreads, smem, stream>>>(
+        lon, lat, out_a, out_b, out_c, n_scans, n_strips, width, res);
     return cudaGetLastError();
+}
+
+}  // namespace
+
+template <typename T>
+cudaError_t gtp_launch_cviirs_generic(const T* lon, const T* lat, const T* satz, T* out_lon, T* out_lat,
+                                      long long n_scans, const CviirsCfg& cfg, cudaStream_t stream)
+{
+    return launch_cviirs<T, false>(lon, lat, satz, out_lon, out_lat, (T*)nullptr, n_scans, cfg, stream);
+}
+
+template <typename T>
+cudaError_t gtp_launch_cviirs_generic_xyz(const T* lon, const T* lat, const T* satz, T* out_x, T* out_y, T* out_z,
+                                          long long n_scans, const CviirsCfg& cfg, cudaStream_t stream)
+{
+    return launch_cviirs<T, true>(lon, lat, satz, out_x, out_y, out_z, n_scans, cfg, stream);
+}
+
+template <typename T>
+cudaError_t gtp_launch_simple_generic(const T* lon, const T* lat, T* out_lon, T* out_lat,
+                                      long long n_scans, int width, int res, cudaStream_t stream)
+{
+    return launch_simple<T, false>(lon, lat, out_lon, out_lat, (T*)nullptr, n_scans, width, res, stream);
+}
+
+template <typename T>
+cudaError_t gtp_launch_simple_generic_xyz(const T* lon, const T* lat, T* out_x, T* out_y, T* out_z,
+                                          long long n_scans, int width, int res, cudaStream_t stream)
+{
+    return launch_simple<T, true>(lon, lat, out_x, out_y, out_z, n_scans, width, res, stream);
 }
 
 template cudaError_t gtp_launch_cviirs_generic<float>(const float*, const float*, const float*, float*, float*,
                                                       long long, const CviirsCfg&, cudaStream_t);
 template cudaError_t gtp_launch_cviirs_generic<double>(const double*, const double*, const double*, double*, double*,
                                                        long long, const CviirsCfg&, cudaStream_t);
+template cudaError_t gtp_launch_cviirs_generic_xyz<float>(const float*, const float*, const float*, float*, float*, float*,
+                                                          long long, const CviirsCfg&, cudaStream_t);
+template cudaError_t gtp_launch_cviirs_generic_xyz<double>(const double*, const double*, const double*, double*, double*, double*,
+                                                           long long, const CviirsCfg&, cudaStream_t);
+template cudaError_t gtp_launch_simple_generic_xyz<float>(const float*, const float*, float*, float*, float*,
+                                                          long long, int, int, cudaStream_t);
+template cudaError_t gtp_launch_simple_generic_xyz<double>(const double*, const double*, double*, double*, double*,
+                                                           long long, int, int, cudaStream_t);
 template cudaError_t gtp_launch_simple_generic<float>(const float*, const float*, float*, float*,
                                                       long long, int, int, cudaStream_t);
 template cudaError_t gtp_launch_simple_generic<double>(const double*, const double*, double*, double*,

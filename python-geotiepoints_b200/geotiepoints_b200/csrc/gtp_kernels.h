@@ -11,6 +11,19 @@ template <typename T>
 cudaError_t gtp_launch_simple_generic(const T* lon, const T* lat, T* out_lon, T* out_lat,
                                       long long n_scans, int width, int res, cudaStream_t stream);
 
+// ECEF output: x / y / z of _compute_fine_xyz instead of their back-transform
+template <typename T>
+cudaError_t gtp_launch_cviirs_generic_xyz(const T* lon, const T* lat, const T* satz, T* out_x, T* out_y, T* out_z,
+                                          long long n_scans, const CviirsCfg& cfg, cudaStream_t stream);
+template <typename T>
+cudaError_t gtp_launch_simple_generic_xyz(const T* lon, const T* lat, T* out_x, T* out_y, T* out_z,
+                                          long long n_scans, int width, int res, cudaStream_t stream);
+// gtp_fast_xyz.cu: float64 math at 1 km (width 1354), p = 4 | 2; satz == nullptr: simple interpolator;
+// returns cudaErrorMisalignedAddress when the vector stores / staged loads cannot be used
+cudaError_t gtp_launch_xyz_fast(const void* lon, const void* lat, const void* satz, int in_is_f64, int zen_kind,
+                                double zen_scale, double zen_offset, void* out_x, void* out_y, void* out_z,
+                                int out_is_f64, long long n_scans, int p, cudaStream_t stream);
+
 // gtp_fast.cu: float64 anchor-relative fast paths
 cudaError_t gtp_launch_cviirs_fast_f64(const double* lon, const double* lat, const double* satz,
                                        double* out_lon, double* out_lat,

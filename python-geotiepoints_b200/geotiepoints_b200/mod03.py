@@ -15,6 +15,9 @@ output traffic of the float64 path, three times the pixel rate of the float32-fa
 
 Inputs are numpy arrays or torch CUDA tensors (zero copy), C-contiguous, whole scans of 10 rows and
 1354 columns; ``sensor_zenith`` is float32 (degrees, or scaled) or int16.
+
+``ecef=True`` (1 km tie points) returns the Cartesian ``(x, y, z)`` in metres that the algorithm
+interpolates - see :mod:`geotiepoints_b200.ecef` - instead of their back-transform to lon / lat.
 """
 import ctypes
 
@@ -27,14 +30,14 @@ _ZEN_KIND = {"float32": 0, "int16": 1}
 _OUT_KIND = {"float32": 0, "float64": 1}
 
 
-def modis_1km_to_250m(lon1, lat1, sensor_zenith, *, zenith_scale=1.0, zenith_offset=0.0, out_dtype=np.float32):
+def modis_1km_to_250m(lon1, lat1, sensor_zenith, *, zenith_scale=1.0, zenith_offset=0.0, out_dtype=np.float32, ecef=False):
     """1 km -> 250 m from float32 lon / lat and float32 | int16 zenith angles, float64 math."""
-    return _interpolate(lon1, lat1, sensor_zenith, 250, zenith_scale, zenith_offset, out_dtype)
+    return _interpolate(lon1, lat1, sensor_zenith, 250, zenith_scale, zenith_offset, out_dtype, ecef=ecef)
 
 
-def modis_1km_to_500m(lon1, lat1, sensor_zenith, *, zenith_scale=1.0, zenith_offset=0.0, out_dtype=np.float32):
+def modis_1km_to_500m(lon1, lat1, sensor_zenith, *, zenith_scale=1.0, zenith_offset=0.0, out_dtype=np.float32, ecef=False):
     """1 km -> 500 m from float32 lon / lat and float32 | int16 zenith angles, float64 math."""
-    return _interpolate(lon1, lat1, sensor_zenith, 500, zenith_scale, zenith_offset, out_dtype)
+    return _interpolate(lon1, lat1, sensor_zenith, 500, zenith_scale, zenith_offset, out_dtype, ecef=ecef)
 
 
 def modis_5km_to_1km(lon1, lat1, sensor_zenith, *, zenith_scale=1.0, zenith_offset=0.0, out_dtype=np.float32):
@@ -42,21 +45,22 @@ def modis_5km_to_1km(lon1, lat1, sensor_zenith, *, zenith_scale=1.0, zenith_offs
     return _interpolate(lon1, lat1, sensor_zenith, 1000, zenith_scale, zenith_offset, out_dtype, coarse_resolution=5000)
 
 
-def simple_modis_1km_to_250m(lon1, lat1, *, out_dtype=np.float32):
+def simple_modis_1km_to_250m(lon1, lat1, *, out_dtype=np.float32, ecef=False):
     """``simple_modis_interpolator.modis_1km_to_250m`` on float32 lon / lat with float64 math."""
-    return _interpolate_simple(lon1, lat1, 4, out_dtype)
+    return _interpolate_simple(lon1, lat1, 4, out_dtype, ecef)
 
 
-def simple_modis_1km_to_500m(lon1, lat1, *, out_dtype=np.float32):
+def simple_modis_1km_to_500m(lon1, lat1, *, out_dtype=np.float32, ecef=False):
     """``simple_modis_interpolator.modis_1km_to_500m`` on float32 lon / lat with float64 math."""
-    return _interpolate_simple(lon1, lat1, 2, out_dtype)
+    return _interpolate_simple(lon1, lat1, 2, out_dtype, ecef)
 
 
 def _dtype_name(a):
     return str(a.dtype).replace("torch.", "")
 
 
-def _interpolate(lon1, lat1, zen, fine_resolution, zenith_scale, zenith_offset, out_dtype, coarse_resolution=1000):
+def _interpolate(lon1, lat1, zen, fine_resolution, zenith_scale, zenith_offset, out_dtype, coarse_resolution=1000,
+                 ecef=False):
     arrays = [lon1, lat1, zen]
     for a in arrays:
         if a.ndim != 2:
@@ -85,7 +89,11 @@ def _interpolate(lon1, lat1, zen, fine_resolution, zenith_scale, zenith_offset, 
             raise NotImplementedError("Can't interpolate if 5km tiepoints have less than 270 columns.")
         out_shape = (rows * 5, 1354)
     scalars = (_ZEN_KIND[_dtype_name(zen)], float(zenith_scale), float(zenith_offset), rows // rows_per_scan,
-               coarse_resolution, fine_resolution, cols if coarse_resolution == 5000 else 0)
+               coarse_resolution, fine_resolution)
+    if not ecef:                # the ECEF operator is 1 km only and has no coarse_width argument
+        scalars += (cols if coarse_resolution == 5000 else 0,)
+    n_out = 3 if ecef else 2
+    name = "gtp_cviirs_interp_xyz_mixed" if ecef else "gtp_cviirs_interp_mixed"
     lib = _capi.lib()
     if all(_is_torch_tensor(a) for a in arrays):
         import torch
@@ -93,21 +101,21 @@ def _interpolate(lon1, lat1, zen, fine_resolution, zenith_scale, zenith_offset, 
             raise TypeError("torch inputs must be CUDA tensors (numpy arrays take the host path)")
         arrays = [a.contiguous() for a in arrays]
         tdtype = torch.float32 if out_name == "float32" else torch.float64
-        out = [torch.empty(out_shape, dtype=tdtype, device=lon1.device) for _ in range(2)]
+        out = [torch.empty(out_shape, dtype=tdtype, device=lon1.device) for _ in range(n_out)]
         stream = torch.cuda.current_stream(lon1.device).cuda_stream
-        rc = lib.gtp_cviirs_interp_mixed(*[a.data_ptr() for a in arrays], *scalars, out[0].data_ptr(), out[1].data_ptr(),
-                                         _OUT_KIND[out_name], lon1.device.index, ctypes.c_void_p(stream))
+        rc = getattr(lib, name)(*[a.data_ptr() for a in arrays], *scalars, *[o.data_ptr() for o in out],
+                                _OUT_KIND[out_name], lon1.device.index, ctypes.c_void_p(stream))
         _capi.check(rc)
-        return out[0], out[1]
+        return tuple(out)
     arrays = [np.ascontiguousarray(a) for a in arrays]
-    out = [_capi.pinned_pool.empty(out_shape, np.dtype(out_dtype)) for _ in range(2)]
-    rc = lib.gtp_cviirs_interp_mixed_host(*[a.ctypes.data for a in arrays], *scalars, out[0].ctypes.data,
-                                          out[1].ctypes.data, _OUT_KIND[out_name], -1)
+    out = [_capi.pinned_pool.empty(out_shape, np.dtype(out_dtype)) for _ in range(n_out)]
+    rc = getattr(lib, name + "_host")(*[a.ctypes.data for a in arrays], *scalars, *[o.ctypes.data for o in out],
+                                      _OUT_KIND[out_name], -1)
     _capi.check(rc)
-    return out[0], out[1]
+    return tuple(out)
 
 
-def _interpolate_simple(lon1, lat1, res, out_dtype):
+def _interpolate_simple(lon1, lat1, res, out_dtype, ecef=False):
     arrays = [lon1, lat1]
     for a in arrays:
         if a.ndim != 2:
@@ -125,6 +133,8 @@ def _interpolate_simple(lon1, lat1, res, out_dtype):
     if cols != 1354:
         raise ValueError(f"Expected 1354 tie-point columns, got {cols}.")
     out_shape = (rows * res, cols * res)
+    n_out = 3 if ecef else 2
+    name = "gtp_simple_interp_xyz_mixed" if ecef else "gtp_simple_interp_mixed"
     lib = _capi.lib()
     if all(_is_torch_tensor(a) for a in arrays):
         import torch
@@ -132,15 +142,15 @@ def _interpolate_simple(lon1, lat1, res, out_dtype):
             raise TypeError("torch inputs must be CUDA tensors (numpy arrays take the host path)")
         arrays = [a.contiguous() for a in arrays]
         tdtype = torch.float32 if out_name == "float32" else torch.float64
-        out = [torch.empty(out_shape, dtype=tdtype, device=lon1.device) for _ in range(2)]
+        out = [torch.empty(out_shape, dtype=tdtype, device=lon1.device) for _ in range(n_out)]
         stream = torch.cuda.current_stream(lon1.device).cuda_stream
-        rc = lib.gtp_simple_interp_mixed(*[a.data_ptr() for a in arrays], rows // 10, res, out[0].data_ptr(),
-                                         out[1].data_ptr(), _OUT_KIND[out_name], lon1.device.index, ctypes.c_void_p(stream))
+        rc = getattr(lib, name)(*[a.data_ptr() for a in arrays], rows // 10, res, *[o.data_ptr() for o in out],
+                                _OUT_KIND[out_name], lon1.device.index, ctypes.c_void_p(stream))
         _capi.check(rc)
-        return out[0], out[1]
+        return tuple(out)
     arrays = [np.ascontiguousarray(a) for a in arrays]
-    out = [_capi.pinned_pool.empty(out_shape, np.dtype(out_dtype)) for _ in range(2)]
-    rc = lib.gtp_simple_interp_mixed_host(*[a.ctypes.data for a in arrays], rows // 10, res, out[0].ctypes.data,
-                                          out[1].ctypes.data, _OUT_KIND[out_name], -1)
+    out = [_capi.pinned_pool.empty(out_shape, np.dtype(out_dtype)) for _ in range(n_out)]
+    rc = getattr(lib, name + "_host")(*[a.ctypes.data for a in arrays], rows // 10, res, *[o.ctypes.data for o in out],
+                                      _OUT_KIND[out_name], -1)
     _capi.check(rc)
-    return out[0], out[1]
+    return tuple(out)

@@ -95,6 +95,66 @@ extern "C" int gtp_emul_cviirs_fast_f64(const double* lon, const double* lat, co
 }
 
 
+// ---- ECEF output (csrc/gtp_fast_xyz.cu): the same tie-point walk, then the bilinear form itself ----
+template <int P>
+static void run_xyz(const double* lon, const double* lat, const double* satz, long n_scans,
+                    double* out_x, double* out_y, double* out_z)
+{
+    const int W = 1354, L = 10, Wf = W * P, N = L * P, H = P / 2;
+    const bool simple = (satz == nullptr);
+    std::vector<TieGeo> geo((size_t)L * W);
+    std::vector<TieZen> zen((size_t)L * W);
+    for (long s = 0; s < n_scans; ++s) {
+        for (int c = 0; c < W; ++c) {
+            TieGeo g = {0.0, 1.0, 0.0, 1.0, 0.0, 0.0};
+            TieZen z = {0.0, 0.0, 1.0, 0.0, 1.0};
+            for (int r = 0; r < L; ++r) {
+                const long o = (s * L + r) * W + c;
+                if (simple) tie_advance<false>(g, z, lon[o], lat[o], 0.0, r == 0);
+                else tie_advance<true>(g, z, lon[o], lat[o], satz[o], r == 0);
+                geo[(size_t)r * W + c] = g; zen[(size_t)r * W + c] = z;
+            }
+        }
+        for (int qc = 0; qc <= W - 1; ++qc) {
+            const bool extra = (qc == W - 1);
+            const int ca = extra ? W - 2 : qc, cb = ca + 1, xoff = extra ? P : 0;
+            for (int qr = 0; qr < L - 1; ++qr) {
+                double ce = 0.0, cal = 0.0;
+                if (!simple) {
+                    const TieZen za = zen[(size_t)qr * W + ca], zb = zen[(size_t)qr * W + cb];
+                    quad_coefficients(za, zb.za, zb.sphi, zb.cphi, 1, ce, cal);
+                }
+                const QuadXyz q = quadxyz_setup(tie_xyz(geo[(size_t)qr * W + ca]), tie_xyz(geo[(size_t)qr * W + cb]),
+                                                tie_xyz(geo[(size_t)(qr + 1) * W + cb]), tie_xyz(geo[(size_t)(qr + 1) * W + ca]));
+                const int j0 = (qr == 0) ? 0 : qr * P + H;
+                const int j1 = (qr == L - 2) ? N : (qr + 1) * P + H;
+                for (int j = j0; j < j1; ++j) {
+                    const double s_t = fine_row_y<P>(j) / (double)P;
+                    const RowXyz rw = rowxyz_setup(q, s_t, simple ? 0.0 : (s_t * (1.0 - s_t)) * cal);
+                    for (int k = 0; k < P; ++k) {
+                        const double s_s = (double)(xoff + k) / (double)P;
+                        const double a_col = simple ? s_s : fma(s_s * (1.0 - s_s), ce, s_s);
+                        const long o = (s * N + j) * (long)Wf + (long)ca * P + xoff + k;
+                        out_x[o] = fma(a_col, rw.U.x, rw.V.x);
+                        out_y[o] = fma(a_col, rw.U.y, rw.V.y);
+                        out_z[o] = fma(a_col, rw.U.z, rw.V.z);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// satz == NULL: the simple interpolator
+extern "C" int gtp_emul_xyz_fast_f64(const double* lon, const double* lat, const double* satz, long n_scans,
+                                     int fine_res, double* out_x, double* out_y, double* out_z)
+{
+    if (fine_res == 250) run_xyz<4>(lon, lat, satz, n_scans, out_x, out_y, out_z);
+    else if (fine_res == 500) run_xyz<2>(lon, lat, satz, n_scans, out_x, out_y, out_z);
+    else return 1;
+    return 0;
+}
+
 // ---- float64 5 km -> 1 km fast path (csrc/gtp_fast5.cu) ------------------------------------------
 extern "C" int gtp_emul_cviirs_fast5_f64(const double* lon, const double* lat, const double* satz, long n_scans,
                                          int W, double* out_lon, double* out_lat, long* mode_counts)

@@ -98,3 +98,40 @@ def haversine_m(lon1, lat1, lon2, lat2, radius=6371008.8):
     lon1, lat1, lon2, lat2 = (np.deg2rad(np.asarray(a, dtype=np.float64)) for a in (lon1, lat1, lon2, lat2))
     a = np.sin((lat2 - lat1) / 2) ** 2 + np.cos(lat1) * np.cos(lat2) * np.sin((lon2 - lon1) / 2) ** 2
     return 2 * radius * np.arcsin(np.sqrt(np.clip(a, 0.0, 1.0)))
+
+
+# ---- ECEF output (metres) ----
+#: float64: 1e-10 deg of arc on the reference's sphere is 1.1e-5 m; the CUDA path is held to 1e-6 m,
+#: i.e. 1e-11 deg.  Measured: <= 5e-8 m, which is the reference's own conditioning - its c_expansion
+#: divides two differences of nearly equal angles (:62-64), so a_scan carries ~1e-11 of relative noise,
+#: times a quad width of up to 5 km.  float32: one float32 ulp of R is 0.5 m; the
+#: rounding-faithful kernels reproduce the reference's rounding points, so at most 1 ulp (a double
+#: rounding of a libm result that differs in its last bit).
+TOL_XYZ_F64_M = 1e-6
+
+
+def compare_xyz(got, exp):
+    """Statistics of an (x, y, z) triple against the oracle's, metres."""
+    n_nan_diff, max_abs, max_ulps, exact, n = 0, 0.0, 0.0, 0, 0
+    for g, e in zip(got, exp):
+        assert g.shape == e.shape and g.dtype == e.dtype
+        n_nan_diff += int((np.isnan(g) != np.isnan(e)).sum())
+        ok = ~(np.isnan(g) | np.isnan(e))
+        d = np.abs(g[ok].astype(np.float64) - e[ok].astype(np.float64))
+        max_abs = max(max_abs, float(d.max(initial=0.0)))
+        ulp = np.spacing(np.maximum(np.abs(e[ok]), np.asarray(1.0, e.dtype))).astype(np.float64)
+        max_ulps = max(max_ulps, float((d / ulp).max(initial=0.0)))
+        exact += int((g[ok] == e[ok]).sum())
+        n += int(ok.sum())
+    return {"n": n, "nan_mismatches": n_nan_diff, "max_abs_m": max_abs, "max_ulps": max_ulps,
+            "bit_exact_fraction": exact / n if n else 1.0}
+
+
+def assert_xyz_parity(got, exp, what=""):
+    s = compare_xyz(got, exp)
+    assert s["nan_mismatches"] == 0, (what, s)
+    if got[0].dtype == np.float64:
+        assert s["max_abs_m"] <= TOL_XYZ_F64_M, (what, s)
+    else:
+        assert s["max_ulps"] <= 1.0, (what, s)
+    return s

@@ -75,6 +75,16 @@ def emul():
         assert rc == 0
         return out_lon, out_lat, dict(zip(("slow", "low", "high", "both", "small", "wide"), modes))
     run.f32 = run_f32
+
+    def run_xyz(lon, lat, satz, fine):
+        ns, p = lon.shape[0] // 10, 1000 // fine
+        out = [np.full((ns * 10 * p, 1354 * p), np.nan) for _ in range(3)]
+        rc = lib.gtp_emul_xyz_fast_f64(lon.ctypes.data_as(dp), lat.ctypes.data_as(dp),
+                                       satz.ctypes.data_as(dp) if satz is not None else None,
+                                       ctypes.c_long(ns), fine, *[o.ctypes.data_as(dp) for o in out])
+        assert rc == 0
+        return tuple(out)
+    run.xyz = run_xyz
     return run
 
 
@@ -196,3 +206,44 @@ def test_f32_fast_math_stress_inputs(emul, golden_inputs, name):
         with np.errstate(all="ignore"):
             exp = gtp_oracle.cviirs(lon, lat, satz, 1000, fine)
         assert_parity(got_lon, got_lat, *exp, what=f"host emulation f32 {name} -> {fine} m, modes {modes}")
+
+
+# ---- ECEF output (csrc/gtp_fast_xyz.cu) ----
+def test_oracle_xyz_is_what_the_oracle_back_transforms():
+    """The oracle's xyz output and its pinned lon / lat come from the same values: back-transforming the
+    former with numpy's acos / asin (_modis_utils.pyx:43-65) reproduces the latter to libm rounding."""
+    lon, lat, satz = testing.modis_granule(3, n_scans=2)
+    x, y, z = gtp_oracle.cviirs_xyz(lon, lat, satz, 1000, 250)
+    exp_lon, exp_lat = gtp_oracle.cviirs(lon, lat, satz, 1000, 250)
+    rho = np.sqrt(x * x + y * y)
+    got_lon = np.rad2deg(np.arccos(x / rho)) * np.sign(y)
+    low = np.abs(z) < 0.8 * 6370997.0
+    got_lat = np.where(low, 90.0 - np.rad2deg(np.arccos(z / 6370997.0)),
+                       np.sign(z) * (90.0 - np.rad2deg(np.arcsin(np.minimum(rho / 6370997.0, 1.0)))))
+    assert_parity(got_lon, got_lat, exp_lon, exp_lat, what="oracle xyz -> lon/lat")
+    sx, sy, sz = gtp_oracle.simple_xyz(lon, lat, 1000, 250)
+    assert np.abs(np.sqrt(sx * sx + sy * sy + sz * sz) - 6370997.0).max() < 5.0       # chords / extrapolation of <= 5 km quads
+
+
+@pytest.mark.parametrize("fine", [250, 500])
+@pytest.mark.parametrize("granule", [0, 3, 5, 287])
+def test_xyz_fast_math_matches_oracle(emul, granule, fine):
+    from parity import assert_xyz_parity
+    lon, lat, satz = testing.modis_granule(granule, n_scans=3)
+    assert_xyz_parity(emul.xyz(lon, lat, satz, fine), gtp_oracle.cviirs_xyz(lon, lat, satz, 1000, fine, n_threads=4),
+                      what=f"host emulation xyz granule {granule} -> {fine} m")
+    assert_xyz_parity(emul.xyz(lon, lat, None, fine), gtp_oracle.simple_xyz(lon, lat, 1000, fine, n_threads=4),
+                      what=f"host emulation simple xyz granule {granule} -> {fine} m")
+
+
+@pytest.mark.parametrize("name", ["antimeridian", "pole", "south_pole", "prime_meridian", "lat_switch",
+                                  "symmetric_satz", "zeros", "nan_holes"])
+def test_xyz_fast_math_stress_inputs(emul, golden_inputs, name):
+    from parity import assert_xyz_parity
+    lon, lat, satz = (a.astype(np.float64) for a in golden_inputs[name])
+    for fine in (250, 500):
+        with np.errstate(all="ignore"):
+            exp = gtp_oracle.cviirs_xyz(lon, lat, satz, 1000, fine)
+            exp_simple = gtp_oracle.simple_xyz(lon, lat, 1000, fine)
+        assert_xyz_parity(emul.xyz(lon, lat, satz, fine), exp, what=f"host emulation xyz {name} -> {fine} m")
+        assert_xyz_parity(emul.xyz(lon, lat, None, fine), exp_simple, what=f"host emulation simple xyz {name} -> {fine} m")
