@@ -105,6 +105,38 @@ def test_mod03_argument_checks():
         mod03.modis_1km_to_250m(lon, lon[:10], zen)
 
 
+def test_ecef_argument_checks_and_abi_validation():
+    """The ECEF extension: host checks mirror the lon / lat operators; the C ABI validates its arguments
+    before it looks for a device (no compute happens here)."""
+    from geotiepoints_b200 import ecef, mod03
+    a = np.zeros((15, 1354), np.float64)
+    with pytest.raises(ValueError, match="whole scans"):
+        ecef.modis_1km_to_250m(a, a, a)
+    with pytest.raises(ValueError, match="whole scans"):
+        ecef.simple_modis_1km_to_500m(a, a)
+    with pytest.raises(NotImplementedError):
+        ecef.interpolate(a[:2, :100], a[:2, :100], a[:2, :100], 5000, 1000, 100)
+    with pytest.raises(TypeError):
+        ecef.modis_1km_to_250m(a[:10].astype(np.int16), a[:10].astype(np.int16), a[:10].astype(np.int16))
+    with pytest.raises(TypeError):
+        mod03.modis_1km_to_250m(a[:10], a[:10], a[:10].astype(np.float32), ecef=True)
+    lib = _capi.lib()
+    buf = np.zeros(16, np.float64).ctypes.data
+    assert lib.gtp_cviirs_interp_xyz_f64(buf, buf, buf, 1, 2000, 250, 0, buf, buf, buf, -1, None) == 1
+    assert lib.gtp_cviirs_interp_xyz_f32(buf, buf, buf, 1, 5000, 1000, 100, buf, buf, buf, -1, None) == _capi.GTP_E_WIDTH_5KM
+    assert lib.gtp_cviirs_interp_xyz_f64(buf, buf, buf, -1, 1000, 250, 0, buf, buf, buf, -1, None) == 4
+    assert lib.gtp_cviirs_interp_xyz_f64(buf, buf, buf, 1, 1000, 250, 0, buf, buf, None, -1, None) == 3
+    assert lib.gtp_cviirs_interp_xyz_f64(None, None, None, 0, 1000, 250, 0, None, None, None, -1, None) == 0
+    assert lib.gtp_cviirs_interp_xyz_host_f64(buf, buf, buf, 1, 1000, 250, 0, buf, None, buf, -1) == 3
+    assert lib.gtp_simple_interp_xyz_f64(buf, buf, 1, 1354, 3, buf, buf, buf, -1, None) == 1
+    assert lib.gtp_simple_interp_xyz_host_f32(buf, buf, 1, 2, 4, buf, buf, buf, -1) == 4
+    assert lib.gtp_cviirs_interp_xyz_mixed(buf, buf, buf, 0, 1.0, 0.0, 1, 5000, 1000, buf, buf, buf, 0, -1, None) == 1
+    assert lib.gtp_cviirs_interp_xyz_mixed(buf, buf, buf, 7, 1.0, 0.0, 1, 1000, 250, buf, buf, buf, 0, -1, None) == 1
+    assert lib.gtp_cviirs_interp_xyz_mixed_host(buf, buf, None, 0, 1.0, 0.0, 1, 1000, 250, buf, buf, buf, 0, -1) == 3
+    assert lib.gtp_simple_interp_xyz_mixed(buf, buf, 1, 3, buf, buf, buf, 0, -1, None) == 1
+    assert lib.gtp_simple_interp_xyz_mixed_host(buf, buf, 0, 4, buf, buf, buf, 1, -1) == 0
+
+
 def test_partial_scan_and_wrong_width_are_refused():
     a = np.zeros((15, 1354), np.float32)
     with pytest.raises(ValueError, match="whole scans"):
