@@ -101,13 +101,17 @@ def haversine_m(lon1, lat1, lon2, lat2, radius=6371008.8):
 
 
 # ---- ECEF output (metres) ----
-#: float64: 1e-10 deg of arc on the reference's sphere is 1.1e-5 m; the CUDA path is held to 1e-6 m,
-#: i.e. 1e-11 deg.  Measured: <= 5e-8 m, which is the reference's own conditioning - its c_expansion
-#: divides two differences of nearly equal angles (:62-64), so a_scan carries ~1e-11 of relative noise,
-#: times a quad width of up to 5 km.  float32: one float32 ulp of R is 0.5 m; the
-#: rounding-faithful kernels reproduce the reference's rounding points, so at most 1 ulp (a double
-#: rounding of a libm result that differs in its last bit).
-TOL_XYZ_F64_M = 1e-6
+#: float64: the north_star tolerance of 1e-10 deg is 1.1e-5 m of arc on the reference's sphere; the CUDA
+#: path is held to 1e-5 m.  Measured over the whole synthetic day (profiles/r01_full_day_parity.txt):
+#: <= 1.5e-6 m for CVIIRS, <= 1.2e-8 m for the simple interpolator.  The CVIIRS figure is the reference's
+#: own conditioning: its c_expansion divides two differences of nearly equal angles (:62-64), so next
+#: to nadir a_scan carries up to ~1e-9 of noise, times a quad width of 1-5 km.  The worst pixel of the
+#: day (granule 72, nadir quad, zenith angles 1.1e-7 deg apart) moves by 5e-7 m in the ORACLE when the
+#: zenith angles are perturbed by one ulp; typical quads agree to 4e-8 m, and the rounding-faithful
+#: kernel (CUDA libm vs glibc) is as far from the oracle as the fast one.
+#: float32: one float32 ulp of R is 0.5 m; the rounding-faithful kernels reproduce the reference's
+#: rounding points, so at most 1 ulp (a double rounding of a libm result that differs in its last bit).
+TOL_XYZ_F64_M = 1e-5
 
 
 def compare_xyz(got, exp):

@@ -2,7 +2,7 @@
 Cartesian coordinates - the values the reference hands to ``xyz2lonlat``
 (``_modis_interpolator.pyx:293``, ``_simple_modis_interpolator.pyx:63``).
 
-Tolerances (tests/parity.py): float64 <= 1e-6 m (1e-11 deg of arc), float32 <= 1 float32 ulp, NaN
+Tolerances (tests/parity.py): float64 <= 1e-5 m (1e-10 deg of arc), float32 <= 1 float32 ulp, NaN
 patterns identical.
 """
 import ctypes
@@ -151,7 +151,7 @@ def test_ecef_full_granule_sampled_scans():
         a = [np.ascontiguousarray(v[s * 10:(s + 1) * 10]) for v in (lon, lat, satz)]
         stats = assert_xyz_parity([g[s * 40:(s + 1) * 40] for g in got], _oracle_xyz(a, 1000, 250, 0), what=f"scan {s}")
         worst = max(worst, stats["max_abs_m"])
-    assert worst < 1e-6
+    assert worst < 1e-5
 
 
 @pytest.mark.parametrize("config", ["f64_250m", "f64_500m", "mixed_f32_250m", "simple_f64_250m"])

@@ -3,6 +3,7 @@
 pixels at 250 m) through the CUDA path and through the oracle, per configuration.
 
     python tools/full_day_parity.py            # needs a GPU; prints one line per configuration
+    python tools/full_day_parity.py ecef       # only the ECEF-output configurations
 
 The oracle (oracle/, test infrastructure) is the checker here, exactly as in tests/."""
 import os
@@ -14,8 +15,10 @@ for p in ("python-geotiepoints_b200", "oracle", "tests"):
     sys.path.insert(0, os.path.join(ROOT, p))
 import numpy as np
 import gtp_oracle
-from geotiepoints_b200 import mod03, modisinterpolator, simple_modis_interpolator, testing
-from parity import compare
+from geotiepoints_b200 import ecef, mod03, modisinterpolator, simple_modis_interpolator, testing
+from parity import compare, compare_xyz
+
+only_ecef = len(sys.argv) > 1 and sys.argv[1] == "ecef"
 
 scans = (0, 101, 202)
 parts = []
@@ -35,7 +38,28 @@ def report(name, got, exp):
     print(f"{name:34s} " + " ".join(f"{k}={s[k]:.3g}" if isinstance(s[k], float) else f"{k}={s[k]}" for k in keys if k in s), flush=True)
 
 
+def report_xyz(name, got, exp):
+    s = compare_xyz(got, exp)
+    print(f"{name:34s} " + " ".join(f"{k}={v:.3g}" if isinstance(v, float) else f"{k}={v}" for k, v in s.items()), flush=True)
+
+
 with np.errstate(all="ignore"):
+    # ECEF output (metres): float64 fast kernel, float32 rounding-faithful kernel, MOD03 types
+    for fine, fn, sfn in ((250, ecef.modis_1km_to_250m, ecef.simple_modis_1km_to_250m),
+                          (500, ecef.modis_1km_to_500m, ecef.simple_modis_1km_to_500m)):
+        for dt in (np.float64, np.float32):
+            a = [x.astype(dt) for x in (lon, lat, satz)]
+            report_xyz(f"ecef cviirs 1km->{fine}m {np.dtype(dt).name}", fn(*a), gtp_oracle.cviirs_xyz(*a, 1000, fine, 0, n_threads=16))
+        a = [lon, lat]
+        report_xyz(f"ecef simple 1km->{fine}m float64", sfn(*a), gtp_oracle.simple_xyz(*a, 1000, fine, n_threads=16))
+    f = [x.astype(np.float32) for x in (lon, lat)]
+    zen = np.round(satz / 0.01).astype(np.int16)
+    exp = gtp_oracle.cviirs_xyz(f[0].astype(np.float64), f[1].astype(np.float64), zen.astype(np.float64) * 0.01, 1000, 250, 0, n_threads=16)
+    report_xyz("ecef mod03 f32+i16 -> f64", mod03.modis_1km_to_250m(*f, zen, zenith_scale=0.01, out_dtype=np.float64, ecef=True), exp)
+    report_xyz("ecef mod03 f32+i16 -> f32", mod03.modis_1km_to_250m(*f, zen, zenith_scale=0.01, ecef=True),
+               tuple(x.astype(np.float32) for x in exp))
+    if only_ecef:
+        sys.exit(0)
     for fine, fn in ((250, modisinterpolator.modis_1km_to_250m), (500, modisinterpolator.modis_1km_to_500m)):
         for dt in (np.float64, np.float32):
             a = [x.astype(dt) for x in (lon, lat, satz)]
