@@ -103,7 +103,10 @@ int simple_device(const T* lon, const T* lat, int64_t n_scans, int64_t width, in
         else
             e = gtp_launch_simple_generic<T>(lon, lat, out_lon, out_lat, n_scans, (int)width, res, (cudaStream_t)stream);
     } else {
-        e = gtp_launch_simple_generic<T>(lon, lat, out_lon, out_lat, n_scans, (int)width, res, (cudaStream_t)stream);
+        if (allow_fast && gtp_simple_fast_f32_supported((int)width, res))
+            e = gtp_launch_simple_fast_f32(lon, lat, out_lon, out_lat, n_scans, res, (cudaStream_t)stream);
+        else
+            e = gtp_launch_simple_generic<T>(lon, lat, out_lon, out_lat, n_scans, (int)width, res, (cudaStream_t)stream);
     }
     if (e != cudaSuccess) return cuda_fail(e, "simple launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);

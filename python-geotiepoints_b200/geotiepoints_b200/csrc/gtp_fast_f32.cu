@@ -1,4 +1,4 @@
-// gtp_fast_f32.cu - float32 CVIIRS 1 km -> 250 m / 500 m fast path for sm_100a.
+// gtp_fast_f32.cu - float32 1 km -> 250 m / 500 m fast paths (CVIIRS and simple interpolator) for sm_100a.
 //
 // Same work decomposition as gtp_fast.cu (one thread per tie-point quad column, ten tie rows
 // top to bottom, right neighbour by warp shuffle, cp.async prefetch of the next tie row, one
@@ -187,6 +187,116 @@ cudaError_t launch(const float* lon, const float* lat, const float* satz, float*
     return cudaGetLastError();
 }
 
+// ---- simple_modis_interpolator, float32: same decomposition, no zenith angles ----
+template <int P, int MODE, bool WRAP>
+__device__ __forceinline__ void quad_rows_simple(const QuadF32& q, bool right, int qr, int nrows, float* olon, float* olat)
+{
+    constexpr long long kPitch = (long long)kW * P;
+#pragma unroll 1
+    for (int m = 0; m < nrows; ++m) {
+        float vlon[P], vlat[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+            double v[3];
+            simple_pixel_f32<P>(q, right, qr, m, k, v);
+            if (MODE == kSlow) {
+                const LonLatF ll = backtransform_f32_slow((float)v[0], (float)v[1], (float)v[2]);
+                vlon[k] = ll.lon; vlat[k] = ll.lat;
+            } else {
+                backtransform_f32<MODE, WRAP>(q, v, vlon[k], vlat[k]);
+            }
+        }
+        store_px<P>(olon, vlon);
+        store_px<P>(olat, vlat);
+        olon += kPitch; olat += kPitch;
+    }
+}
+
+template <int P>
+__global__ void __launch_bounds__(kThreads, 4)
+simple_fast_1km_f32_kernel(const float* __restrict__ lon, const float* __restrict__ lat,
+                           float* __restrict__ out_lon, float* __restrict__ out_lat, long long n_scans)
+{
+    constexpr int kWf = kW * P;
+    constexpr int kN = kL * P;
+    constexpr int kHalf = P / 2;
+
+    const long long warp_global = (blockIdx.x * (long long)kThreads + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long scan = warp_global / kWarpsPerScan;
+    if (scan >= n_scans) return;
+    const int w = (int)(warp_global - scan * kWarpsPerScan);
+    const int c = w * kQuadColsPerWarp + lane;
+    const int tc = min(c, kW - 1);
+    const bool extra = (c == kW - 1);      // the lane of tie column 1353: pixels right of the last tie column
+    const bool quad_lane = (lane < kQuadColsPerWarp) && (c <= kW - 2);
+    const bool active = quad_lane || extra;
+    const int quad_col = extra ? kW - 2 : c;
+    const int xoff = extra ? P : 0;
+
+    const long long scan_base = scan * (long long)(kL * kW);
+    const float* plon = lon + scan_base + tc;
+    const float* plat = lat + scan_base + tc;
+    float* olon = out_lon + scan * (long long)kN * kWf + (long long)quad_col * P + xoff;
+    float* olat = out_lat + scan * (long long)kN * kWf + (long long)quad_col * P + xoff;
+
+    TieGeoF topA;
+    Vec3F topB;
+    __shared__ float stage[2][2][kThreads];
+    cp_async4(&stage[0][0][threadIdx.x], plon);
+    cp_async4(&stage[0][1][threadIdx.x], plat);
+    cp_async_commit();
+
+#pragma unroll 1
+    for (int r = 0; r < kL; ++r) {
+        cp_async_wait_all();
+        const float clon = stage[r & 1][0][threadIdx.x], clat = stage[r & 1][1][threadIdx.x];
+        if (r + 1 < kL) {
+            plon += kW; plat += kW;
+            cp_async4(&stage[(r + 1) & 1][0][threadIdx.x], plon);
+            cp_async4(&stage[(r + 1) & 1][1][threadIdx.x], plat);
+            cp_async_commit();
+        }
+        const TieGeoF own = tie_geo_f32(clon, clat);
+        TieGeoF curA = own;
+        Vec3F curB;
+        curB.x = __shfl_down_sync(kFull, own.x, 1);
+        curB.y = __shfl_down_sync(kFull, own.y, 1);
+        curB.z = __shfl_down_sync(kFull, own.z, 1);
+        if (extra) {                 // A = tie column 1352 (recomputed by this one lane), B = own column 1353
+            const long long o = scan_base + (long long)r * kW + (kW - 2);
+            curA = tie_geo_f32(__ldg(lon + o), __ldg(lat + o));
+            curB.x = own.x; curB.y = own.y; curB.z = own.z;
+        }
+
+        if (r > 0 && active) {
+            const int qr = r - 1;
+            const int nrows = P + ((qr == 0 || qr == kL - 2) ? kHalf : 0);
+            Vec3F curAv; curAv.x = curA.x; curAv.y = curA.y; curAv.z = curA.z;
+            const QuadF32 q = quad_setup_f32(topA, topB, curB, curAv, 0.0f, 0.0f);
+            if (q.mode == kSlow) quad_rows_simple<P, kSlow, false>(q, extra, qr, nrows, olon, olat);
+            else if (q.wrap) quad_rows_simple<P, kBoth, true>(q, extra, qr, nrows, olon, olat);
+            else if (q.mode == kLow) quad_rows_simple<P, kLow, false>(q, extra, qr, nrows, olon, olat);
+            else if (q.mode == kHigh) quad_rows_simple<P, kHigh, false>(q, extra, qr, nrows, olon, olat);
+            else quad_rows_simple<P, kBoth, false>(q, extra, qr, nrows, olon, olat);
+            olon += (long long)nrows * kWf;
+            olat += (long long)nrows * kWf;
+        }
+        topA = curA;
+        topB = curB;
+    }
+}
+
+template <int P>
+cudaError_t launch_simple(const float* lon, const float* lat, float* out_lon, float* out_lat, long long n_scans, cudaStream_t stream)
+{
+    const long long warps = n_scans * kWarpsPerScan;
+    const long long blocks = (warps * 32 + kThreads - 1) / kThreads;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    simple_fast_1km_f32_kernel<P><<<(unsigned)blocks, kThreads, 0, stream>>>(lon, lat, out_lon, out_lat, n_scans);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 bool gtp_cviirs_fast_f32_supported(const CviirsCfg& cfg)
@@ -204,4 +314,20 @@ cudaError_t gtp_launch_cviirs_fast_f32(const float* lon, const float* lat, const
         return gtp_launch_cviirs_generic<float>(lon, lat, satz, out_lon, out_lat, n_scans, cfg, stream);
     return cfg.p == 4 ? launch<4>(lon, lat, satz, out_lon, out_lat, n_scans, stream)
                       : launch<2>(lon, lat, satz, out_lon, out_lat, n_scans, stream);
+}
+
+bool gtp_simple_fast_f32_supported(int width, int res)
+{
+    return width == kW && (res == 4 || res == 2);
+}
+
+cudaError_t gtp_launch_simple_fast_f32(const float* lon, const float* lat, float* out_lon, float* out_lat,
+                                       long long n_scans, int res, cudaStream_t stream)
+{
+    if (n_scans <= 0) return cudaSuccess;
+    const uintptr_t align = (res == 4) ? 16 : 8;
+    if (((uintptr_t)out_lon | (uintptr_t)out_lat) & (align - 1))
+        return gtp_launch_simple_generic<float>(lon, lat, out_lon, out_lat, n_scans, kW, res, stream);
+    return res == 4 ? launch_simple<4>(lon, lat, out_lon, out_lat, n_scans, stream)
+                    : launch_simple<2>(lon, lat, out_lon, out_lat, n_scans, stream);
 }

@@ -287,4 +287,92 @@ GTP_FD_COLD LonLatF backtransform_f32_slow(float xf, float yf, float zf)
     return r;
 }
 
+// ---- simple_modis_interpolator, float32 (_simple_modis_interpolator.pyx:13-277) --------------------
+// The reference samples the float32 tie-point xyz with scipy's order-1 map_coordinates (double
+// accumulation t = 0; t += (v wy) wx per tap, result cast to float32, :121-132), then extrapolates the
+// last nc = 3 | 1 fine columns (:139-150) and the first / last 2 | 1 fine rows of the scan (:157-277)
+// in float32 arithmetic.  Weights are multiples of 1/8, so every tap product is exact and the chain
+// of four FMAs below reproduces scipy's sum bit for bit.
+GTP_FD double simple_taps_f32(double A, float B, float C, double D, double w00, double w01, double w10, double w11)
+{
+    // taps in scipy's order: (y0, x0) = A, (y0, x1) = B, (y1, x0) = D, (y1, x1) = C
+    return fma((double)C, w11, fma(D, w10, fma((double)B, w01, A * w00)));
+}
+
+// the sample at column fraction tx (k / P inside the quad) and row fraction ty, a float32 value held in a double
+GTP_FD void simple_sample_f32(const QuadF32& q, double tx, double ty, double (&v)[3])
+{
+    const double wy1 = ty, wy0 = 1.0 - ty, wx1 = tx, wx0 = 1.0 - tx;
+    const double w00 = wy0 * wx0, w01 = wy0 * wx1, w10 = wy1 * wx0, w11 = wy1 * wx1;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v[k] = round_to_f32(simple_taps_f32(q.A[k], q.B[k], q.C[k], q.D[k], w00, w01, w10, w11));
+}
+
+// The pixels right of the last tie column (fine columns Wf - P .. Wf - 1, evaluated on the quad of tie
+// columns 1352 | 1353): column Wf - P sits on tie column 1353 (both taps clamp to it, 'nearest'), the
+// nc = P - 1 columns after it are that value + diff (o + 1), diff = v[Wf - nc - 1] - v[Wf - nc - 2] (:146-150)
+GTP_FD void simple_sample_right_f32(const QuadF32& q, int P, int k, double ty, double (&v)[3])
+{
+    const double wy1 = ty, wy0 = 1.0 - ty;
+    double prev[3];
+    if (k > 0) simple_sample_f32(q, (double)(P - 1) / (double)P, ty, prev);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const double e = round_to_f32(fma((double)q.C[c], wy1, (double)q.B[c] * wy0));
+        if (k == 0) { v[c] = e; continue; }
+        const float ef = (float)e;
+        const float diff = fsub_rn(ef, (float)prev[c]);
+        v[c] = (double)fadd_rn(ef, fmul_rn(diff, (float)k));
+    }
+}
+
+// first / last rows of a scan: the line through the samples of two interior rows, float32 arithmetic
+// (_compute_slope_offset / _extrapolate, :227-277): m = (v_hi - v_lo) / (y_hi - y_lo), b = v_hi - m y_hi
+GTP_FD float simple_line_f32(float v_lo, float v_hi, float y_lo, float y_hi, float y)
+{
+#ifdef __CUDA_ARCH__
+    const float m = __fdiv_rn(fsub_rn(v_hi, v_lo), fsub_rn(y_hi, y_lo));
+#else
+    volatile float m = fsub_rn(v_hi, v_lo) / fsub_rn(y_hi, y_lo);
+#endif
+    const float b = fsub_rn(v_hi, fmul_rn(m, y_hi));
+    return fadd_rn(fmul_rn(m, y), b);
+}
+
+// yc[j] of _compute_yx_coordinate_arrays (:71-81): j / res - (res / 16 + 1 / 8), exact in float32
+GTP_FD float simple_ycoord_f32(int res, int j)
+{
+    return (float)((double)j * (1.0 / (double)res) - ((double)res * (1.0 / 16.0) + 0.125));
+}
+
+// One fine pixel of the simple interpolator: quad row qr (0..8), row m of that quad row, pixel k of
+// the quad column; `right`: the lane that evaluates the pixels right of the last tie column.
+template <int P>
+GTP_FD void simple_pixel_f32(const QuadF32& q, bool right, int qr, int m, int k, double (&v)[3])
+{
+    constexpr int kHalf = P / 2;
+    const double ty0 = ((qr == 0) ? (0.5 - kHalf) : 0.5) / P;
+    const bool top = (qr == 0) && (m < kHalf), bottom = (qr == 8) && (m >= P);
+    if (!top && !bottom) {
+        const double ty = ty0 + (double)m / (double)P;
+        if (right) simple_sample_right_f32(q, P, k, ty, v);
+        else simple_sample_f32(q, (double)k / (double)P, ty, v);
+        return;
+    }
+    // the two interior rows the line goes through (:157-225): 250 m rows (2, 5) / (34, 37), 500 m rows (1, 2) / (17, 18)
+    const int m_lo = top ? kHalf : 0, m_hi = top ? kHalf + P - 1 : P - 1;
+    const int j0 = (qr == 0) ? 0 : 8 * P + kHalf;                       // scan row of m = 0
+    double lo[3], hi[3];
+    if (right) {
+        simple_sample_right_f32(q, P, k, ty0 + (double)m_lo / (double)P, lo);
+        simple_sample_right_f32(q, P, k, ty0 + (double)m_hi / (double)P, hi);
+    } else {
+        simple_sample_f32(q, (double)k / (double)P, ty0 + (double)m_lo / (double)P, lo);
+        simple_sample_f32(q, (double)k / (double)P, ty0 + (double)m_hi / (double)P, hi);
+    }
+    const float y_lo = simple_ycoord_f32(P, j0 + m_lo), y_hi = simple_ycoord_f32(P, j0 + m_hi), y = simple_ycoord_f32(P, j0 + m);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = (double)simple_line_f32((float)lo[c], (float)hi[c], y_lo, y_hi, y);
+}
+
 }  // namespace gtpfast32

@@ -54,3 +54,8 @@ cudaError_t gtp_launch_cviirs_fast_f32(const float* lon, const float* lat, const
                                        float* out_lon, float* out_lat,
                                        long long n_scans, const CviirsCfg& cfg, cudaStream_t stream);
 bool gtp_cviirs_fast_f32_supported(const CviirsCfg& cfg);
+// float32 simple interpolator at width 1354: scipy's tap sum and the float32 edge extrapolations
+// reproduced exactly, anchor-relative back-transform
+cudaError_t gtp_launch_simple_fast_f32(const float* lon, const float* lat, float* out_lon, float* out_lat,
+                                       long long n_scans, int res, cudaStream_t stream);
+bool gtp_simple_fast_f32_supported(int width, int res);

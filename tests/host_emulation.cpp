@@ -262,3 +262,57 @@ extern "C" int gtp_emul_cviirs_fast_f32(const float* lon, const float* lat, cons
     else return 1;
     return 0;
 }
+
+// ---- float32 simple interpolator (simple_pixel_f32 of gtp_fast_f32_math.cuh) ----------------------
+// xyz != NULL additionally returns the float32 fine Cartesian coordinates (for the bit-exactness check
+// against the oracle's new_xyz)
+template <int P>
+static void run_simple_f32(const float* lon, const float* lat, long n_scans, float* out_lon, float* out_lat,
+                           float* const* xyz, long* mode_counts)
+{
+    using namespace gtpfast32;
+    const int W = 1354, L = 10, Wf = W * P, N = L * P, H = P / 2;
+    for (long s = 0; s < n_scans; ++s) {
+        for (int qc = 0; qc <= W - 1; ++qc) {
+            const bool extra = (qc == W - 1);
+            const int ca = extra ? W - 2 : qc, cb = ca + 1, xoff = extra ? P : 0;
+            for (int qr = 0; qr < L - 1; ++qr) {
+                auto geo = [&](int r, int c) { long o = (s * L + r) * W + c; return tie_geo_f32(lon[o], lat[o]); };
+                auto v3 = [](const TieGeoF& t) { Vec3F v; v.x = t.x; v.y = t.y; v.z = t.z; return v; };
+                const TieGeoF A = geo(qr, ca);
+                const Vec3F B = v3(geo(qr, cb)), D = v3(geo(qr + 1, ca)), C = v3(geo(qr + 1, cb));
+                const QuadF32 q = quad_setup_f32(A, B, C, D, 0.0f, 0.0f);
+                mode_counts[q.mode]++;
+                const int nrows = P + ((qr == 0 || qr == L - 2) ? H : 0);
+                const int j0 = (qr == 0) ? 0 : qr * P + H;
+                for (int m = 0; m < nrows; ++m) {
+                    for (int k = 0; k < P; ++k) {
+                        double v[3];
+                        float lo, la;
+                        simple_pixel_f32<P>(q, extra, qr, m, k, v);
+                        if (q.mode == kSlow) { const LonLatF ll = backtransform_f32_slow((float)v[0], (float)v[1], (float)v[2]); lo = ll.lon; la = ll.lat; }
+                        else if (q.wrap) backtransform_f32<kBoth, true>(q, v, lo, la);
+                        else if (q.mode == kLow) backtransform_f32<kLow, false>(q, v, lo, la);
+                        else if (q.mode == kHigh) backtransform_f32<kHigh, false>(q, v, lo, la);
+                        else backtransform_f32<kBoth, false>(q, v, lo, la);
+                        const long o = (s * N + j0 + m) * (long)Wf + (long)ca * P + xoff + k;
+                        out_lon[o] = lo; out_lat[o] = la;
+                        if (xyz) for (int c = 0; c < 3; ++c) xyz[c][o] = (float)v[c];
+                    }
+                }
+            }
+        }
+    }
+}
+
+extern "C" int gtp_emul_simple_fast_f32(const float* lon, const float* lat, long n_scans, int fine_res,
+                                        float* out_lon, float* out_lat, float* out_x, float* out_y, float* out_z,
+                                        long* mode_counts)
+{
+    for (int k = 0; k < 5; ++k) mode_counts[k] = 0;
+    float* const xyz[3] = {out_x, out_y, out_z};
+    if (fine_res == 250) run_simple_f32<4>(lon, lat, n_scans, out_lon, out_lat, out_x ? xyz : nullptr, mode_counts);
+    else if (fine_res == 500) run_simple_f32<2>(lon, lat, n_scans, out_lon, out_lat, out_x ? xyz : nullptr, mode_counts);
+    else return 1;
+    return 0;
+}

@@ -76,6 +76,16 @@ def emul():
         return out_lon, out_lat, dict(zip(("slow", "low", "high", "both", "small", "wide"), modes))
     run.f32 = run_f32
 
+    def run_simple_f32(lon, lat, fine):
+        ns, p = lon.shape[0] // 10, 1000 // fine
+        out = [np.full((ns * 10 * p, 1354 * p), np.nan, np.float32) for _ in range(5)]
+        modes = (ctypes.c_long * 6)()
+        rc = lib.gtp_emul_simple_fast_f32(lon.ctypes.data_as(fp), lat.ctypes.data_as(fp), ctypes.c_long(ns), fine,
+                                          *[o.ctypes.data_as(fp) for o in out], modes)
+        assert rc == 0
+        return out[0], out[1], tuple(out[2:]), dict(zip(("slow", "low", "high", "both", "small", "wide"), modes))
+    run.simple_f32 = run_simple_f32
+
     def run_xyz(lon, lat, satz, fine):
         ns, p = lon.shape[0] // 10, 1000 // fine
         out = [np.full((ns * 10 * p, 1354 * p), np.nan) for _ in range(3)]
@@ -247,3 +257,32 @@ def test_xyz_fast_math_stress_inputs(emul, golden_inputs, name):
             exp_simple = gtp_oracle.simple_xyz(lon, lat, 1000, fine)
         assert_xyz_parity(emul.xyz(lon, lat, satz, fine), exp, what=f"host emulation xyz {name} -> {fine} m")
         assert_xyz_parity(emul.xyz(lon, lat, None, fine), exp_simple, what=f"host emulation simple xyz {name} -> {fine} m")
+
+
+# ---- float32 simple interpolator fast path (simple_fast_1km_f32_kernel) ----
+@pytest.mark.parametrize("fine", [250, 500])
+@pytest.mark.parametrize("granule", [0, 3, 5, 14, 287])
+def test_simple_f32_fast_math_matches_oracle(emul, granule, fine):
+    """scipy's tap sum and the float32 column / row extrapolations are reproduced exactly: the float32
+    fine xyz are bit-identical to the oracle's, lon / lat follow from the anchor-relative back-transform."""
+    lon, lat, _ = testing.modis_granule(granule, n_scans=3, dtype=np.float32)
+    got_lon, got_lat, xyz, modes = emul.simple_f32(lon, lat, fine)
+    exp_xyz = gtp_oracle.simple_xyz(lon, lat, 1000, fine, n_threads=4)
+    for g, e, name in zip(xyz, exp_xyz, "xyz"):
+        assert np.array_equal(g, e), f"simple f32 {name} differs in {(g != e).sum()} pixels, max {np.abs(g - e).max()}"
+    exp = gtp_oracle.simple(lon, lat, 1000, fine, n_threads=4)
+    s = assert_parity(got_lon, got_lat, *exp, what=f"host emulation simple f32 granule {granule} -> {fine} m, modes {modes}")
+    assert s["bit_exact_fraction"] > 0.999, s
+
+
+@pytest.mark.parametrize("name", ["real", "antimeridian", "pole", "south_pole", "prime_meridian", "lat_switch", "zeros", "nan_holes"])
+def test_simple_f32_fast_math_stress_inputs(emul, golden_inputs, name):
+    lon, lat, _ = golden_inputs[name]
+    for fine in (250, 500):
+        got_lon, got_lat, xyz, modes = emul.simple_f32(lon, lat, fine)
+        with np.errstate(all="ignore"):
+            exp = gtp_oracle.simple(lon, lat, 1000, fine)
+            exp_xyz = gtp_oracle.simple_xyz(lon, lat, 1000, fine)
+        for g, e in zip(xyz, exp_xyz):
+            assert np.array_equal(g, e, equal_nan=True), f"{name}: {(g != e).sum()} float32 xyz values differ"
+        assert_parity(got_lon, got_lat, *exp, what=f"host emulation simple f32 {name} -> {fine} m, modes {modes}")
