@@ -194,11 +194,12 @@ __device__ __forceinline__ void quad_rows_simple(const QuadF32& q, bool right, i
     constexpr long long kPitch = (long long)kW * P;
 #pragma unroll 1
     for (int m = 0; m < nrows; ++m) {
+        const SimpleRowsF32<P> rows = simple_rows_f32<P>(q, qr, m);
         float vlon[P], vlat[P];
 #pragma unroll
         for (int k = 0; k < P; ++k) {
             double v[3];
-            simple_pixel_f32<P>(q, right, qr, m, k, v);
+            simple_pixel_f32<P>(rows, right, k, v);
             if (MODE == kSlow) {
                 const LonLatF ll = backtransform_f32_slow((float)v[0], (float)v[1], (float)v[2]);
                 vlon[k] = ll.lon; vlat[k] = ll.lat;

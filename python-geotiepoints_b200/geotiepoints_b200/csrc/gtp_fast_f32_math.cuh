@@ -291,34 +291,43 @@ GTP_FD_COLD LonLatF backtransform_f32_slow(float xf, float yf, float zf)
 // The reference samples the float32 tie-point xyz with scipy's order-1 map_coordinates (double
 // accumulation t = 0; t += (v wy) wx per tap, result cast to float32, :121-132), then extrapolates the
 // last nc = 3 | 1 fine columns (:139-150) and the first / last 2 | 1 fine rows of the scan (:157-277)
-// in float32 arithmetic.  Weights are multiples of 1/8, so every tap product is exact and the chain
-// of four FMAs below reproduces scipy's sum bit for bit.
-GTP_FD double simple_taps_f32(double A, float B, float C, double D, double w00, double w01, double w10, double w11)
+// in float32 arithmetic.  The corners are float32 and the weights multiples of 1/8, so every tap product
+// and partial sum is exact in double: the cast to float32 is the only rounding, and any way of writing
+// the bilinear form gives scipy's value bit for bit (tests/test_fast_math_host.py checks the float32 xyz
+// against the oracle with array_equal).
+// One fine row of a quad: its left edge L = (1 - ty) A + ty D and right-minus-left dR, per component.
+// All of it is exact in double (24-bit corners, 3-bit weights), which is why the evaluation order is free.
+struct SimpleRowF32 { double L[3], dR[3]; };
+
+GTP_FD SimpleRowF32 simple_row_f32(const QuadF32& q, double ty)
 {
-    // taps in scipy's order: (y0, x0) = A, (y0, x1) = B, (y1, x0) = D, (y1, x1) = C
-    return fma((double)C, w11, fma(D, w10, fma((double)B, w01, A * w00)));
+    SimpleRowF32 r;
+    const double wy0 = 1.0 - ty;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        r.L[c] = fma(q.D[c], ty, q.A[c] * wy0);
+        r.dR[c] = fma((double)q.C[c], ty, (double)q.B[c] * wy0) - r.L[c];
+    }
+    return r;
 }
 
-// the sample at column fraction tx (k / P inside the quad) and row fraction ty, a float32 value held in a double
-GTP_FD void simple_sample_f32(const QuadF32& q, double tx, double ty, double (&v)[3])
+// the sample at column fraction tx (k / P inside the quad), a float32 value held in a double
+GTP_FD void simple_sample_f32(const SimpleRowF32& r, double tx, double (&v)[3])
 {
-    const double wy1 = ty, wy0 = 1.0 - ty, wx1 = tx, wx0 = 1.0 - tx;
-    const double w00 = wy0 * wx0, w01 = wy0 * wx1, w10 = wy1 * wx0, w11 = wy1 * wx1;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) v[k] = round_to_f32(simple_taps_f32(q.A[k], q.B[k], q.C[k], q.D[k], w00, w01, w10, w11));
+    for (int c = 0; c < 3; ++c) v[c] = round_to_f32(fma(tx, r.dR[c], r.L[c]));
 }
 
 // The pixels right of the last tie column (fine columns Wf - P .. Wf - 1, evaluated on the quad of tie
 // columns 1352 | 1353): column Wf - P sits on tie column 1353 (both taps clamp to it, 'nearest'), the
 // nc = P - 1 columns after it are that value + diff (o + 1), diff = v[Wf - nc - 1] - v[Wf - nc - 2] (:146-150)
-GTP_FD void simple_sample_right_f32(const QuadF32& q, int P, int k, double ty, double (&v)[3])
+GTP_FD void simple_sample_right_f32(const SimpleRowF32& r, int P, int k, double (&v)[3])
 {
-    const double wy1 = ty, wy0 = 1.0 - ty;
     double prev[3];
-    if (k > 0) simple_sample_f32(q, (double)(P - 1) / (double)P, ty, prev);
+    if (k > 0) simple_sample_f32(r, (double)(P - 1) / (double)P, prev);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        const double e = round_to_f32(fma((double)q.C[c], wy1, (double)q.B[c] * wy0));
+        const double e = round_to_f32(r.L[c] + r.dR[c]);
         if (k == 0) { v[c] = e; continue; }
         const float ef = (float)e;
         const float diff = fsub_rn(ef, (float)prev[c]);
@@ -345,34 +354,52 @@ GTP_FD float simple_ycoord_f32(int res, int j)
     return (float)((double)j * (1.0 / (double)res) - ((double)res * (1.0 / 16.0) + 0.125));
 }
 
-// One fine pixel of the simple interpolator: quad row qr (0..8), row m of that quad row, pixel k of
-// the quad column; `right`: the lane that evaluates the pixels right of the last tie column.
+// What one fine row m of quad row qr (0..8) needs: the row itself, or - for the first / last rows of a
+// scan - the two interior rows the extrapolation line goes through (:157-225): 250 m rows (2, 5) /
+// (34, 37), 500 m rows (1, 2) / (17, 18), and their yc.
 template <int P>
-GTP_FD void simple_pixel_f32(const QuadF32& q, bool right, int qr, int m, int k, double (&v)[3])
+struct SimpleRowsF32 {
+    bool edge;
+    SimpleRowF32 a, b;          // the row | the line's two rows
+    float y_lo, y_hi, y;
+};
+
+template <int P>
+GTP_FD SimpleRowsF32<P> simple_rows_f32(const QuadF32& q, int qr, int m)
 {
     constexpr int kHalf = P / 2;
+    SimpleRowsF32<P> r;
     const double ty0 = ((qr == 0) ? (0.5 - kHalf) : 0.5) / P;
     const bool top = (qr == 0) && (m < kHalf), bottom = (qr == 8) && (m >= P);
-    if (!top && !bottom) {
-        const double ty = ty0 + (double)m / (double)P;
-        if (right) simple_sample_right_f32(q, P, k, ty, v);
-        else simple_sample_f32(q, (double)k / (double)P, ty, v);
-        return;
+    r.edge = top || bottom;
+    r.y_lo = r.y_hi = r.y = 0.0f;
+    if (!r.edge) {
+        r.a = simple_row_f32(q, ty0 + (double)m / (double)P);
+        r.b = r.a;
+        return r;
     }
-    // the two interior rows the line goes through (:157-225): 250 m rows (2, 5) / (34, 37), 500 m rows (1, 2) / (17, 18)
     const int m_lo = top ? kHalf : 0, m_hi = top ? kHalf + P - 1 : P - 1;
     const int j0 = (qr == 0) ? 0 : 8 * P + kHalf;                       // scan row of m = 0
-    double lo[3], hi[3];
-    if (right) {
-        simple_sample_right_f32(q, P, k, ty0 + (double)m_lo / (double)P, lo);
-        simple_sample_right_f32(q, P, k, ty0 + (double)m_hi / (double)P, hi);
-    } else {
-        simple_sample_f32(q, (double)k / (double)P, ty0 + (double)m_lo / (double)P, lo);
-        simple_sample_f32(q, (double)k / (double)P, ty0 + (double)m_hi / (double)P, hi);
+    r.a = simple_row_f32(q, ty0 + (double)m_lo / (double)P);
+    r.b = simple_row_f32(q, ty0 + (double)m_hi / (double)P);
+    r.y_lo = simple_ycoord_f32(P, j0 + m_lo); r.y_hi = simple_ycoord_f32(P, j0 + m_hi); r.y = simple_ycoord_f32(P, j0 + m);
+    return r;
+}
+
+// pixel k of the quad column; `right`: the lane that evaluates the pixels right of the last tie column
+template <int P>
+GTP_FD void simple_pixel_f32(const SimpleRowsF32<P>& r, bool right, int k, double (&v)[3])
+{
+    if (!r.edge) {
+        if (right) simple_sample_right_f32(r.a, P, k, v);
+        else simple_sample_f32(r.a, (double)k / (double)P, v);
+        return;
     }
-    const float y_lo = simple_ycoord_f32(P, j0 + m_lo), y_hi = simple_ycoord_f32(P, j0 + m_hi), y = simple_ycoord_f32(P, j0 + m);
+    double lo[3], hi[3];
+    if (right) { simple_sample_right_f32(r.a, P, k, lo); simple_sample_right_f32(r.b, P, k, hi); }
+    else { simple_sample_f32(r.a, (double)k / (double)P, lo); simple_sample_f32(r.b, (double)k / (double)P, hi); }
 #pragma unroll
-    for (int c = 0; c < 3; ++c) v[c] = (double)simple_line_f32((float)lo[c], (float)hi[c], y_lo, y_hi, y);
+    for (int c = 0; c < 3; ++c) v[c] = (double)simple_line_f32((float)lo[c], (float)hi[c], r.y_lo, r.y_hi, r.y);
 }
 
 }  // namespace gtpfast32

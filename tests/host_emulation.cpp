@@ -286,10 +286,11 @@ static void run_simple_f32(const float* lon, const float* lat, long n_scans, flo
                 const int nrows = P + ((qr == 0 || qr == L - 2) ? H : 0);
                 const int j0 = (qr == 0) ? 0 : qr * P + H;
                 for (int m = 0; m < nrows; ++m) {
+                    const SimpleRowsF32<P> rows = simple_rows_f32<P>(q, qr, m);
                     for (int k = 0; k < P; ++k) {
                         double v[3];
                         float lo, la;
-                        simple_pixel_f32<P>(q, extra, qr, m, k, v);
+                        simple_pixel_f32<P>(rows, extra, k, v);
                         if (q.mode == kSlow) { const LonLatF ll = backtransform_f32_slow((float)v[0], (float)v[1], (float)v[2]); lo = ll.lon; la = ll.lat; }
                         else if (q.wrap) backtransform_f32<kBoth, true>(q, v, lo, la);
                         else if (q.mode == kLow) backtransform_f32<kLow, false>(q, v, lo, la);
