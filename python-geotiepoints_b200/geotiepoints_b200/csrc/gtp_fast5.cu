@@ -71,6 +71,41 @@ __device__ __forceinline__ void store_pair(float* dst, int pair, double2 v)
     __stcs(reinterpret_cast<float2*>(dst) + pair, make_float2((float)v.x, (float)v.y));
 }
 
+// One fine row of a lane's quad (kF pixels) into the warp's staging buffer.  Every evaluation mode writes
+// its pixels itself (arrays merged across the modes would live in local memory); lanes of the inner warps
+// own all 5 columns, so only the swath-edge warps mask.  SHORT: the 5-term forms of the 1 km path (Quad::small).
+template <int MODE, bool MASKED, bool SHORT>
+__device__ __forceinline__ void stage_row(const Quad& q, const RowCoef& rc, const double (&a_col)[kF], unsigned kmask,
+                                          double* my_lon, double* my_lat)
+{
+#pragma unroll
+    for (int k = 0; k < kF; ++k) {
+        double lo, la;
+        if (SHORT) pixel_eval<MODE, false>(q, rc, a_col[k], lo, la);
+        else pixel_eval_long<MODE>(q, rc, a_col[k], lo, la);
+        if (!MASKED || ((kmask >> k) & 1u)) { my_lon[k] = lo; my_lat[k] = la; }
+    }
+}
+
+// The warp's staged row -> global memory: 150 | 152 columns = 75 | 76 pairs, two full rounds of 32 lanes
+// and one of 11 | 12.
+template <typename TOut>
+__device__ __forceinline__ void copy_row_out(const double2* span_lon, const double2* span_lat, int span2, int lane,
+                                             TOut*& dst_lon, TOut*& dst_lat, int pitch)
+{
+    __syncwarp();
+    store_pair(dst_lon, lane, span_lon[lane]);
+    store_pair(dst_lat, lane, span_lat[lane]);
+    store_pair(dst_lon, lane + 32, span_lon[lane + 32]);
+    store_pair(dst_lat, lane + 32, span_lat[lane + 32]);
+    if (lane + 64 < span2) {
+        store_pair(dst_lon, lane + 64, span_lon[lane + 64]);
+        store_pair(dst_lat, lane + 64, span_lat[lane + 64]);
+    }
+    __syncwarp();
+    dst_lon += pitch; dst_lat += pitch;
+}
+
 // TIn / TZen / TOut as in gtp_fast.cu: all-double is the reference's interface; float lon/lat, float
 // or int16 * zen_scale + zen_offset zenith angles and float | double results serve gtp_cviirs_interp_mixed.
 template <typename TIn, typename TZen, typename TOut>
@@ -181,39 +216,9 @@ modis_fast_5km_f64_kernel(const TIn* __restrict__ lon, const TIn* __restrict__ l
     }
     const int mode = (kmask == 0u) ? -1 : ((q.mode == kSlow) ? kSlow : ((q.wrap || q.mode == kBoth) ? kBoth : q.mode));
 
-    // every branch writes its pixels to the buffer itself (arrays merged across the branches would live
-    // in local memory); lanes of the inner warps own all 5 columns, so only the swath-edge warps mask
-#define GTP_STAGE(MODE_, MASKED_)                                                          \
-    _Pragma("unroll") for (int k = 0; k < kF; ++k) {                                       \
-        double lo_, la_;                                                                   \
-        pixel_eval_long<MODE_>(q, rc, a_col[k], lo_, la_);                                 \
-        if (!(MASKED_) || ((kmask >> k) & 1u)) { my_lon[k] = lo_; my_lat[k] = la_; }       \
-    }
-    // the same with the 5-term forms of the 1 km path (Quad::small)
-#define GTP_STAGE_SHORT(MODE_)                                                             \
-    _Pragma("unroll") for (int k = 0; k < kF; ++k) {                                       \
-        double lo_, la_;                                                                   \
-        pixel_eval<MODE_, false>(q, rc, a_col[k], lo_, la_);                               \
-        my_lon[k] = lo_; my_lat[k] = la_;                                                  \
-    }
     const bool edge = first_warp || last_warp;                       // warp-uniform
     TOut* dst_lon = out_lon + row0;
     TOut* dst_lat = out_lat + row0;
-    // the warp's staged row -> global memory: 150 | 152 columns = 75 | 76 pairs, two full rounds of 32
-    // lanes and one of 11 | 12
-#define GTP_COPY_OUT()                                                                     \
-    __syncwarp();                                                                          \
-    store_pair(dst_lon, lane, span_lon[lane]);                                             \
-    store_pair(dst_lat, lane, span_lat[lane]);                                             \
-    store_pair(dst_lon, lane + 32, span_lon[lane + 32]);                                   \
-    store_pair(dst_lat, lane + 32, span_lat[lane + 32]);                                   \
-    if (lane + 64 < span2) {                                                               \
-        store_pair(dst_lon, lane + 64, span_lon[lane + 64]);                               \
-        store_pair(dst_lat, lane + 64, span_lat[lane + 64]);                               \
-    }                                                                                      \
-    __syncwarp();                                                                          \
-    dst_lon += kFineCols; dst_lat += kFineCols;
-
     // Inner warps whose quads all evaluate the same way - nearly all of them - run a row loop without
     // the per-row dispatch (lanes 30 and 31 own no quad there and only help with the copy).
     const bool all_low = !edge && __all_sync(kFull, mode == kLow || mode < 0);
@@ -225,9 +230,9 @@ modis_fast_5km_f64_kernel(const TIn* __restrict__ lon, const TIn* __restrict__ l
             if (mode >= 0) {
                 const double s_t = kTrack5[j];
                 const RowCoef rc = row_setup(q, s_t, s_t * (1.0 - s_t));
-                GTP_STAGE_SHORT(kLow)
+                stage_row<kLow, false, true>(q, rc, a_col, kmask, my_lon, my_lat);
             }
-            GTP_COPY_OUT()
+            copy_row_out(span_lon, span_lat, span2, lane, dst_lon, dst_lat, kFineCols);
         }
         return;
     }
@@ -237,9 +242,9 @@ modis_fast_5km_f64_kernel(const TIn* __restrict__ lon, const TIn* __restrict__ l
             if (mode >= 0) {
                 const double s_t = kTrack5[j];
                 const RowCoef rc = row_setup(q, s_t, s_t * (1.0 - s_t));
-                GTP_STAGE_SHORT(kHigh)
+                stage_row<kHigh, false, true>(q, rc, a_col, kmask, my_lon, my_lat);
             }
-            GTP_COPY_OUT()
+            copy_row_out(span_lon, span_lat, span2, lane, dst_lon, dst_lat, kFineCols);
         }
         return;
     }
@@ -249,9 +254,9 @@ modis_fast_5km_f64_kernel(const TIn* __restrict__ lon, const TIn* __restrict__ l
             if (mode >= 0) {
                 const double s_t = kTrack5[j];
                 const RowCoef rc = row_setup(q, s_t, s_t * (1.0 - s_t));
-                GTP_STAGE(kLow, false)
+                stage_row<kLow, false, false>(q, rc, a_col, kmask, my_lon, my_lat);
             }
-            GTP_COPY_OUT()
+            copy_row_out(span_lon, span_lat, span2, lane, dst_lon, dst_lat, kFineCols);
         }
         return;
     }
@@ -261,9 +266,9 @@ modis_fast_5km_f64_kernel(const TIn* __restrict__ lon, const TIn* __restrict__ l
             if (mode >= 0) {
                 const double s_t = kTrack5[j];
                 const RowCoef rc = row_setup(q, s_t, s_t * (1.0 - s_t));
-                GTP_STAGE(kHigh, false)
+                stage_row<kHigh, false, false>(q, rc, a_col, kmask, my_lon, my_lat);
             }
-            GTP_COPY_OUT()
+            copy_row_out(span_lon, span_lat, span2, lane, dst_lon, dst_lat, kFineCols);
         }
         return;
     }
@@ -272,9 +277,9 @@ modis_fast_5km_f64_kernel(const TIn* __restrict__ lon, const TIn* __restrict__ l
         const double s_t = kTrack5[j];
         if (mode == kLow || mode == kHigh || mode == kBoth) {
             const RowCoef rc = row_setup(q, s_t, s_t * (1.0 - s_t));
-            if (mode == kLow) { GTP_STAGE(kLow, true) }
-            else if (mode == kHigh) { GTP_STAGE(kHigh, true) }
-            else { GTP_STAGE(kBoth, true) }
+            if (mode == kLow) stage_row<kLow, true, false>(q, rc, a_col, kmask, my_lon, my_lat);
+            else if (mode == kHigh) stage_row<kHigh, true, false>(q, rc, a_col, kmask, my_lon, my_lat);
+            else stage_row<kBoth, true, false>(q, rc, a_col, kmask, my_lon, my_lat);
         } else if (mode == kSlow) {
 #pragma unroll 1
             for (int k = 0; k < kF; ++k) {
@@ -289,11 +294,8 @@ modis_fast_5km_f64_kernel(const TIn* __restrict__ lon, const TIn* __restrict__ l
                 my_lon[k] = ll.lon; my_lat[k] = ll.lat;
             }
         }
-        GTP_COPY_OUT()
+        copy_row_out(span_lon, span_lat, span2, lane, dst_lon, dst_lat, kFineCols);
     }
-#undef GTP_COPY_OUT
-#undef GTP_STAGE_SHORT
-#undef GTP_STAGE
 }
 
 }  // namespace
