@@ -78,7 +78,7 @@ int cviirs_device(const T* lon, const T* lat, const T* satz, int64_t n_scans, in
         if (allow_fast && gtp_cviirs_fast_f32_supported(cfg))
             e = gtp_launch_cviirs_fast_f32(lon, lat, satz, out_lon, out_lat, n_scans, cfg, (cudaStream_t)stream);
         else
-            e = gtp_launch_cviirs_generic<T>(lon, lat, satz, out_lon, out_lat, n_scans, cfg, (cudaStream_t)stream);
+            e = gtp_launch_cviirs_generic<T>(lon, lat, satz, out_lon, out_lat, n_scans, cfg, (cudaStream_t)stream, allow_fast);
     }
     if (e != cudaSuccess) return cuda_fail(e, "cviirs launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);

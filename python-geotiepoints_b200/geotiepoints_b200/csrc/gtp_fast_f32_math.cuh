@@ -125,7 +125,15 @@ struct QuadF32 {
     double b1, b2, b3, b4, b5;          // series of sign(z) acos(rho/R) around rho_A'/R, degrees
 };
 
-GTP_FD QuadF32 quad_setup_f32(const TieGeoF& A, const Vec3F& B, const Vec3F& C, const Vec3F& D, float ce, float ca)
+// max_horiz / max_w: acceptance limits of the series, |d_horizontal| / rho_A' and |d_z| / R over the quad.
+// The defaults keep the truncation error below ~1e-13 deg (1 km quads).  5 km quads (gtp_generic.cu) pass
+// kMaxRelHoriz5 / kMaxRelZ5: the float32 result needs ~1e-8 deg, and the first neglected terms are
+// t^7 / 7 <= 3e-12 rad of longitude and a6 w^6 <= 1500 deg x 1e-12 of latitude there.
+GTP_DCONST(kMaxRelHoriz5, 0.03);
+GTP_DCONST(kMaxRelZ5, 1.0e-2);
+
+GTP_FD QuadF32 quad_setup_f32(const TieGeoF& A, const Vec3F& B, const Vec3F& C, const Vec3F& D, float ce, float ca,
+                              double max_horiz, double max_w)
 {
     QuadF32 q;
     q.ce = ce; q.ca = ca;
@@ -159,7 +167,7 @@ GTP_FD QuadF32 quad_setup_f32(const TieGeoF& A, const Vec3F& B, const Vec3F& C, 
     const double horiz = kABound * (absd(Pe) + absd(Ph)) + kTBound * (absd(Qe) + absd(Qh))
                          + kATBound * (absd(Se) + absd(Sh)) + 2.0 * inv_rho;
     const double wmax = (kABound * absd(Pz) + kTBound * absd(Qz) + kATBound * absd(Sz) + 2.0) * kInvEarthR;
-    const bool ok = (horiz <= kMaxRelHoriz) && (wmax <= kMaxRelZ)
+    const bool ok = (horiz <= max_horiz) && (wmax <= max_w)
                     && (absd((double)ce) <= 1.0) && (absd((double)ca) <= 0.5) && (A.cp > 1e-6);
     if (!ok) { q.mode = kSlow; return q; }
 
@@ -199,6 +207,11 @@ GTP_FD QuadF32 quad_setup_f32(const TieGeoF& A, const Vec3F& B, const Vec3F& C, 
         m *= u * c; q.b5 = fma(c2, fma(8.0, c2, 24.0), 3.0) * k1_40 * m;
     }
     return q;
+}
+
+GTP_FD QuadF32 quad_setup_f32(const TieGeoF& A, const Vec3F& B, const Vec3F& C, const Vec3F& D, float ce, float ca)
+{
+    return quad_setup_f32(A, B, C, D, ce, ca, kMaxRelHoriz, kMaxRelZ);
 }
 
 // per (quad, fine row): a_track = s_t (:343) and the s_t-dependent part of a_scan (:344)

@@ -22,10 +22,12 @@
 //   quad_exp_ali       _modis_interpolator.pyx:41-82 _compute_expansion_alignment
 //   cviirs pixel body  _modis_interpolator.pyx:328-344, :379-398
 //   simple pixel body  _simple_modis_interpolator.pyx:71-277 + scipy map_coordinates(order=1,'nearest')
+#include <type_traits>
 #include <cuda_runtime.h>
 #include <math.h>
 #include "gtp_common.cuh"
 #include "gtp_kernels.h"
+#include "gtp_fast_f32_math.cuh"
 
 namespace {
 
@@ -89,14 +91,20 @@ __device__ __forceinline__ void quad_exp_ali(T satz_a, T satz_b, int km, T& c_ex
 // ---------------------------------------------------------------------------------
 // CVIIRS (satellite-zenith driven) interpolator, any configuration.
 // ---------------------------------------------------------------------------------
+// SERIES (float32 5 km -> 1 km only): the back-transform of a pixel is the anchor-relative series of
+// gtp_fast_f32_math.cuh around the float32-rounded corner A of its quad (one QuadF32 per quad in shared
+// memory, set up once per strip) instead of acos / asin / sqrt / two divisions per pixel; quads the
+// series cannot take (6 % of a day's, next to the poles) keep the library formulas.  The blend above it
+// is unchanged, so the float32 fine xyz - and with them the result - stay the reference's.
 // XYZ = true stores the fine Cartesian coordinates (_compute_fine_xyz, :346-398) in out_lon / out_lat /
 // out_z = x / y / z instead of their back-transform.
-template <typename T, bool XYZ>
+template <typename T, bool XYZ, bool SERIES>
 __global__ void __launch_bounds__(kThreads)
 cviirs_generic_kernel(const T* __restrict__ lon, const T* __restrict__ lat, const T* __restrict__ satz,
                       T* __restrict__ out_lon, T* __restrict__ out_lat, T* __restrict__ out_z,
                       long long n_scans, int n_strips, CviirsCfg cfg)
 {
+    static_assert(!SERIES || (std::is_same<T, float>::value && !XYZ), "the series back-transform is float32 lon / lat only");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int L = cfg.L, W = cfg.W;
     const int TC = kStripQuads + 1;                 // tie columns held (with halo)
@@ -105,6 +113,8 @@ cviirs_generic_kernel(const T* __restrict__ lon, const T* __restrict__ lat, cons
     T* sz = sy + L * TC;
     T* sce = sz + L * TC;                           // [L-1][kStripQuads]
     T* sca = sce + (L - 1) * kStripQuads;
+    // SERIES: one QuadF32 per quad behind the coefficient planes (8-byte aligned: an even number of floats precedes it)
+    gtpfast32::QuadF32* sq = reinterpret_cast<gtpfast32::QuadF32*>(sca + (L - 1) * kStripQuads);
 
     const long long scan = blockIdx.x / n_strips;
     const int strip = (int)(blockIdx.x % n_strips);
@@ -130,6 +140,19 @@ cviirs_generic_kernel(const T* __restrict__ lon, const T* __restrict__ lat, cons
         sce[r * kStripQuads + c] = ce; sca[r * kStripQuads + c] = ca;
     }
     __syncthreads();
+    if constexpr (SERIES) {
+        for (int t = threadIdx.x; t < (L - 1) * nq; t += kThreads) {
+            int r = t / nq, c = t - r * nq;
+            const gtpfast32::TieGeoF A = gtpfast32::tie_geo_f32(slon[r * W + q0 + c], slat[r * W + q0 + c]);
+            gtpfast32::Vec3F B, C, D;
+            B.x = sx[r * TC + c + 1]; B.y = sy[r * TC + c + 1]; B.z = sz[r * TC + c + 1];
+            C.x = sx[(r + 1) * TC + c + 1]; C.y = sy[(r + 1) * TC + c + 1]; C.z = sz[(r + 1) * TC + c + 1];
+            D.x = sx[(r + 1) * TC + c]; D.y = sy[(r + 1) * TC + c]; D.z = sz[(r + 1) * TC + c];
+            sq[r * kStripQuads + c] = gtpfast32::quad_setup_f32(A, B, C, D, sce[r * kStripQuads + c], sca[r * kStripQuads + c],
+                                                                gtpfast32::kMaxRelHoriz5, gtpfast32::kMaxRelZ5);
+        }
+        __syncthreads();
+    }
 
     const int i_lo = gtp_quad_col_begin(cfg, q0);
     const int i_hi = (q0 + nq >= W - 1) ? cfg.Wf : gtp_quad_col_begin(cfg, q0 + nq);
@@ -137,6 +160,34 @@ cviirs_generic_kernel(const T* __restrict__ lon, const T* __restrict__ lat, cons
     const T fT = (T)cfg.f;
     T* olon = out_lon + scan * (long long)cfg.n * cfg.Wf;
     T* olat = out_lat + scan * (long long)cfg.n * cfg.Wf;
+
+    if constexpr (SERIES) {
+        // 5 km -> 1 km float32 (f = 5, one quad row per scan): the same rounding points written as in
+        // gtp_fast_f32_math.cuh (blend_f32: 22 instead of 44 float <-> double conversions per pixel, which
+        // is what bounds the loop below), constants instead of run-time divisions, series back-transform
+        constexpr int kInner = 5 * kStripQuads;
+        for (int t = threadIdx.x; t < 10 * ncols; t += kThreads) {
+            int j, ii;
+            if (ncols == kInner) { j = t / kInner; ii = t - j * kInner; }
+            else { j = t / ncols; ii = t - j * ncols; }
+            const int i = i_lo + ii;
+            const int qc = gtpfast::quad_col_5km(i, W);                                 // a7
+            const int c = qc - q0;
+            const float s_s = (float)(i - 2 - 5 * qc) / 5.0f;                           // a5, :341
+            const float s_t = (float)(j - 2) / 5.0f;                                    // :342
+            const gtpfast32::QuadF32& q = sq[c];
+            const gtpfast32::RowF32 rc = gtpfast32::row_setup_f32(q, s_t);
+            const double k1d = gtpfast32::mul_rn((double)s_s, gtpfast32::add_rn(1.0, -(double)s_s));
+            double v[3];
+            gtpfast32::blend_f32(q, rc, s_s, k1d, v);
+            float lo, la;
+            if (q.mode != gtpfast::kSlow) gtpfast32::backtransform_f32<gtpfast::kBoth, true>(q, v, lo, la);
+            else xyz_to_lonlat((float)v[0], (float)v[1], (float)v[2], lo, la);
+            olon[(long long)j * cfg.Wf + i] = lo;
+            olat[(long long)j * cfg.Wf + i] = la;
+        }
+        return;
+    }
 
     for (int t = threadIdx.x; t < cfg.n * ncols; t += kThreads) {
         int j = t / ncols, i = i_lo + (t - j * ncols);
@@ -316,14 +367,25 @@ namespace {
 
 template <typename T, bool XYZ>
 cudaError_t launch_cviirs(const T* lon, const T* lat, const T* satz, T* out_a, T* out_b, T* out_c,
-                          long long n_scans, const CviirsCfg& cfg, cudaStream_t stream)
+                          long long n_scans, const CviirsCfg& cfg, cudaStream_t stream, bool allow_series)
 {
     if (n_scans <= 0) return cudaSuccess;
     const int n_strips = (cfg.W - 1 + kStripQuads - 1) / kStripQuads;
     const size_t smem = sizeof(T) * (3 * cfg.L * (kStripQuads + 1) + 2 * (cfg.L - 1) * kStripQuads);
     const long long blocks = n_scans * n_strips;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    cviirs_generic_kernel<T, XYZ><<<(unsigned)blocks, kThreads, smem, stream>>>(
+    if constexpr (std::is_same<T, float>::value && !XYZ) {
+        // 5 km -> 1 km float32: series back-transform.  Its acceptance limits assume the coordinate range of
+        // f = 5 (|a_track| <= 1.4, |a_scan| <= 2.3); 5 km -> 500 | 250 m reach further (a5: not scaled with f)
+        if (allow_series && cfg.km == 5 && cfg.p == 1) {
+            static_assert(sizeof(gtpfast32::QuadF32) % 8 == 0 && (3 * (kStripQuads + 1) * 2 + 2 * kStripQuads) % 2 == 0, "QuadF32 alignment");
+            const size_t smem_series = smem + sizeof(gtpfast32::QuadF32) * (cfg.L - 1) * kStripQuads;
+            cviirs_generic_kernel<T, false, true><<<(unsigned)blocks, kThreads, smem_series, stream>>>(
+                lon, lat, satz, out_a, out_b, out_c, n_scans, n_strips, cfg);
+            return cudaGetLastError();
+        }
+    }
+    cviirs_generic_kernel<T, XYZ, false><<<(unsigned)blocks, kThreads, smem, stream>>>(
         lon, lat, satz, out_a, out_b, out_c, n_scans, n_strips, cfg);
     return cudaGetLastError();
 }
@@ -346,16 +408,16 @@ cudaError_t launch_simple(const T* lon, const T* lat, T* out_a, T* out_b, T* out
 
 template <typename T>
 cudaError_t gtp_launch_cviirs_generic(const T* lon, const T* lat, const T* satz, T* out_lon, T* out_lat,
-                                      long long n_scans, const CviirsCfg& cfg, cudaStream_t stream)
+                                      long long n_scans, const CviirsCfg& cfg, cudaStream_t stream, bool allow_series)
 {
-    return launch_cviirs<T, false>(lon, lat, satz, out_lon, out_lat, (T*)nullptr, n_scans, cfg, stream);
+    return launch_cviirs<T, false>(lon, lat, satz, out_lon, out_lat, (T*)nullptr, n_scans, cfg, stream, allow_series);
 }
 
 template <typename T>
 cudaError_t gtp_launch_cviirs_generic_xyz(const T* lon, const T* lat, const T* satz, T* out_x, T* out_y, T* out_z,
                                           long long n_scans, const CviirsCfg& cfg, cudaStream_t stream)
 {
-    return launch_cviirs<T, true>(lon, lat, satz, out_x, out_y, out_z, n_scans, cfg, stream);
+    return launch_cviirs<T, true>(lon, lat, satz, out_x, out_y, out_z, n_scans, cfg, stream, false);
 }
 
 template <typename T>
@@ -373,9 +435,9 @@ cudaError_t gtp_launch_simple_generic_xyz(const T* lon, const T* lat, T* out_x, 
 }
 
 template cudaError_t gtp_launch_cviirs_generic<float>(const float*, const float*, const float*, float*, float*,
-                                                      long long, const CviirsCfg&, cudaStream_t);
+                                                      long long, const CviirsCfg&, cudaStream_t, bool);
 template cudaError_t gtp_launch_cviirs_generic<double>(const double*, const double*, const double*, double*, double*,
-                                                       long long, const CviirsCfg&, cudaStream_t);
+                                                       long long, const CviirsCfg&, cudaStream_t, bool);
 template cudaError_t gtp_launch_cviirs_generic_xyz<float>(const float*, const float*, const float*, float*, float*, float*,
                                                           long long, const CviirsCfg&, cudaStream_t);
 template cudaError_t gtp_launch_cviirs_generic_xyz<double>(const double*, const double*, const double*, double*, double*, double*,

@@ -3,10 +3,11 @@
 #include <cuda_runtime.h>
 #include "gtp_common.cuh"
 
-// gtp_generic.cu: rounding-faithful kernels (all configurations, float32/float64)
+// gtp_generic.cu: rounding-faithful kernels (all configurations, float32/float64).  allow_series: float32
+// 5 km -> 1 km may back-transform with the anchor-relative series (same float32 fine xyz, ~3x faster)
 template <typename T>
 cudaError_t gtp_launch_cviirs_generic(const T* lon, const T* lat, const T* satz, T* out_lon, T* out_lat,
-                                      long long n_scans, const CviirsCfg& cfg, cudaStream_t stream);
+                                      long long n_scans, const CviirsCfg& cfg, cudaStream_t stream, bool allow_series = false);
 template <typename T>
 cudaError_t gtp_launch_simple_generic(const T* lon, const T* lat, T* out_lon, T* out_lat,
                                       long long n_scans, int width, int res, cudaStream_t stream);

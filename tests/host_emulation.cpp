@@ -317,3 +317,45 @@ extern "C" int gtp_emul_simple_fast_f32(const float* lon, const float* lat, long
     else return 1;
     return 0;
 }
+
+// ---- float32 5 km -> 1 km: the series back-transform of the strip kernel (gtp_generic.cu, use_series) ----
+// the reference's float32 blend (blend_f32 has the same rounding points as the kernel's) followed by the
+// anchor-relative back-transform with the 5 km acceptance limits
+extern "C" int gtp_emul_cviirs5_series_f32(const float* lon, const float* lat, const float* satz, long n_scans,
+                                           int W, float* out_lon, float* out_lat, long* mode_counts)
+{
+    using namespace gtpfast32;
+    for (int k = 0; k < 5; ++k) mode_counts[k] = 0;
+    if (W != 270 && W != 271) return 1;
+    const int Wf = 1354, nq = W - 1;
+    for (long s = 0; s < n_scans; ++s) {
+        for (int qc = 0; qc < nq; ++qc) {
+            auto geo = [&](int r, int c) { long o = (s * 2 + r) * W + c; return tie_geo_f32(lon[o], lat[o]); };
+            auto v3 = [](const TieGeoF& t) { Vec3F v; v.x = t.x; v.y = t.y; v.z = t.z; return v; };
+            const TieGeoF A = geo(0, qc);
+            const Vec3F B = v3(geo(0, qc + 1)), D = v3(geo(1, qc)), C = v3(geo(1, qc + 1));
+            const TieZenF za = tie_zen_f32(satz[(s * 2) * W + qc]), zb = tie_zen_f32(satz[(s * 2) * W + qc + 1]);
+            float ce, cal;
+            quad_exp_ali_f32(za, zb.phi, zb.theta, 5, ce, cal);
+            const QuadF32 q = quad_setup_f32(A, B, C, D, ce, cal, kMaxRelHoriz5, kMaxRelZ5);
+            mode_counts[q.mode]++;
+            const int i0 = (qc == 0) ? 0 : 2 + 5 * qc, i1 = (qc == nq - 1) ? Wf : 2 + 5 * qc + 5;
+            for (int j = 0; j < 10; ++j) {
+                const float s_t = (float)(j - 2) / 5.0f;
+                const RowF32 rc = row_setup_f32(q, s_t);
+                for (int i = i0; i < i1; ++i) {
+                    const float s_s = (float)coord_x_5km(i, W) / 5.0f;
+                    const double k1d = mul_rn((double)s_s, add_rn(1.0, -(double)s_s));
+                    double v[3];
+                    float lo, la;
+                    blend_f32(q, rc, s_s, k1d, v);
+                    if (q.mode == kSlow) { const LonLatF ll = backtransform_f32_slow((float)v[0], (float)v[1], (float)v[2]); lo = ll.lon; la = ll.lat; }
+                    else backtransform_f32<kBoth, true>(q, v, lo, la);
+                    const long o = (s * 10 + j) * (long)Wf + i;
+                    out_lon[o] = lo; out_lat[o] = la;
+                }
+            }
+        }
+    }
+    return 0;
+}

@@ -86,6 +86,17 @@ def emul():
         return out[0], out[1], tuple(out[2:]), dict(zip(("slow", "low", "high", "both", "small", "wide"), modes))
     run.simple_f32 = run_simple_f32
 
+    def run_5km_f32(lon, lat, satz):
+        ns, w = lon.shape[0] // 2, lon.shape[1]
+        out_lon = np.full((ns * 10, 1354), np.nan, np.float32)
+        out_lat = np.full_like(out_lon, np.nan)
+        modes = (ctypes.c_long * 6)()
+        rc = lib.gtp_emul_cviirs5_series_f32(lon.ctypes.data_as(fp), lat.ctypes.data_as(fp), satz.ctypes.data_as(fp),
+                                             ctypes.c_long(ns), w, out_lon.ctypes.data_as(fp), out_lat.ctypes.data_as(fp), modes)
+        assert rc == 0
+        return out_lon, out_lat, dict(zip(("slow", "low", "high", "both", "small", "wide"), modes))
+    run.five_km_f32 = run_5km_f32
+
     def run_xyz(lon, lat, satz, fine):
         ns, p = lon.shape[0] // 10, 1000 // fine
         out = [np.full((ns * 10 * p, 1354 * p), np.nan) for _ in range(3)]
@@ -286,3 +297,29 @@ def test_simple_f32_fast_math_stress_inputs(emul, golden_inputs, name):
         for g, e in zip(xyz, exp_xyz):
             assert np.array_equal(g, e, equal_nan=True), f"{name}: {(g != e).sum()} float32 xyz values differ"
         assert_parity(got_lon, got_lat, *exp, what=f"host emulation simple f32 {name} -> {fine} m, modes {modes}")
+
+
+# ---- float32 5 km -> 1 km: series back-transform inside the strip kernel (gtp_generic.cu) ----
+@pytest.mark.parametrize("width", [271, 270])
+@pytest.mark.parametrize("granule", [0, 3, 4, 5, 14, 34, 287])
+def test_5km_f32_series_matches_oracle(emul, granule, width):
+    lon, lat, satz = testing.subsample_5km(*testing.modis_granule(granule, dtype=np.float32), width=width)
+    got_lon, got_lat, modes = emul.five_km_f32(lon, lat, satz)
+    with np.errstate(all="ignore"):
+        exp = gtp_oracle.cviirs(lon, lat, satz, 5000, 1000, width, n_threads=8)
+    s = assert_parity(got_lon, got_lat, *exp, what=f"host emulation 5km({width}) f32 granule {granule}, modes {modes}")
+    assert s["bit_exact_fraction"] > 0.999, (s, modes)
+    if granule in (0, 3, 287):          # away from the poles the series takes (nearly) every quad
+        assert modes["slow"] < 0.02 * sum(modes.values()), modes
+
+
+@pytest.mark.parametrize("name", ["real", "antimeridian", "pole", "south_pole", "prime_meridian", "lat_switch",
+                                  "symmetric_satz", "zeros", "nan_holes"])
+def test_5km_f32_series_stress_inputs(emul, golden_inputs, name):
+    from cases import cviirs_inputs
+    for width in (271, 270):
+        lon, lat, satz = cviirs_inputs(golden_inputs[name], 5000, width, np.float32)
+        got_lon, got_lat, modes = emul.five_km_f32(lon, lat, satz)
+        with np.errstate(all="ignore"):
+            exp = gtp_oracle.cviirs(lon, lat, satz, 5000, 1000, width)
+        assert_parity(got_lon, got_lat, *exp, what=f"host emulation 5km({width}) f32 {name}, modes {modes}")
