@@ -109,3 +109,41 @@ def test_output_stays_near_the_tie_points_full_granule():
     assert d.max() < 6000.0, d.max()
     lons5, lats5 = modisinterpolator.modis_5km_to_1km(*testing.subsample_5km(lon, lat, satz, 271))
     assert haversine_m(lons5, lats5, lon, lat).max() < 60.0
+
+
+def _lon_diff(a, b):
+    d = np.abs(a - b)
+    return np.minimum(d, 360.0 - d)
+
+
+@pytest.mark.parametrize("granule", [7, 14])
+def test_mirror_and_rotation_symmetries_full_granule(granule):
+    """Symmetries of the algorithm, at full size and without the oracle: mirroring the tie points at the
+    equator (lat -> -lat) mirrors the result; rotating them about the Earth's axis (lon -> lon + 30 deg,
+    the reference's own equivariance test, tests/test_modisinterpolator.py:152-164) rotates it.  Granule 14
+    sweeps over the pole, so every evaluation mode of the fast path takes part."""
+    lon, lat, satz = testing.modis_granule(granule)
+    base = modisinterpolator.modis_1km_to_250m(lon, lat, satz)
+    base = (np.array(base[0]), np.array(base[1]))
+    mirrored = modisinterpolator.modis_1km_to_250m(lon, -lat, satz)
+    # sin(-x) = -sin(x) exactly, so z -> -z exactly: the series around the mirrored anchor are the mirror images
+    assert np.abs(mirrored[1] + base[1]).max() <= 1e-12
+    assert _lon_diff(mirrored[0], base[0]).max() <= 1e-12
+    shifted_in = ((lon + 30.0 + 180.0) % 360.0) - 180.0
+    rotated = modisinterpolator.modis_1km_to_250m(shifted_in, lat, satz)
+    assert np.abs(rotated[1] - base[1]).max() <= 1e-10
+    # longitude: 1e-10 deg where it is well conditioned (tests/parity.py: away from the |sin lon| band of
+    # either result and from the poles)
+    expect = ((base[0] + 30.0 + 180.0) % 360.0) - 180.0
+    ok = (np.abs(np.sin(np.deg2rad(base[0]))) > 2e-4) & (np.abs(np.sin(np.deg2rad(expect))) > 2e-4) & (np.abs(base[1]) < 89.9)
+    assert _lon_diff(rotated[0], expect)[ok].max() <= 1e-10
+    # the same two symmetries through the 5 km path and the ECEF output
+    from geotiepoints_b200 import ecef
+    l5 = testing.subsample_5km(lon, lat, satz, 271)
+    b5 = modisinterpolator.modis_5km_to_1km(*l5)
+    b5 = (np.array(b5[0]), np.array(b5[1]))
+    m5 = modisinterpolator.modis_5km_to_1km(l5[0], -l5[1], l5[2])
+    assert np.abs(m5[1] + b5[1]).max() <= 1e-12 and _lon_diff(m5[0], b5[0]).max() <= 1e-12
+    x, y, z = (np.array(a) for a in ecef.modis_1km_to_250m(lon, lat, satz))
+    xm, ym, zm = ecef.modis_1km_to_250m(lon, -lat, satz)
+    assert np.abs(xm - x).max() <= 1e-8 and np.abs(ym - y).max() <= 1e-8 and np.abs(zm + z).max() <= 1e-8
