@@ -188,28 +188,56 @@ cudaError_t launch(const float* lon, const float* lat, const float* satz, float*
 }
 
 // ---- simple_modis_interpolator, float32: same decomposition, no zenith angles ----
+template <int MODE, bool WRAP>
+__device__ __forceinline__ void simple_backtransform(const QuadF32& q, const double (&v)[3], float& lon, float& lat)
+{
+    if (MODE == kSlow) {
+        const LonLatF ll = backtransform_f32_slow((float)v[0], (float)v[1], (float)v[2]);
+        lon = ll.lon; lat = ll.lat;
+    } else {
+        backtransform_f32<MODE, WRAP>(q, v, lon, lat);
+    }
+}
+
+// The fine rows of one quad.  Interior rows (all but the first / last 2 | 1 rows of a scan) are one
+// bilinear sample per pixel; the scan-edge rows, which only quad rows 0 and 8 have, go through the
+// reference's float32 line fit (simple_rows_f32 / simple_pixel_f32) in a loop of their own.
 template <int P, int MODE, bool WRAP>
 __device__ __forceinline__ void quad_rows_simple(const QuadF32& q, bool right, int qr, int nrows, float* olon, float* olat)
 {
     constexpr long long kPitch = (long long)kW * P;
+    constexpr int kHalf = P / 2;
+    const int m0 = (qr == 0) ? kHalf : 0;                       // interior rows [m0, m0 + P)
+    double ty = 0.5 / P;                                        // row fraction of row m0: the first fine row below the tie row
 #pragma unroll 1
-    for (int m = 0; m < nrows; ++m) {
+    for (int m = m0; m < m0 + P; ++m) {
+        const SimpleRowF32 row = simple_row_f32(q, ty);
+        float vlon[P], vlat[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+            double v[3];
+            if (right) simple_sample_right_f32(row, P, k, v);
+            else simple_sample_f32(row, (double)k / (double)P, v);
+            simple_backtransform<MODE, WRAP>(q, v, vlon[k], vlat[k]);
+        }
+        store_px<P>(olon + m * kPitch, vlon);
+        store_px<P>(olat + m * kPitch, vlat);
+        ty += 1.0 / P;
+    }
+    if (nrows == P) return;
+    const int e0 = (qr == 0) ? 0 : P;                           // scan-edge rows [e0, e0 + kHalf)
+#pragma unroll 1
+    for (int m = e0; m < e0 + kHalf; ++m) {
         const SimpleRowsF32<P> rows = simple_rows_f32<P>(q, qr, m);
         float vlon[P], vlat[P];
 #pragma unroll
         for (int k = 0; k < P; ++k) {
             double v[3];
             simple_pixel_f32<P>(rows, right, k, v);
-            if (MODE == kSlow) {
-                const LonLatF ll = backtransform_f32_slow((float)v[0], (float)v[1], (float)v[2]);
-                vlon[k] = ll.lon; vlat[k] = ll.lat;
-            } else {
-                backtransform_f32<MODE, WRAP>(q, v, vlon[k], vlat[k]);
-            }
+            simple_backtransform<MODE, WRAP>(q, v, vlon[k], vlat[k]);
         }
-        store_px<P>(olon, vlon);
-        store_px<P>(olat, vlat);
-        olon += kPitch; olat += kPitch;
+        store_px<P>(olon + m * kPitch, vlon);
+        store_px<P>(olat + m * kPitch, vlat);
     }
 }
 
