@@ -11,7 +11,9 @@ values of ``MODISInterpolator._compute_fine_xyz`` (``_modis_interpolator.pyx:346
     x, y, z = ecef.modis_1km_to_250m(lon1, lat1, satz1)
 
 Same argument rules as :mod:`geotiepoints_b200.modisinterpolator`: 2-D float32 or float64 arrays of one
-dtype, whole scans, numpy arrays (host path) or torch CUDA tensors (zero copy).  The MOD03 on-disk
+dtype, whole scans, numpy arrays (host path) or torch CUDA tensors (zero copy); dask / xarray inputs
+are converted with ``numpy.ascontiguousarray``, i.e. computed eagerly (the lazy whole-scan block mapping
+of ``scanline_mapblocks`` is wired to the lon / lat operators only).  The MOD03 on-disk
 types are served by ``mod03.modis_1km_to_250m(..., ecef=True)``.
 """
 import warnings
