@@ -73,6 +73,79 @@ __device__ __forceinline__ void quad_rows(const QuadF32& q, const float (&s_s)[P
     }
 }
 
+// The same rows with the blend on the FP32 pipe (gtp_fast_f32_math.cuh, "error-free transforms"): pixel
+// pairs in the two lanes of the packed float instructions, one component after the other; the displacement
+// from corner A goes to double for the back-transform (3 conversions per pixel instead of 23).  One
+// instance serves low- and high-latitude quads (the latitude series is chosen per quad: `high`); quads that
+// need the per-pixel latitude switch or the +-180 wrap are rare and stay with quad_rows.  Returns true when
+// any value of the quad sat within 2^-20 of a rounding boundary (one quad in ~1500): the caller then
+// evaluates the whole quad again with blend_f32 (the stores are idempotent).
+template <int P>
+__device__ __forceinline__ bool quad_rows_eft(const QuadF32& q, const QuadEft& qe, const float (&s_s)[P],
+                                              const double (&k1d)[P], float s_t0, int nrows, float* olon, float* olat)
+{
+    constexpr long long kPitch = (long long)kW * P;
+    const bool high = (q.mode == kHigh);
+    EdgeP2 top[3], bot[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        top[c].A = p2_dup(qe.A[c]); top[c].B = p2_dup(qe.B[c]); top[c].d = p2_dup(qe.dAB[c]);
+        bot[c].A = p2_dup(qe.D[c]); bot[c].B = p2_dup(qe.C[c]); bot[c].d = p2_dup(qe.dDC[c]);
+    }
+    // the latitude series of this quad: in w = dz / R (low) or in v = rho / rho_A - 1 (high)
+    const double c0 = high ? q.lat0_high : q.lat0_low;
+    const double c1 = high ? q.b1 : q.a1, c2 = high ? q.b2 : q.a2, c3 = high ? q.b3 : q.a3,
+                 c4 = high ? q.b4 : q.a4, c5 = high ? q.b5 : q.a5;
+    const double ced = (double)q.ce;
+    double a_col[P];                                    // s_s + s_s (1 - s_s) c_exp, the row-independent part of a_scan
+#pragma unroll
+    for (int k = 0; k < P; ++k) a_col[k] = add_rn((double)s_s[k], mul_rn(k1d[k], ced));
+    const P2 m1 = p2_dup(-1.0f);
+    P2 acc = p2_dup(0.0f);
+    float s_t = s_t0;
+#pragma unroll 1
+    for (int m = 0; m < nrows; ++m) {
+        const RowF32 rc = row_setup_f32(q, s_t);
+        const P2 st2 = p2_dup(s_t), omt2 = p2_dup(fsub_rn(1.0f, s_t));      // exact: multiples of 1/8
+        float vlon[P], vlat[P];
+#pragma unroll
+        for (int k = 0; k < P; k += 2) {
+            const P2 a2 = p2_make((float)add_rn(a_col[k], rc.row_ca), (float)add_rn(a_col[k + 1], rc.row_ca));
+            const P2 na2 = p2_mul(a2, m1);
+            F2 d[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const P2 s1 = eft_edge(a2, na2, top[c], acc);
+                const P2 s2 = eft_edge(a2, na2, bot[c], acc);
+                d[c] = p2_get(eft_track(s1, s2, st2, omt2, top[c].A));
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const double dx = (double)(u ? d[0].y : d[0].x), dy = (double)(u ? d[1].y : d[1].x),
+                             dz = (double)(u ? d[2].y : d[2].x);
+                const double e = fma(q.ue0, dx, q.ue1 * dy);
+                const double h = fma(q.uh0, dx, q.uh1 * dy);
+                const double g = 1.0 + h;
+                double rcp = fma(h, h - 1.0, 1.0);
+                rcp = fma(rcp, fma(-g, rcp, 1.0), rcp);
+                const double t = e * rcp;
+                const double t2 = t * t;
+                const double at = fma(t * t2, fma(t2, 0.2, -kThird), t);
+                vlon[k + u] = (float)fma(at, kRad2Deg, q.lon0);
+                double x = dz * kInvEarthR;
+                if (high) x = fma(g, t2 * fma(t2, fma(t2, 0.0625, -0.125), 0.5), h);
+                vlat[k + u] = (float)fma(x, fma(x, fma(x, fma(x, fma(x, c5, c4), c3), c2), c1), c0);
+            }
+        }
+        store_px<P>(olon, vlon);
+        store_px<P>(olat, vlat);
+        olon += kPitch; olat += kPitch;
+        s_t += 1.0f / P;
+    }
+    const F2 fl = p2_get(acc);
+    return !(fl.x == 0.0f) || !(fl.y == 0.0f);
+}
+
 template <int P>
 __global__ void __launch_bounds__(kThreads, 4)
 cviirs_fast_1km_f32_kernel(const float* __restrict__ lon, const float* __restrict__ lat,
@@ -150,11 +223,16 @@ cviirs_fast_1km_f32_kernel(const float* __restrict__ lon, const float* __restric
             const float s_t0 = ((qr == 0) ? (0.5f - kHalf) : 0.5f) / P;     // y[j] / f (:342)
             Vec3F curAv; curAv.x = curA.x; curAv.y = curA.y; curAv.z = curA.z;
             const QuadF32 q = quad_setup_f32(topA, topB, curB, curAv, top_ce, top_ca);
+            Vec3F topAv; topAv.x = topA.x; topAv.y = topA.y; topAv.z = topA.z;
+            const QuadEft qe = quad_eft_setup(topAv, topB, curB, curAv, extra ? 16.0f : 8.0f);
+            // FP32-pipe blend for plain low- / high-latitude quads; the rest (a component near 0, the latitude
+            // switch or the +-180 wrap inside the quad, a value on a rounding boundary) the reference's way
+            bool faithful = !qe.ok || q.wrap || q.mode == kBoth;
             if (q.mode == kSlow) quad_rows<P, kSlow, false>(q, s_s, k1d, s_t0, nrows, olon, olat);
-            else if (q.wrap) quad_rows<P, kBoth, true>(q, s_s, k1d, s_t0, nrows, olon, olat);
-            else if (q.mode == kLow) quad_rows<P, kLow, false>(q, s_s, k1d, s_t0, nrows, olon, olat);
-            else if (q.mode == kHigh) quad_rows<P, kHigh, false>(q, s_s, k1d, s_t0, nrows, olon, olat);
-            else quad_rows<P, kBoth, false>(q, s_s, k1d, s_t0, nrows, olon, olat);
+            else {
+                if (!faithful) faithful = quad_rows_eft<P>(q, qe, s_s, k1d, s_t0, nrows, olon, olat);
+                if (faithful) quad_rows<P, kBoth, true>(q, s_s, k1d, s_t0, nrows, olon, olat);
+            }
             olon += (long long)nrows * kWf;
             olat += (long long)nrows * kWf;
         }

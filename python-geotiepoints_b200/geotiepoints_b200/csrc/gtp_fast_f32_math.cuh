@@ -246,12 +246,109 @@ GTP_FD void blend_f32(const QuadF32& q, const RowF32& r, float s_s, double k1d, 
     }
 }
 
-// xyz2lonlat of the float32 xyz, anchor-relative in double, result rounded to float (:51-65)
-template <int MODE, bool WRAP>
-GTP_FD void backtransform_f32(const QuadF32& q, const double (&v)[3], float& lon, float& lat)
+// ---- the same blend on the FP32 pipe: error-free transforms instead of double arithmetic -----------
+// blend_f32 spends 7 float<->double conversions (16 / clk / SM) and 11 FP64 instructions (2 issue slots
+// each) per component and pixel.  The reference's value of one edge,
+//     s = (float)((1.0 - a) * A + (double)(float)(a * B))          (_modis_interpolator.pyx:396-397)
+// is the float32 rounding of E = A + a (B - A) - ep up to the rounding of its double operations
+// (<= 2^-29 float32 ulps), with ep = a B - RN32(a B), the error of the float product, itself a float
+// (one FMA).  With beta = B - A exact in float32 and |a beta| <= |A| / 2:
+//     sigma = RN32(A + a beta)                   1 FMA
+//     eps   = RN32((A - sigma) + a beta)         1 ADD (exact, Sterbenz) + 1 FMA: the residual of sigma to 2^-24
+//     tau   = eps - ep                           1 MUL + 1 FMA (ep) + 1 ADD; |tau| <~ 1 ulp(sigma)
+//     s     = RN32(sigma + tau)
+// tau carries a relative error <= 2^-22, so s can be wrong only where sigma + tau lies within 2^-22 |tau| of
+// a rounding boundary: s is evaluated with tau (1 +- 2^-20) and the pixel is FLAGGED when the two differ
+// (one pixel in ~1e5); the caller re-evaluates flagged rows with blend_f32.  Everything is written on
+// pairs of float lanes (fma.rn.f32x2 & co. on sm_100: one issue slot for two lanes).  The second blend,
+//     v = (float)((1.0 - s_t) * s1 + (double)(float)(s_t * s2))    (:398)
+// has a 4-bit weight, so (1.0 - s_t) s1 and the sum are exact in double and one float FMA rounds identically.
+struct F2 { float x, y; };
+
+#ifdef __CUDA_ARCH__
+typedef unsigned long long P2;          // two float lanes in one 64-bit register
+GTP_FD P2 p2_make(float lo, float hi) { P2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+GTP_FD F2 p2_get(P2 v) { F2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+GTP_FD P2 p2_fma(P2 a, P2 b, P2 c) { P2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+GTP_FD P2 p2_mul(P2 a, P2 b) { P2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+GTP_FD P2 p2_add(P2 a, P2 b) { P2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+#else
+typedef F2 P2;
+GTP_FD P2 p2_make(float lo, float hi) { P2 r; r.x = lo; r.y = hi; return r; }
+GTP_FD F2 p2_get(P2 v) { return v; }
+GTP_FD P2 p2_fma(P2 a, P2 b, P2 c) { P2 d; d.x = fmaf(a.x, b.x, c.x); d.y = fmaf(a.y, b.y, c.y); return d; }
+GTP_FD P2 p2_mul(P2 a, P2 b) { P2 d; d.x = fmul_rn(a.x, b.x); d.y = fmul_rn(a.y, b.y); return d; }
+GTP_FD P2 p2_add(P2 a, P2 b) { P2 d; d.x = fadd_rn(a.x, b.x); d.y = fadd_rn(a.y, b.y); return d; }
+#endif
+GTP_FD P2 p2_dup(float v) { return p2_make(v, v); }
+
+// One edge of a quad for a pair of lanes: the anchor corner, the other corner and their difference.
+struct EdgeP2 { P2 A, B, d; };
+
+#define GTP_EFT_UP 1.00000095367431640625f      // 1 + 2^-20
+#define GTP_EFT_DN 0.999999046325683593750f     // 1 - 2^-20
+
+// s of the header comment for two lanes; acc collects (s+ - s-)^2: non-zero (or NaN) = flagged
+GTP_FD P2 eft_edge(P2 a, P2 na, const EdgeP2& e, P2& acc)
 {
-    const double zd = v[2];
-    const double dx = v[0] - q.A[0], dy = v[1] - q.A[1], dz = zd - q.A[2];
+    const P2 m1 = p2_dup(-1.0f);
+    const P2 sigma = p2_fma(a, e.d, e.A);
+    const P2 d0 = p2_fma(sigma, m1, e.A);
+    const P2 eps = p2_fma(a, e.d, d0);
+    const P2 p = p2_mul(a, e.B);
+    const P2 nep = p2_fma(na, e.B, p);
+    const P2 tau = p2_add(eps, nep);
+    const P2 sp = p2_fma(tau, p2_dup(GTP_EFT_UP), sigma);
+    const P2 sm = p2_fma(tau, p2_dup(GTP_EFT_DN), sigma);
+    const P2 df = p2_fma(sm, m1, sp);
+    acc = p2_fma(df, df, acc);
+    return sp;
+}
+
+// v - A_top for two lanes: the second blend (:398) and the displacement from the anchor (exact)
+GTP_FD P2 eft_track(P2 s1, P2 s2, P2 st, P2 omt, P2 A)
+{
+    const P2 v = p2_fma(omt, s1, p2_mul(st, s2));
+    return p2_fma(A, p2_dup(-1.0f), v);
+}
+
+// What the FP32-pipe blend of one quad needs.  ok: in every component the corners A and D are at least
+// `margin` times larger than the quad's extent ext = max(|B - A|, |C - D|, |D - A|) (or the component is 0
+// at all four corners).  Then B - A and C - D are exact (Sterbenz), |a beta| <= |A| / 2 for |a| <= margin / 2
+// - 0.7, and |v - A| <= (|1 - t| a + |t| (1 + a)) ext < |A| / 2, so A - sigma and v - A are exact too:
+// margin 8 for |a| <= 1.3, |t| <= 1.375 (the quad's own pixels), 16 for the lane that extrapolates right of
+// the last quad (|a| <= 3.3).  Quads that fail (a component changes sign within a few quad widths: ~1 % of
+// a day) take blend_f32.
+struct QuadEft {
+    float A[3], B[3], C[3], D[3];
+    float dAB[3], dDC[3];               // B - A, C - D
+    bool ok;
+};
+
+GTP_FD QuadEft quad_eft_setup(const Vec3F& A, const Vec3F& B, const Vec3F& C, const Vec3F& D, float margin)
+{
+    QuadEft q;
+    q.A[0] = A.x; q.A[1] = A.y; q.A[2] = A.z; q.B[0] = B.x; q.B[1] = B.y; q.B[2] = B.z;
+    q.C[0] = C.x; q.C[1] = C.y; q.C[2] = C.z; q.D[0] = D.x; q.D[1] = D.y; q.D[2] = D.z;
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        q.dAB[k] = fsub_rn(q.B[k], q.A[k]);
+        q.dDC[k] = fsub_rn(q.C[k], q.D[k]);
+        const float ext = fmaxf(fmaxf(fabsf(q.dAB[k]), fabsf(q.dDC[k])), fabsf(fsub_rn(q.D[k], q.A[k])));
+        const float amin = fminf(fabsf(q.A[k]), fabsf(q.D[k]));
+        // NaN corners fail the first comparison; 1e-20: no underflow in the error terms of the products
+        ok = ok && (amin >= fmul_rn(margin, ext)) && (amin >= 1e-20f || (amin == 0.0f && ext == 0.0f));
+    }
+    q.ok = ok;
+    return q;
+}
+
+// xyz2lonlat of the float32 xyz, anchor-relative in double, result rounded to float (:51-65)
+// (dx, dy, dz) = the float32 xyz minus corner A (exact either way), zd = the float32 z
+template <int MODE, bool WRAP>
+GTP_FD void backtransform_f32_d(const QuadF32& q, double dx, double dy, double dz, double zd, float& lon, float& lat)
+{
     const double e = fma(q.ue0, dx, q.ue1 * dy);
     const double h = fma(q.uh0, dx, q.uh1 * dy);
     const double w = dz * kInvEarthR;
@@ -283,6 +380,12 @@ GTP_FD void backtransform_f32(const QuadF32& q, const double (&v)[3], float& lon
         la = (zd < thr_r && zd > -thr_r) ? la_low : la_high;
     }
     lat = (float)la;
+}
+
+template <int MODE, bool WRAP>
+GTP_FD void backtransform_f32(const QuadF32& q, const double (&v)[3], float& lon, float& lat)
+{
+    backtransform_f32_d<MODE, WRAP>(q, v[0] - q.A[0], v[1] - q.A[1], v[2] - q.A[2], v[2], lon, lat);
 }
 
 struct LonLatF { float lon, lat; };

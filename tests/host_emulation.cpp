@@ -231,14 +231,58 @@ static void run_f32(const float* lon, const float* lat, const float* satz, long 
                 const int j0 = (qr == 0) ? 0 : qr * P + H;
                 const int j1 = (qr == L - 2) ? N : (qr + 1) * P + H;
                 float s_t = ((qr == 0) ? (0.5f - H) : 0.5f) / P;
+                Vec3F Av; Av.x = A.x; Av.y = A.y; Av.z = A.z;
+                const QuadEft qe = quad_eft_setup(Av, B, C, D, extra ? 16.0f : 8.0f);
+                const bool use_eft = qe.ok && q.mode != kSlow;
+                if (use_eft) mode_counts[5]++;
                 for (int j = j0; j < j1; ++j, s_t += 1.0f / P) {
                     const RowF32 rc = row_setup_f32(q, s_t);
+                    // the kernel's FP32-pipe blend: pairs of pixels, three components each
+                    double dv[P][3]; float vz[P]; bool flagged = false;
+                    if (use_eft) {
+                        const P2 st2 = p2_dup(s_t), omt2 = p2_dup((float)rc.omt);
+                        for (int k = 0; k < P; k += 2) {
+                            float af[2];
+                            for (int u = 0; u < 2; ++u) {
+                                const float s_s = (float)(xoff + k + u) / (float)P;
+                                const double k1d = mul_rn((double)s_s, add_rn(1.0, -(double)s_s));
+                                af[u] = (float)add_rn(add_rn((double)s_s, mul_rn(k1d, (double)q.ce)), rc.row_ca);
+                            }
+                            const P2 a2 = p2_make(af[0], af[1]), na2 = p2_make(-af[0], -af[1]);
+                            P2 acc = p2_dup(0.0f);
+                            for (int c = 0; c < 3; ++c) {
+                                EdgeP2 top, bot;
+                                top.A = p2_dup(qe.A[c]); top.B = p2_dup(qe.B[c]); top.d = p2_dup(qe.dAB[c]);
+                                bot.A = p2_dup(qe.D[c]); bot.B = p2_dup(qe.C[c]); bot.d = p2_dup(qe.dDC[c]);
+                                const P2 s1 = eft_edge(a2, na2, top, acc), s2 = eft_edge(a2, na2, bot, acc);
+                                const F2 d = p2_get(eft_track(s1, s2, st2, omt2, top.A));
+                                dv[k][c] = (double)d.x; dv[k + 1][c] = (double)d.y;
+                                if (c == 2) { vz[k] = fadd_rn(d.x, qe.A[2]); vz[k + 1] = fadd_rn(d.y, qe.A[2]); }
+                            }
+                            const F2 fl = p2_get(acc);
+                            if (!(fl.x == 0.0f) || !(fl.y == 0.0f)) flagged = true;
+                        }
+                        if (flagged) mode_counts[6]++;
+                    }
                     for (int k = 0; k < P; ++k) {
                         const float s_s = (float)(xoff + k) / (float)P;
                         const double k1d = mul_rn((double)s_s, add_rn(1.0, -(double)s_s));
                         double v[3];
                         float lo, la;
                         blend_f32(q, rc, s_s, k1d, v);
+                        if (use_eft && !flagged) {
+                            // the two blends must agree bit for bit wherever the FP32 one is trusted
+                            for (int c = 0; c < 3; ++c) if (v[c] - q.A[c] != dv[k][c]) mode_counts[7]++;
+                            if ((double)vz[k] != v[2]) mode_counts[7]++;
+                            const double zd = (double)vz[k];
+                            if (q.wrap) backtransform_f32_d<kBoth, true>(q, dv[k][0], dv[k][1], dv[k][2], zd, lo, la);
+                            else if (q.mode == kLow) backtransform_f32_d<kLow, false>(q, dv[k][0], dv[k][1], dv[k][2], zd, lo, la);
+                            else if (q.mode == kHigh) backtransform_f32_d<kHigh, false>(q, dv[k][0], dv[k][1], dv[k][2], zd, lo, la);
+                            else backtransform_f32_d<kBoth, false>(q, dv[k][0], dv[k][1], dv[k][2], zd, lo, la);
+                            const long o = (s * N + j) * (long)Wf + (long)ca * P + xoff + k;
+                            out_lon[o] = lo; out_lat[o] = la;
+                            continue;
+                        }
                         if (q.mode == kSlow) { const LonLatF ll = backtransform_f32_slow((float)v[0], (float)v[1], (float)v[2]); lo = ll.lon; la = ll.lat; }
                         else if (q.wrap) backtransform_f32<kBoth, true>(q, v, lo, la);
                         else if (q.mode == kLow) backtransform_f32<kLow, false>(q, v, lo, la);
@@ -253,10 +297,11 @@ static void run_f32(const float* lon, const float* lat, const float* satz, long 
     }
 }
 
+// mode_counts[5..7]: quads on the FP32-pipe blend, flagged fine rows, pixels where it differs from blend_f32
 extern "C" int gtp_emul_cviirs_fast_f32(const float* lon, const float* lat, const float* satz, long n_scans,
                                         int fine_res, float* out_lon, float* out_lat, long* mode_counts)
 {
-    for (int k = 0; k < 5; ++k) mode_counts[k] = 0;
+    for (int k = 0; k < 8; ++k) mode_counts[k] = 0;
     if (fine_res == 250) run_f32<4>(lon, lat, satz, n_scans, out_lon, out_lat, mode_counts);
     else if (fine_res == 500) run_f32<2>(lon, lat, satz, n_scans, out_lon, out_lat, mode_counts);
     else return 1;

@@ -68,12 +68,13 @@ def emul():
         ns, p = lon.shape[0] // 10, 1000 // fine
         out_lon = np.full((ns * 10 * p, 1354 * p), np.nan, np.float32)
         out_lat = np.full_like(out_lon, np.nan)
-        modes = (ctypes.c_long * 6)()
+        modes = (ctypes.c_long * 8)()
         rc = lib.gtp_emul_cviirs_fast_f32(lon.ctypes.data_as(fp), lat.ctypes.data_as(fp), satz.ctypes.data_as(fp),
                                           ctypes.c_long(ns), fine, out_lon.ctypes.data_as(fp),
                                           out_lat.ctypes.data_as(fp), modes)
         assert rc == 0
-        return out_lon, out_lat, dict(zip(("slow", "low", "high", "both", "small", "wide"), modes))
+        return out_lon, out_lat, dict(zip(("slow", "low", "high", "both", "small", "eft_quads", "eft_flagged_rows",
+                                           "eft_mismatches"), modes))
     run.f32 = run_f32
 
     def run_simple_f32(lon, lat, fine):

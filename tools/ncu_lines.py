@@ -1,47 +1,52 @@
 #!/usr/bin/env python
-"""Per-source-line executed-instruction counts of the first kernel in an .ncu-rep (needs -lineinfo
-and --import-source on):  python tools/ncu_lines.py report.ncu-rep [units] [min_per_unit]
-`units` divides the counts (e.g. the number of quad-row warps) so the numbers read "per quad"."""
+"""Per-source-line executed-instruction and stall-sample shares of an .ncu-rep captured with
+--import-source on (kernels built with -lineinfo).
+
+    python tools/ncu_lines.py gpurun_out/prof.ncu-rep [min_percent]
+"""
 import collections
 import csv
-import re
+import io
 import subprocess
 import sys
 
-rep = sys.argv[1]
-units = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
-floor = float(sys.argv[3]) if len(sys.argv) > 3 else 3.0
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
-                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
-rows = list(csv.reader(out.splitlines()))
-cur, hdr, agg, samples = None, None, collections.OrderedDict(), {}
-ops = collections.Counter()
-for r in rows:
-    if r and r[0] == "File Path":
-        cur = r[1].split("/")[-1]; continue
-    if r and r[0] == "Function Name":
-        continue
-    if r and r[0] == "Line No":
-        hdr = r; iI = hdr.index("Instructions Executed"); iS = hdr.index("# Samples"); continue
-    if hdr is None or len(r) < len(hdr) - 2:
-        continue
-    try:
-        c = int(r[iI])
-    except ValueError:
-        continue
-    if r[2] == "-":
-        if c:
-            agg[(cur, int(r[0]))] = (c, int(r[iS] or 0), r[1][:100])
-    else:
-        op = re.sub(r"^\s*(@!?U?P\d+\s+)?", "", r[3]).split()
-        if op:
-            ops[op[0].split(".")[0]] += c
-tot = sum(v[0] for v in agg.values())
-tots = sum(v[1] for v in agg.values()) or 1
-print(f"total {tot / units:.1f} per unit")
-for (f, l), (c, smp, src) in agg.items():
-    if c / units >= floor:
-        print(f"{f:22s}:{l:4d} {c / units:7.1f} {100.0 * smp / tots:5.1f}%  {src}")
-print("== opcodes per unit")
-for op, c in ops.most_common(30):
-    print(f"   {op:10s} {c / units:7.1f}")
+
+def main(rep, min_pct=0.4):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda"],
+                         capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    cur, ln, src = None, None, ""
+    data = collections.defaultdict(lambda: collections.defaultdict(lambda: [0, 0, "", collections.Counter()]))
+    for r in rows:
+        if not r:
+            continue
+        if r[0] == "File Path":
+            cur = r[1].split("/")[-1]
+            continue
+        if r[0] in ("Function Name", "Kernel Name", "Line No"):
+            continue
+        if r[0].strip().isdigit():
+            ln, src = int(r[0]), r[1]
+            data[cur][ln][2] = src
+            continue
+        if r[0] == "" and len(r) > 7 and r[2].startswith("0x"):
+            d = data[cur][ln]
+            d[0] += int(r[7] or 0)
+            d[1] += int(r[6] or 0)
+            parts = r[3].split()
+            op = parts[1] if parts[0].startswith("@") and len(parts) > 1 else parts[0]
+            d[3][op.split(".")[0]] += int(r[7] or 0)
+    tot = sum(d[0] for v in data.values() for d in v.values())
+    smp = sum(d[1] for v in data.values() for d in v.values())
+    print(f"total warp instructions {tot}, stall samples {smp}")
+    for f, v in data.items():
+        ft = sum(d[0] for d in v.values())
+        print(f"== {f}: {100 * ft / tot:.1f} % of instructions, {100 * sum(d[1] for d in v.values()) / max(smp, 1):.1f} % of samples")
+        for ln, d in sorted(v.items()):
+            if d[0] > min_pct / 100 * tot:
+                ops = " ".join(f"{o}:{100 * n / tot:.1f}" for o, n in d[3].most_common(3))
+                print(f"  {ln:4d} {100 * d[0] / tot:5.2f}% inst {100 * d[1] / max(smp, 1):5.2f}% smp | {d[2].strip()[:90]} [{ops}]")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], float(sys.argv[2]) if len(sys.argv) > 2 else 0.4)
