@@ -75,31 +75,33 @@ __device__ __forceinline__ void quad_rows(const QuadF32& q, const float (&s_s)[P
 
 // The same rows with the blend on the FP32 pipe (gtp_fast_f32_math.cuh, "error-free transforms"): pixel
 // pairs in the two lanes of the packed float instructions, one component after the other; the displacement
-// from corner A goes to double for the back-transform (3 conversions per pixel instead of 23).  One
-// instance serves low- and high-latitude quads (the latitude series is chosen per quad: `high`); quads that
-// need the per-pixel latitude switch or the +-180 wrap are rare and stay with quad_rows.  Returns true when
-// any value of the quad sat within 2^-20 of a rounding boundary (one quad in ~1500): the caller then
-// evaluates the whole quad again with blend_f32 (the stores are idempotent).
-template <int P>
-__device__ __forceinline__ bool quad_rows_eft(const QuadF32& q, const QuadEft& qe, const float (&s_s)[P],
-                                              const double (&k1d)[P], float s_t0, int nrows, float* olon, float* olat)
+// from corner A goes to double for the back-transform (3 conversions per pixel instead of 23), which is
+// written step by step over the P pixels of the row so that their dependent FP64 chains interleave (one
+// pixel after the other they ran at the FP64 latency, 300 stall samples per instruction).  HIGH: the
+// latitude series in v = rho / rho_A - 1 (|z| >= 0.8 R) instead of w = dz / R; quads that need the
+// per-pixel latitude switch or the +-180 wrap are rare and stay with quad_rows.  Returns true when any
+// value of the quad sat within 2^-20 of a rounding boundary (one quad in ~1500): the caller then evaluates
+// the whole quad again with blend_f32 (the stores are idempotent).
+template <int P, bool HIGH>
+__device__ __forceinline__ bool quad_rows_eft(const QuadF32& q, const QuadEft& qe, bool extra, float s_t0, int nrows,
+                                              float* olon, float* olat)
 {
     constexpr long long kPitch = (long long)kW * P;
-    const bool high = (q.mode == kHigh);
     EdgeP2 top[3], bot[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         top[c].A = p2_dup(qe.A[c]); top[c].B = p2_dup(qe.B[c]); top[c].d = p2_dup(qe.dAB[c]);
         bot[c].A = p2_dup(qe.D[c]); bot[c].B = p2_dup(qe.C[c]); bot[c].d = p2_dup(qe.dDC[c]);
     }
-    // the latitude series of this quad: in w = dz / R (low) or in v = rho / rho_A - 1 (high)
-    const double c0 = high ? q.lat0_high : q.lat0_low;
-    const double c1 = high ? q.b1 : q.a1, c2 = high ? q.b2 : q.a2, c3 = high ? q.b3 : q.a3,
-                 c4 = high ? q.b4 : q.a4, c5 = high ? q.b5 : q.a5;
-    const double ced = (double)q.ce;
-    double a_col[P];                                    // s_s + s_s (1 - s_s) c_exp, the row-independent part of a_scan
+    const WideBT bt = wide_bt_setup<HIGH>(q);
+    // s_s + s_s (1 - s_s) c_exp (:344): s_s = (xoff + k) / P, exact products, one rounding
+    const double ced = (double)q.ce, xo = extra ? 1.0 : 0.0;
+    double a_col[P];
 #pragma unroll
-    for (int k = 0; k < P; ++k) a_col[k] = add_rn((double)s_s[k], mul_rn(k1d[k], ced));
+    for (int k = 0; k < P; ++k) {
+        const double ss = xo + (double)k / P;
+        a_col[k] = fma(ss * (1.0 - ss), ced, ss);
+    }
     const P2 m1 = p2_dup(-1.0f);
     P2 acc = p2_dup(0.0f);
     float s_t = s_t0;
@@ -107,10 +109,13 @@ __device__ __forceinline__ bool quad_rows_eft(const QuadF32& q, const QuadEft& q
     for (int m = 0; m < nrows; ++m) {
         const RowF32 rc = row_setup_f32(q, s_t);
         const P2 st2 = p2_dup(s_t), omt2 = p2_dup(fsub_rn(1.0f, s_t));      // exact: multiples of 1/8
-        float vlon[P], vlat[P];
+        float af[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) af[k] = (float)add_rn(a_col[k], rc.row_ca);
+        double dx[P], dy[P], dz[P];
 #pragma unroll
         for (int k = 0; k < P; k += 2) {
-            const P2 a2 = p2_make((float)add_rn(a_col[k], rc.row_ca), (float)add_rn(a_col[k + 1], rc.row_ca));
+            const P2 a2 = p2_make(af[k], af[k + 1]);
             const P2 na2 = p2_mul(a2, m1);
             F2 d[3];
 #pragma unroll
@@ -119,24 +124,12 @@ __device__ __forceinline__ bool quad_rows_eft(const QuadF32& q, const QuadEft& q
                 const P2 s2 = eft_edge(a2, na2, bot[c], acc);
                 d[c] = p2_get(eft_track(s1, s2, st2, omt2, top[c].A));
             }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const double dx = (double)(u ? d[0].y : d[0].x), dy = (double)(u ? d[1].y : d[1].x),
-                             dz = (double)(u ? d[2].y : d[2].x);
-                const double e = fma(q.ue0, dx, q.ue1 * dy);
-                const double h = fma(q.uh0, dx, q.uh1 * dy);
-                const double g = 1.0 + h;
-                double rcp = fma(h, h - 1.0, 1.0);
-                rcp = fma(rcp, fma(-g, rcp, 1.0), rcp);
-                const double t = e * rcp;
-                const double t2 = t * t;
-                const double at = fma(t * t2, fma(t2, 0.2, -kThird), t);
-                vlon[k + u] = (float)fma(at, kRad2Deg, q.lon0);
-                double x = dz * kInvEarthR;
-                if (high) x = fma(g, t2 * fma(t2, fma(t2, 0.0625, -0.125), 0.5), h);
-                vlat[k + u] = (float)fma(x, fma(x, fma(x, fma(x, fma(x, c5, c4), c3), c2), c1), c0);
-            }
+            dx[k] = (double)d[0].x; dx[k + 1] = (double)d[0].y;
+            dy[k] = (double)d[1].x; dy[k + 1] = (double)d[1].y;
+            dz[k] = (double)d[2].x; dz[k + 1] = (double)d[2].y;
         }
+        float vlon[P], vlat[P];
+        backtransform_f32_wide<P, HIGH>(bt, dx, dy, dz, vlon, vlat);
         store_px<P>(olon, vlon);
         store_px<P>(olat, vlat);
         olon += kPitch; olat += kPitch;
@@ -184,6 +177,8 @@ cviirs_fast_1km_f32_kernel(const float* __restrict__ lon, const float* __restric
         k1d[k] = mul_rn((double)s_s[k], add_rn(1.0, -(double)s_s[k]));
     }
 
+    const bool last_warp = (w == kWarpsPerScan - 1);      // holds tie column 1353 and its left neighbour
+    TieColF st;                                            // own tie column, walked down the scan
     TieGeoF topA;
     Vec3F topB;
     float top_ce = 0.0f, top_ca = 0.0f;
@@ -205,16 +200,36 @@ cviirs_fast_1km_f32_kernel(const float* __restrict__ lon, const float* __restric
             cp_async4(&stage[(r + 1) & 1][2][threadIdx.x], psatz);
             cp_async_commit();
         }
-        const TieGeoF own = tie_geo_f32(clon, clat);
+        if (r == 0) tie_col_first<true>(st, clon, clat, csatz);
+        else tie_col_next<true>(st, clon, clat, csatz);
+        const TieGeoF own = tie_col_geo(st);
+        const TieZenF zen = tie_col_zen(st);
         TieGeoF curA = own;
         Vec3F curB;
         curB.x = __shfl_down_sync(kFull, own.x, 1);
         curB.y = __shfl_down_sync(kFull, own.y, 1);
         curB.z = __shfl_down_sync(kFull, own.z, 1);
-        if (extra) {                 // A = tie column 1352 (recomputed by this one lane), B = own column 1353
-            const long long o = scan_base + (long long)r * kW + (kW - 2);
-            curA = tie_geo_f32(__ldg(lon + o), __ldg(lat + o));
-            curB.x = own.x; curB.y = own.y; curB.z = own.z;
+        TieColF zst = st;                // the state the quad's zenith chain starts from: its upper LEFT corner's
+        TieZenF za = zen;
+        float phi_b = __shfl_down_sync(kFull, zen.phi, 1);
+        float theta_b = __shfl_down_sync(kFull, zen.theta, 1);
+        if (last_warp) {
+            // the lane of tie column 1353 evaluates the quad of columns 1352 | 1353 right of its last tie
+            // column: A = the left neighbour's tie point (by shuffle), B = its own
+            TieGeoF lg; TieColF ls; TieZenF lz;
+            lg.x = __shfl_up_sync(kFull, own.x, 1); lg.y = __shfl_up_sync(kFull, own.y, 1); lg.z = __shfl_up_sync(kFull, own.z, 1);
+            ls.lam = __shfl_up_sync(kFull, st.lam, 1); ls.sl = __shfl_up_sync(kFull, st.sl, 1); ls.cl = __shfl_up_sync(kFull, st.cl, 1);
+            ls.phi = __shfl_up_sync(kFull, st.phi, 1); ls.sp = __shfl_up_sync(kFull, st.sp, 1); ls.cp = __shfl_up_sync(kFull, st.cp, 1);
+            ls.za = __shfl_up_sync(kFull, st.za, 1); ls.sz = __shfl_up_sync(kFull, st.sz, 1); ls.cz = __shfl_up_sync(kFull, st.cz, 1);
+            ls.pt = __shfl_up_sync(kFull, st.pt, 1); ls.spt = __shfl_up_sync(kFull, st.spt, 1); ls.cpt = __shfl_up_sync(kFull, st.cpt, 1);
+            lz.za = __shfl_up_sync(kFull, zen.za, 1); lz.phi = __shfl_up_sync(kFull, zen.phi, 1); lz.theta = __shfl_up_sync(kFull, zen.theta, 1);
+            if (extra) {
+                lg.lam = ls.lam; lg.phi = ls.phi; lg.sl = ls.sl; lg.cl = ls.cl; lg.sp = ls.sp; lg.cp = ls.cp;
+                curA = lg;
+                curB.x = own.x; curB.y = own.y; curB.z = own.z;
+                zst = ls; za = lz;
+                phi_b = zen.phi; theta_b = zen.theta;
+            }
         }
 
         if (r > 0 && active) {
@@ -230,7 +245,8 @@ cviirs_fast_1km_f32_kernel(const float* __restrict__ lon, const float* __restric
             bool faithful = !qe.ok || q.wrap || q.mode == kBoth;
             if (q.mode == kSlow) quad_rows<P, kSlow, false>(q, s_s, k1d, s_t0, nrows, olon, olat);
             else {
-                if (!faithful) faithful = quad_rows_eft<P>(q, qe, s_s, k1d, s_t0, nrows, olon, olat);
+                if (!faithful) faithful = (q.mode == kHigh) ? quad_rows_eft<P, true>(q, qe, extra, s_t0, nrows, olon, olat)
+                                                            : quad_rows_eft<P, false>(q, qe, extra, s_t0, nrows, olon, olat);
                 if (faithful) quad_rows<P, kBoth, true>(q, s_s, k1d, s_t0, nrows, olon, olat);
             }
             olon += (long long)nrows * kWf;
@@ -239,18 +255,8 @@ cviirs_fast_1km_f32_kernel(const float* __restrict__ lon, const float* __restric
         topA = curA;
         topB = curB;
 
-        if (r + 1 < kL) {
-            // expansion / alignment of the quad row below this tie row (upper corners only, :307-308)
-            const TieZenF zen = tie_zen_f32(csatz);
-            float phi_b = __shfl_down_sync(kFull, zen.phi, 1);
-            float theta_b = __shfl_down_sync(kFull, zen.theta, 1);
-            TieZenF za = zen;
-            if (extra) {
-                za = tie_zen_f32(__ldg(satz + scan_base + (long long)r * kW + (kW - 2)));
-                phi_b = zen.phi; theta_b = zen.theta;
-            }
-            quad_exp_ali_f32(za, phi_b, theta_b, 1, top_ce, top_ca);
-        }
+        // expansion / alignment of the quad row below this tie row (upper corners only, :307-308)
+        if (r + 1 < kL && active) quad_exp_ali_col(zst, za, phi_b, theta_b, 1, top_ce, top_ca);
     }
 }
 
@@ -347,6 +353,7 @@ simple_fast_1km_f32_kernel(const float* __restrict__ lon, const float* __restric
     float* olon = out_lon + scan * (long long)kN * kWf + (long long)quad_col * P + xoff;
     float* olat = out_lat + scan * (long long)kN * kWf + (long long)quad_col * P + xoff;
 
+    TieColF st;                    // own tie column, walked down the scan
     TieGeoF topA;
     Vec3F topB;
     __shared__ float stage[2][2][kThreads];
@@ -364,16 +371,21 @@ simple_fast_1km_f32_kernel(const float* __restrict__ lon, const float* __restric
             cp_async4(&stage[(r + 1) & 1][1][threadIdx.x], plat);
             cp_async_commit();
         }
-        const TieGeoF own = tie_geo_f32(clon, clat);
+        if (r == 0) tie_col_first<false>(st, clon, clat, 0.0f);
+        else tie_col_next<false>(st, clon, clat, 0.0f);
+        const TieGeoF own = tie_col_geo(st);
         TieGeoF curA = own;
         Vec3F curB;
         curB.x = __shfl_down_sync(kFull, own.x, 1);
         curB.y = __shfl_down_sync(kFull, own.y, 1);
         curB.z = __shfl_down_sync(kFull, own.z, 1);
-        if (extra) {                 // A = tie column 1352 (recomputed by this one lane), B = own column 1353
-            const long long o = scan_base + (long long)r * kW + (kW - 2);
-            curA = tie_geo_f32(__ldg(lon + o), __ldg(lat + o));
-            curB.x = own.x; curB.y = own.y; curB.z = own.z;
+        if (w == kWarpsPerScan - 1) {
+            // the lane of tie column 1353: A = the left neighbour's tie point (by shuffle), B = its own
+            TieGeoF lg;
+            lg.x = __shfl_up_sync(kFull, own.x, 1); lg.y = __shfl_up_sync(kFull, own.y, 1); lg.z = __shfl_up_sync(kFull, own.z, 1);
+            lg.lam = __shfl_up_sync(kFull, own.lam, 1); lg.sl = __shfl_up_sync(kFull, own.sl, 1); lg.cl = __shfl_up_sync(kFull, own.cl, 1);
+            lg.phi = __shfl_up_sync(kFull, own.phi, 1); lg.sp = __shfl_up_sync(kFull, own.sp, 1); lg.cp = __shfl_up_sync(kFull, own.cp, 1);
+            if (extra) { curA = lg; curB.x = own.x; curB.y = own.y; curB.z = own.z; }
         }
 
         if (r > 0 && active) {

@@ -110,6 +110,207 @@ GTP_FD void quad_exp_ali_f32(const TieZenF& a, float phi_b, float theta_b, int k
     c_ali = (float)(mul_rn(mul_rn(4.0, (double)e), szeta) / (double)den);
 }
 
+// ---- the same set-up, walked down a tie column ------------------------------------------------------
+// tie_geo_f32 / tie_zen_f32 / quad_exp_ali_f32 cost five sincos, two asin, a sqrt and six divisions per
+// tie row and thread (~500 FP64 instructions: as much as the 16 pixels of the quad).  The kernel walks a
+// tie column down the ten tie rows of a scan, and consecutive rows (and the neighbouring column) are
+// ~1e-4 rad apart, so every one of those functions is evaluated as a small step from a value the thread
+// already holds:
+//   * sin / cos of the float32 longitude, latitude and zenith angle: rotation of the previous row's by
+//     the (exact) difference of the float32 radians;
+//   * phi = asin(R sin(za) / (R + H)) (:74): Newton step on sin(phi) = x from the previous row's phi
+//     (asin_step: 4th-order start, one rotation, first-order finish; error < 1e-17 rad);
+//   * sin / cos of the quad's mean phi (:59): rotation of corner a's; zeta = asin((R + H) sin(phi) / R)
+//     (:82): asin_step from corner a's zenith angle, whose sine and cosine the thread has;
+//   * divisions by Markstein's two-FMA correction of x * (1 / y).
+// The float32 values the reference keeps (x, y, z, phi, theta, zeta, c_exp, c_ali) are roundings of
+// doubles that agree with glibc's to a few ulps, i.e. they differ from the reference's in ~1e-8 of the
+// tie points (the row-0 evaluation with sincos / asin has the same property).  Steps beyond the limits
+// below, NaN and out-of-range inputs restart from the full evaluation.
+GTP_DCONST(kStepMax, 4.0e-3);            // largest rotation / asin_step the series below are good for (rad)
+GTP_DCONST(kRcpRkH, 1.0 / (GTP_RK + GTP_H));
+GTP_DCONST(kRcpRk, 1.0 / GTP_RK);
+
+// (sin, cos)(x + d) from (sin, cos)(x), |d| <= 5e-3: sin d to d^5 (next 1.5e-20), cos d to d^6 (next 1e-23)
+GTP_FD void rotate_step(double& sn, double& cs, double d)
+{
+    const double d2 = d * d;
+    const double sd = fma(d * d2, fma(d2, k1_120, -kSixth), d);
+    const double cm = d2 * fma(d2, fma(d2, -k1_720, k1_24), -0.5);
+    const double s1 = fma(sn, cm, fma(cs, sd, sn));
+    const double c1 = fma(cs, cm, fma(-sn, sd, cs));
+    sn = s1; cs = c1;
+}
+
+// n / c for a constant c with rc = RN(1 / c): q = n rc corrected by its own residual (correctly rounded
+// except for a handful of n per binade)
+GTP_FD double div_const(double n, double c, double rc)
+{
+    const double q = n * rc;
+    return fma(fma(-q, c, n), rc, q);
+}
+
+// The angle with sine x from a nearby angle of sine s0 and cosine c0, |x - s0| <= kStepMax c0: returns the
+// step and replaces (s0, c0) by (x, its cosine).  With u = (x - s0) / c0, w = tan:
+//   asin(x) - asin(s0) = u + w u^2 / 2 + (1 + 3 w^2) u^3 / 6 + w (9 + 15 w^2) u^4 / 24 + O(u^5)
+// then one Newton step on the rotated sine with d(asin) / dx = (1 + w d1) / c0 (relative error d1^2).
+GTP_FD double asin_step(double x, double& s0, double& c0)
+{
+    const double ic = fast_rcp(c0);
+    const double u = (x - s0) * ic, w = s0 * ic, w2 = w * w;
+    const double t3 = fma(w2, 0.5, kSixth);
+    const double t4 = w * fma(w2, 0.625, 0.375);
+    const double d1 = fma(u * u, fma(u, fma(u, t4, t3), 0.5 * w), u);
+    double s1 = s0, c1 = c0;
+    rotate_step(s1, c1, d1);
+    const double d2 = (x - s1) * fma(w * d1, ic, ic);
+    s0 = x;
+    c0 = fma(-s1, d2, c1);
+    return d1 + d2;
+}
+
+GTP_FD double deg2rad_f32(float v) { return (double)(float)mul_rn((double)v, kDeg2Rad); }     // :76-77
+
+struct TieColF {
+    double lam, sl, cl;                 // float32 longitude in radians (as a double), sine, cosine
+    double phi, sp, cp;                 // latitude
+    double za, sz, cz;                  // zenith angle
+    double pt, spt, cpt;                // phi of :74 before its rounding to float32, sine, cosine
+};
+
+template <bool WITH_ZEN>
+GTP_FD void tie_col_first(TieColF& t, float lon, float lat, float satz)
+{
+    t.lam = deg2rad_f32(lon); t.phi = deg2rad_f32(lat);
+    fast_sincos(t.lam, t.sl, t.cl);
+    fast_sincos(t.phi, t.sp, t.cp);
+    if (WITH_ZEN) {
+        t.za = deg2rad_f32(satz);
+        fast_sincos(t.za, t.sz, t.cz);
+        t.spt = mul_rn(GTP_RK, t.sz) / (GTP_RK + GTP_H);
+        t.pt = asin(t.spt);
+        t.cpt = sqrt(fma(-t.spt, t.spt, 1.0));
+    }
+}
+
+template <bool WITH_ZEN>
+GTP_FD_COLD TieColF tie_col_first_cold(float lon, float lat, float satz)
+{
+    TieColF t;
+    t.za = t.sz = t.cz = t.pt = t.spt = t.cpt = 0.0;
+    tie_col_first<WITH_ZEN>(t, lon, lat, satz);
+    return t;
+}
+
+template <bool WITH_ZEN>
+GTP_FD void tie_col_take(TieColF& t, const TieColF& f)
+{
+    t.lam = f.lam; t.sl = f.sl; t.cl = f.cl; t.phi = f.phi; t.sp = f.sp; t.cp = f.cp;
+    if (WITH_ZEN) { t.za = f.za; t.sz = f.sz; t.cz = f.cz; t.pt = f.pt; t.spt = f.spt; t.cpt = f.cpt; }
+}
+
+// the tie point below t in the same tie column
+template <bool WITH_ZEN>
+GTP_FD void tie_col_next(TieColF& t, float lon, float lat, float satz)
+{
+    const double lam = deg2rad_f32(lon), phi = deg2rad_f32(lat), za = WITH_ZEN ? deg2rad_f32(satz) : 0.0;
+    const double dl = lam - t.lam, dp = phi - t.phi, dz = WITH_ZEN ? za - t.za : 0.0;
+    bool ok = (fabs(dl) <= kStepMax) && (fabs(dp) <= kStepMax) && (fabs(dz) <= kStepMax) && (fabs(lam) <= 8.0) && (fabs(phi) <= 8.0);
+    double sz = t.sz, cz = t.cz, x = 0.0;
+    if (WITH_ZEN) {
+        rotate_step(sz, cz, dz);
+        x = div_const(mul_rn(GTP_RK, sz), GTP_RK + GTP_H, kRcpRkH);
+        ok = ok && (fabs(x - t.spt) <= kStepMax * t.cpt) && (za >= 0.0) && (za <= 1.3);
+    }
+    if (ok) {
+        t.lam = lam; t.phi = phi;
+        rotate_step(t.sl, t.cl, dl);
+        rotate_step(t.sp, t.cp, dp);
+        if (WITH_ZEN) {
+            t.za = za; t.sz = sz; t.cz = cz;
+            const double step = asin_step(x, t.spt, t.cpt);
+            t.pt += step;
+        }
+    } else {
+        const TieColF f = tie_col_first_cold<WITH_ZEN>(lon, lat, satz);
+        tie_col_take<WITH_ZEN>(t, f);
+    }
+}
+
+// lonlat2xyz rounded to float (_modis_utils.pyx:38-40)
+GTP_FD Vec3F tie_col_xyz(const TieColF& t)
+{
+    Vec3F v;
+    const double rc = mul_rn(kEarthR, t.cp);
+    v.x = (float)mul_rn(rc, t.cl);
+    v.y = (float)mul_rn(rc, t.sl);
+    v.z = (float)mul_rn(kEarthR, t.sp);
+    return v;
+}
+
+GTP_FD TieGeoF tie_col_geo(const TieColF& t)
+{
+    TieGeoF g;
+    const Vec3F v = tie_col_xyz(t);
+    g.x = v.x; g.y = v.y; g.z = v.z;
+    g.lam = t.lam; g.phi = t.phi; g.sl = t.sl; g.cl = t.cl; g.sp = t.sp; g.cp = t.cp;
+    return g;
+}
+
+GTP_FD TieZenF tie_col_zen(const TieColF& t)
+{
+    TieZenF z;
+    z.za = (float)t.za;                       // exact: t.za is a float32 value
+    z.phi = (float)t.pt;                      // :74
+    z.theta = fsub_rn(z.za, z.phi);           // :78
+    return z;
+}
+
+struct ExpAliF { float ce, ca; };
+GTP_FD_COLD ExpAliF quad_exp_ali_f32_cold(float za, float phi_a, float theta_a, float phi_b, float theta_b, int km)
+{
+    TieZenF a; a.za = za; a.phi = phi_a; a.theta = theta_a;
+    ExpAliF r;
+    quad_exp_ali_f32(a, phi_b, theta_b, km, r.ce, r.ca);
+    return r;
+}
+
+// _compute_expansion_alignment (:41-70) for the quad whose upper left corner is the tie point of state t
+// (za = (float)t.za etc. in a) and whose upper right corner has phi_b, theta_b
+GTP_FD void quad_exp_ali_col(const TieColF& t, const TieZenF& a, float phi_b, float theta_b, int km, float& c_exp, float& c_ali)
+{
+    const float phi = fmul_rn(0.5f, fadd_rn(a.phi, phi_b));            // (float)((double)(phi_a + phi_b) / 2.0)
+    const double h = (double)phi - t.pt;
+    double sphi = t.spt, cphi = t.cpt;
+    rotate_step(sphi, cphi, h);
+    const double x = div_const(mul_rn(GTP_RK + GTP_H, sphi), GTP_RK, kRcpRk);
+    double sz = t.sz, cz = t.cz;
+    const bool ok = (fabs(h) <= kStepMax) && (fabs(x - sz) <= kStepMax * cz) && (fabs(phi) >= 1e-30f);
+    const double dzeta = asin_step(x, sz, cz);
+    const float zeta = (float)(t.za + dzeta);
+    const double eps = ((double)zeta - t.za) - dzeta;                   // the rounding of zeta
+    const double szeta = fma(eps, fma(-0.5 * eps, sz, cz), sz);
+    const double czeta = fma(eps, fma(-0.5 * eps, cz, -sz), cz);
+    const float theta = fsub_rn(zeta, phi);
+    const float den = (a.theta == theta_b) ? fmul_rn(a.theta, 2.0f) : fsub_rn(a.theta, theta_b);
+    const double dend = (double)den, rd = fast_rcp(dend);
+    const double num = add_rn((double)fadd_rn(a.theta, theta_b) * 0.5, -(double)theta);
+    double q = num * rd;
+    q = fma(fma(-q, dend, num), rd, q);
+    const float ce = (float)mul_rn(4.0, q);
+    const float sin_beta_2 = (float)((double)km / (2.0 * GTP_H));
+    const float d = (float)mul_rn(add_rn(mul_rn((GTP_RK + GTP_H) / GTP_RK, cphi), -czeta), (double)sin_beta_2);
+    const float dd = fmul_rn(d, d);
+    const float e = (float)add_rn(czeta, -fast_sqrt(add_rn(mul_rn(czeta, czeta), -(double)dd)));
+    const double n2 = mul_rn(mul_rn(4.0, (double)e), szeta);
+    double q2 = n2 * rd;
+    q2 = fma(fma(-q2, dend, n2), rd, q2);
+    const float ca = (float)q2;
+    // the step limits, a zero / tiny / non-finite denominator and NaN: the reference's own operations
+    if (ok && (fabsf(ce) <= 1e30f) && (fabsf(ca) <= 1e30f) && (fabsf(den) >= 1e-30f)) { c_exp = ce; c_ali = ca; }
+    else { const ExpAliF r = quad_exp_ali_f32_cold(a.za, a.phi, a.theta, phi_b, theta_b, km); c_exp = r.ce; c_ali = r.ca; }
+}
+
 // Everything the pixels of one quad need.
 struct QuadF32 {
     int mode;
@@ -121,7 +322,7 @@ struct QuadF32 {
     double lon0;                        // longitude of A', degrees
     double lat0_low, lat0_high;         // latitude of A' by the low / high latitude formula, degrees
     double s0;                          // z_A' / R
-    double a1, a2, a3, a4, a5;          // series of asin((z_A' + dz)/R) around z_A'/R, degrees
+    double a1, a2, a3, a4, a5;          // series of asin((z_A' + dz)/R) around z_A'/R in dz (metres), degrees
     double b1, b2, b3, b4, b5;          // series of sign(z) acos(rho/R) around rho_A'/R, degrees
 };
 
@@ -147,28 +348,31 @@ GTP_FD QuadF32 quad_setup_f32(const TieGeoF& A, const Vec3F& B, const Vec3F& C, 
     q.C[0] = C.x; q.C[1] = C.y; q.C[2] = C.z;
 
     // local frame at A' = the float32-rounded corner A (what the reference back-transforms)
-    const double rho = fast_sqrt(fma(q.A[0], q.A[0], q.A[1] * q.A[1]));
-    const double inv_rho = fast_rcp(rho);
+    double inv_rho;
+    const double rho = fast_sqrt_rsqrt(fma(q.A[0], q.A[0], q.A[1] * q.A[1]), inv_rho);
     const double cl = q.A[0] * inv_rho, sl = q.A[1] * inv_rho;
     q.ue0 = -sl * inv_rho; q.ue1 = cl * inv_rho;
-    q.uh0 = cl * inv_rho; q.uh1 = sl * inv_rho;
+    q.uh0 = q.ue1; q.uh1 = -q.ue0;
     // lon(A') = lambda + asin(sin(lon(A') - lambda)): A' is within half a float32 ulp of the exact point
     q.lon0 = (A.lam + fma(A.cl, sl, -(A.sl * cl))) * kRad2Deg;
     q.s0 = q.A[2] * kInvEarthR;
 
-    // displacement bounds over the quad (same role as in gtp_fast_math.cuh)
-    const double Px = (double)B.x - q.A[0], Py = (double)B.y - q.A[1], Pz = (double)B.z - q.A[2];
-    const double Qx = q.D[0] - q.A[0], Qy = q.D[1] - q.A[1], Qz = q.D[2] - q.A[2];
-    const double Sx = ((double)C.x - q.D[0]) - Px, Sy = ((double)C.y - q.D[1]) - Py, Sz = ((double)C.z - q.D[2]) - Pz;
-    const double Pe = fma(q.ue0, Px, q.ue1 * Py), Ph = fma(q.uh0, Px, q.uh1 * Py);
-    const double Qe = fma(q.ue0, Qx, q.ue1 * Qy), Qh = fma(q.uh0, Qx, q.uh1 * Qy);
-    const double Se = fma(q.ue0, Sx, q.ue1 * Sy), Sh = fma(q.uh0, Sx, q.uh1 * Sy);
+    // displacement bounds over the quad (same role as in gtp_fast_math.cuh), on the FP32 pipe: they only
+    // feed comparisons with a few per cent of slack (kBoundSlack)
+    const float Px = fsub_rn(B.x, A.x), Py = fsub_rn(B.y, A.y), Pz = fsub_rn(B.z, A.z);
+    const float Qx = fsub_rn(D.x, A.x), Qy = fsub_rn(D.y, A.y), Qz = fsub_rn(D.z, A.z);
+    const float Sx = fsub_rn(fsub_rn(C.x, D.x), Px), Sy = fsub_rn(fsub_rn(C.y, D.y), Py), Sz = fsub_rn(fsub_rn(C.z, D.z), Pz);
+    const float e0 = (float)q.ue0, e1 = (float)q.ue1;
+    const float Pe = fmaf(e0, Px, e1 * Py), Ph = fmaf(e1, Px, -e0 * Py);
+    const float Qe = fmaf(e0, Qx, e1 * Qy), Qh = fmaf(e1, Qx, -e0 * Qy);
+    const float Se = fmaf(e0, Sx, e1 * Sy), Sh = fmaf(e1, Sx, -e0 * Sy);
     // 2 m of slack for the float32 roundings of the fine xyz themselves
-    const double horiz = kABound * (absd(Pe) + absd(Ph)) + kTBound * (absd(Qe) + absd(Qh))
-                         + kATBound * (absd(Se) + absd(Sh)) + 2.0 * inv_rho;
-    const double wmax = (kABound * absd(Pz) + kTBound * absd(Qz) + kATBound * absd(Sz) + 2.0) * kInvEarthR;
+    const float kA = (float)kABound, kT = (float)kTBound, kAT = (float)kATBound;
+    const double horiz = (double)(1.0001f * (kA * (fabsf(Pe) + fabsf(Ph)) + kT * (fabsf(Qe) + fabsf(Qh))
+                                             + kAT * (fabsf(Se) + fabsf(Sh)) + 2.0f * fabsf(e0) + 2.0f * fabsf(e1)));
+    const double wmax = (double)(1.0001f * (kA * fabsf(Pz) + kT * fabsf(Qz) + kAT * fabsf(Sz) + 2.0f)) * kInvEarthR;
     const bool ok = (horiz <= max_horiz) && (wmax <= max_w)
-                    && (absd((double)ce) <= 1.0) && (absd((double)ca) <= 0.5) && (A.cp > 1e-6);
+                    && (fabsf(ce) <= 1.0f) && (fabsf(ca) <= 0.5f) && (A.cp > 1e-6);
     if (!ok) { q.mode = kSlow; return q; }
 
     const double zr_lo = q.s0 - wmax, zr_hi = q.s0 + wmax;
@@ -181,22 +385,26 @@ GTP_FD QuadF32 quad_setup_f32(const TieGeoF& A, const Vec3F& B, const Vec3F& C, 
     if (q.mode & kLow) {
         // asin around s0 = z_A'/R with c0 = sqrt(1 - s0^2); asin(s0) = phi + asin(s0 cos phi - c0 sin phi)
         const double s = q.s0, s2 = s * s;
-        const double c0 = fast_sqrt(fma(-s, s, 1.0));
-        const double inv_c = fast_rcp(c0), u = inv_c * inv_c;
+        double inv_c;
+        const double c0 = fast_sqrt_rsqrt(fma(-s, s, 1.0), inv_c);
+        const double u = inv_c * inv_c;
         q.lat0_low = (A.phi + fma(s, A.cp, -(c0 * A.sp))) * kRad2Deg;
-        double m = inv_c * kRad2Deg;
+        // coefficients per power of dz (metres): 1 / R^k folded in
+        const double ur = u * kInvEarthR;
+        double m = inv_c * (kRad2Deg * kInvEarthR);
         q.a1 = m;
-        m *= u; q.a2 = 0.5 * s * m;
-        m *= u; q.a3 = fma(2.0, s2, 1.0) * kSixth * m;
-        m *= u; q.a4 = s * fma(2.0, s2, 3.0) * 0.125 * m;
-        m *= u; q.a5 = fma(s2, fma(8.0, s2, 24.0), 3.0) * k1_40 * m;
+        m *= ur; q.a2 = 0.5 * s * m;
+        m *= ur; q.a3 = fma(2.0, s2, 1.0) * kSixth * m;
+        m *= ur; q.a4 = s * fma(2.0, s2, 3.0) * 0.125 * m;
+        m *= ur; q.a5 = fma(s2, fma(8.0, s2, 24.0), 3.0) * k1_40 * m;
     }
     if (q.mode & kHigh) {
         // sign(z) acos(rho/R) around c = rho_A'/R with s' = sqrt(1 - c^2):
         // acos(c) = |phi| - asin(|sin phi| c - cos phi s')
         const double c = rho * kInvEarthR, c2 = c * c;
-        const double sa = fast_sqrt(fma(-c, c, 1.0));
-        const double inv_s = fast_rcp(sa), u = inv_s * inv_s;
+        double inv_s;
+        const double sa = fast_sqrt_rsqrt(fma(-c, c, 1.0), inv_s);
+        const double u = inv_s * inv_s;
         const double sign = (q.A[2] < 0.0) ? -1.0 : 1.0;
         q.lat0_high = sign * (absd(A.phi) - fma(absd(A.sp), c, -(A.cp * sa))) * kRad2Deg;
         double m = inv_s * c * (-sign * kRad2Deg);
@@ -351,7 +559,7 @@ GTP_FD void backtransform_f32_d(const QuadF32& q, double dx, double dy, double d
 {
     const double e = fma(q.ue0, dx, q.ue1 * dy);
     const double h = fma(q.uh0, dx, q.uh1 * dy);
-    const double w = dz * kInvEarthR;
+    const double w = dz;
     const double g = 1.0 + h;
     double rcp = fma(h, h - 1.0, 1.0);
     rcp = fma(rcp, fma(-g, rcp, 1.0), rcp);
@@ -386,6 +594,87 @@ template <int MODE, bool WRAP>
 GTP_FD void backtransform_f32(const QuadF32& q, const double (&v)[3], float& lon, float& lat)
 {
     backtransform_f32_d<MODE, WRAP>(q, v[0] - q.A[0], v[1] - q.A[1], v[2] - q.A[2], v[2], lon, lat);
+}
+
+// The same back-transform for the P pixels of a fine row side by side (their dependent FP64 chains
+// interleave), from the displacements (dx, dy, dz) = float32 xyz - corner A.  One latitude series per
+// quad: HIGH in v = rho / rho_A - 1 (|z| >= 0.8 R), else in dz.
+struct WideBT { double ue0, ue1, lon0, c0, c1, c2, c3, c4, c5; };
+
+template <bool HIGH>
+GTP_FD WideBT wide_bt_setup(const QuadF32& q)
+{
+    WideBT b;
+    b.ue0 = q.ue0; b.ue1 = q.ue1; b.lon0 = q.lon0;
+    b.c0 = HIGH ? q.lat0_high : q.lat0_low;
+    b.c1 = HIGH ? q.b1 : q.a1; b.c2 = HIGH ? q.b2 : q.a2; b.c3 = HIGH ? q.b3 : q.a3;
+    b.c4 = HIGH ? q.b4 : q.a4; b.c5 = HIGH ? q.b5 : q.a5;
+    return b;
+}
+
+template <int P, bool HIGH>
+GTP_FD void backtransform_f32_wide(const WideBT& b, const double (&dx)[P], const double (&dy)[P], const double (&dz)[P],
+                                   float (&vlon)[P], float (&vlat)[P])
+{
+    // xyz2lonlat, anchor-relative (backtransform_f32_d), the P pixels side by side
+    double e[P], h[P], g[P], rcp[P], t[P], t2[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) e[k] = b.ue1 * dy[k];
+#pragma unroll
+    for (int k = 0; k < P; ++k) h[k] = -b.ue0 * dy[k];
+#pragma unroll
+    for (int k = 0; k < P; ++k) e[k] = fma(b.ue0, dx[k], e[k]);
+#pragma unroll
+    for (int k = 0; k < P; ++k) h[k] = fma(b.ue1, dx[k], h[k]);
+    // 1 / (1 + h) = (1 - h) (1 + h^2) (1 + h^4) (1 - h^8)^-1, |h| <= 0.01: three levels deep
+#pragma unroll
+    for (int k = 0; k < P; ++k) rcp[k] = 1.0 - h[k];
+#pragma unroll
+    for (int k = 0; k < P; ++k) t2[k] = h[k] * h[k];
+#pragma unroll
+    for (int k = 0; k < P; ++k) g[k] = 1.0 + h[k];
+#pragma unroll
+    for (int k = 0; k < P; ++k) rcp[k] = fma(t2[k], rcp[k], rcp[k]);
+#pragma unroll
+    for (int k = 0; k < P; ++k) t2[k] = t2[k] * t2[k];
+#pragma unroll
+    for (int k = 0; k < P; ++k) rcp[k] = fma(t2[k], rcp[k], rcp[k]);
+#pragma unroll
+    for (int k = 0; k < P; ++k) t[k] = e[k] * rcp[k];
+#pragma unroll
+    for (int k = 0; k < P; ++k) t2[k] = t[k] * t[k];
+#pragma unroll
+    for (int k = 0; k < P; ++k) e[k] = fma(t2[k], 0.2, -kThird);
+#pragma unroll
+    for (int k = 0; k < P; ++k) rcp[k] = t[k] * t2[k];
+#pragma unroll
+    for (int k = 0; k < P; ++k) t[k] = fma(rcp[k], e[k], t[k]);
+#pragma unroll
+    for (int k = 0; k < P; ++k) vlon[k] = (float)fma(t[k], kRad2Deg, b.lon0);
+    double x[P], pl[P];
+    if (HIGH) {
+#pragma unroll
+        for (int k = 0; k < P; ++k) x[k] = fma(t2[k], 0.0625, -0.125);
+#pragma unroll
+        for (int k = 0; k < P; ++k) x[k] = fma(t2[k], x[k], 0.5);
+#pragma unroll
+        for (int k = 0; k < P; ++k) x[k] = t2[k] * x[k];
+#pragma unroll
+        for (int k = 0; k < P; ++k) x[k] = fma(g[k], x[k], h[k]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < P; ++k) x[k] = dz[k];
+    }
+#pragma unroll
+    for (int k = 0; k < P; ++k) pl[k] = fma(x[k], b.c5, b.c4);
+#pragma unroll
+    for (int k = 0; k < P; ++k) pl[k] = fma(x[k], pl[k], b.c3);
+#pragma unroll
+    for (int k = 0; k < P; ++k) pl[k] = fma(x[k], pl[k], b.c2);
+#pragma unroll
+    for (int k = 0; k < P; ++k) pl[k] = fma(x[k], pl[k], b.c1);
+#pragma unroll
+    for (int k = 0; k < P; ++k) vlat[k] = (float)fma(x[k], pl[k], b.c0);
 }
 
 struct LonLatF { float lon, lat; };

@@ -207,25 +207,87 @@ extern "C" int gtp_emul_cviirs_fast5_f64(const double* lon, const double* lat, c
 }
 
 // ---- float32 fast path (gtp_fast_f32_math.cuh) -------------------------------------------------
+// one quad with the blend on the FP32 pipe, exactly as quad_rows_eft of gtp_fast_f32.cu does it
+template <int P, bool HIGH>
+static bool eft_quad(const gtpfast32::QuadF32& q, const gtpfast32::QuadEft& qe, bool extra, float s_t, int j0, int j1,
+                     float* out_lon, float* out_lat, long base, long Wf, long* mode_counts)
+{
+    using namespace gtpfast32;
+    EdgeP2 top[3], bot[3];
+    for (int c = 0; c < 3; ++c) {
+        top[c].A = p2_dup(qe.A[c]); top[c].B = p2_dup(qe.B[c]); top[c].d = p2_dup(qe.dAB[c]);
+        bot[c].A = p2_dup(qe.D[c]); bot[c].B = p2_dup(qe.C[c]); bot[c].d = p2_dup(qe.dDC[c]);
+    }
+    const WideBT bt = wide_bt_setup<HIGH>(q);
+    const double ced = (double)q.ce, xo = extra ? 1.0 : 0.0;
+    double a_col[P];
+    for (int k = 0; k < P; ++k) { const double ss = xo + (double)k / P; a_col[k] = fma(ss * (1.0 - ss), ced, ss); }
+    const P2 m1 = p2_dup(-1.0f);
+    P2 acc = p2_dup(0.0f);
+    for (int j = j0; j < j1; ++j, s_t += 1.0f / P) {
+        const RowF32 rc = row_setup_f32(q, s_t);
+        const P2 st2 = p2_dup(s_t), omt2 = p2_dup(fsub_rn(1.0f, s_t));
+        double dx[P], dy[P], dz[P];
+        for (int k = 0; k < P; k += 2) {
+            const P2 a2 = p2_make((float)add_rn(a_col[k], rc.row_ca), (float)add_rn(a_col[k + 1], rc.row_ca));
+            const P2 na2 = p2_mul(a2, m1);
+            F2 d[3];
+            const P2 acc_before = acc;
+            for (int c = 0; c < 3; ++c) {
+                const P2 s1 = eft_edge(a2, na2, top[c], acc), s2 = eft_edge(a2, na2, bot[c], acc);
+                d[c] = p2_get(eft_track(s1, s2, st2, omt2, top[c].A));
+            }
+            dx[k] = (double)d[0].x; dx[k + 1] = (double)d[0].y;
+            dy[k] = (double)d[1].x; dy[k + 1] = (double)d[1].y;
+            dz[k] = (double)d[2].x; dz[k + 1] = (double)d[2].y;
+            // cross-check against the reference's arithmetic wherever nothing was flagged in this pair
+            const F2 f0 = p2_get(acc_before), f1 = p2_get(acc);
+            if (f0.x == f1.x && f0.y == f1.y) {
+                for (int u = 0; u < 2; ++u) {
+                    const float s_s = (float)((extra ? P : 0) + k + u) / (float)P;
+                    double v[3];
+                    blend_f32(q, rc, s_s, mul_rn((double)s_s, add_rn(1.0, -(double)s_s)), v);
+                    if (v[0] - q.A[0] != dx[k + u] || v[1] - q.A[1] != dy[k + u] || v[2] - q.A[2] != dz[k + u]) mode_counts[7]++;
+                }
+            }
+        }
+        float vlon[P], vlat[P];
+        backtransform_f32_wide<P, HIGH>(bt, dx, dy, dz, vlon, vlat);
+        for (int k = 0; k < P; ++k) { out_lon[base + j * Wf + k] = vlon[k]; out_lat[base + j * Wf + k] = vlat[k]; }
+    }
+    const F2 fl = p2_get(acc);
+    return !(fl.x == 0.0f) || !(fl.y == 0.0f);
+}
+
 template <int P>
 static void run_f32(const float* lon, const float* lat, const float* satz, long n_scans,
                     float* out_lon, float* out_lat, long* mode_counts)
 {
     using namespace gtpfast32;
     const int W = 1354, L = 10, Wf = W * P, N = L * P, H = P / 2;
+    std::vector<TieColF> col((size_t)L * W);
     for (long s = 0; s < n_scans; ++s) {
+        // like the kernel: every tie column is walked down the ten tie rows (row 0: full evaluation)
+        for (int c = 0; c < W; ++c) {
+            TieColF t;
+            for (int r = 0; r < L; ++r) {
+                const long o = (s * L + r) * W + c;
+                if (r == 0) tie_col_first<true>(t, lon[o], lat[o], satz[o]);
+                else tie_col_next<true>(t, lon[o], lat[o], satz[o]);
+                col[(size_t)r * W + c] = t;
+            }
+        }
         for (int qc = 0; qc <= W - 1; ++qc) {
             const bool extra = (qc == W - 1);
             const int ca = extra ? W - 2 : qc, cb = ca + 1, xoff = extra ? P : 0;
             for (int qr = 0; qr < L - 1; ++qr) {
-                auto geo = [&](int r, int c) { long o = (s * L + r) * W + c; return tie_geo_f32(lon[o], lat[o]); };
-                auto zen = [&](int r, int c) { long o = (s * L + r) * W + c; return tie_zen_f32(satz[o]); };
+                auto geo = [&](int r, int c) { return tie_col_geo(col[(size_t)r * W + c]); };
                 auto v3 = [](const TieGeoF& t) { Vec3F v; v.x = t.x; v.y = t.y; v.z = t.z; return v; };
                 const TieGeoF A = geo(qr, ca);
                 const Vec3F B = v3(geo(qr, cb)), D = v3(geo(qr + 1, ca)), C = v3(geo(qr + 1, cb));
-                const TieZenF za = zen(qr, ca), zb = zen(qr, cb);
+                const TieZenF za = tie_col_zen(col[(size_t)qr * W + ca]), zb = tie_col_zen(col[(size_t)qr * W + cb]);
                 float ce, cal;
-                quad_exp_ali_f32(za, zb.phi, zb.theta, 1, ce, cal);
+                quad_exp_ali_col(col[(size_t)qr * W + ca], za, zb.phi, zb.theta, 1, ce, cal);
                 const QuadF32 q = quad_setup_f32(A, B, C, D, ce, cal);
                 mode_counts[q.mode]++;
                 const int j0 = (qr == 0) ? 0 : qr * P + H;
@@ -233,61 +295,26 @@ static void run_f32(const float* lon, const float* lat, const float* satz, long 
                 float s_t = ((qr == 0) ? (0.5f - H) : 0.5f) / P;
                 Vec3F Av; Av.x = A.x; Av.y = A.y; Av.z = A.z;
                 const QuadEft qe = quad_eft_setup(Av, B, C, D, extra ? 16.0f : 8.0f);
-                const bool use_eft = qe.ok && q.mode != kSlow;
-                if (use_eft) mode_counts[5]++;
+                // like the kernel: the FP32-pipe blend for plain low / high latitude quads, and the whole quad
+                // again with blend_f32 when any of its values sat on a rounding boundary
+                bool faithful = !qe.ok || q.wrap || q.mode == kBoth || q.mode == kSlow;
+                if (!faithful) {
+                    mode_counts[5]++;
+                    faithful = (q.mode == kHigh) ? eft_quad<P, true>(q, qe, extra, s_t, j0, j1, out_lon, out_lat, (s * N) * (long)Wf + (long)ca * P + xoff, Wf, mode_counts)
+                                                 : eft_quad<P, false>(q, qe, extra, s_t, j0, j1, out_lon, out_lat, (s * N) * (long)Wf + (long)ca * P + xoff, Wf, mode_counts);
+                    if (faithful) mode_counts[6]++;
+                }
+                if (!faithful) continue;
                 for (int j = j0; j < j1; ++j, s_t += 1.0f / P) {
                     const RowF32 rc = row_setup_f32(q, s_t);
-                    // the kernel's FP32-pipe blend: pairs of pixels, three components each
-                    double dv[P][3]; float vz[P]; bool flagged = false;
-                    if (use_eft) {
-                        const P2 st2 = p2_dup(s_t), omt2 = p2_dup((float)rc.omt);
-                        for (int k = 0; k < P; k += 2) {
-                            float af[2];
-                            for (int u = 0; u < 2; ++u) {
-                                const float s_s = (float)(xoff + k + u) / (float)P;
-                                const double k1d = mul_rn((double)s_s, add_rn(1.0, -(double)s_s));
-                                af[u] = (float)add_rn(add_rn((double)s_s, mul_rn(k1d, (double)q.ce)), rc.row_ca);
-                            }
-                            const P2 a2 = p2_make(af[0], af[1]), na2 = p2_make(-af[0], -af[1]);
-                            P2 acc = p2_dup(0.0f);
-                            for (int c = 0; c < 3; ++c) {
-                                EdgeP2 top, bot;
-                                top.A = p2_dup(qe.A[c]); top.B = p2_dup(qe.B[c]); top.d = p2_dup(qe.dAB[c]);
-                                bot.A = p2_dup(qe.D[c]); bot.B = p2_dup(qe.C[c]); bot.d = p2_dup(qe.dDC[c]);
-                                const P2 s1 = eft_edge(a2, na2, top, acc), s2 = eft_edge(a2, na2, bot, acc);
-                                const F2 d = p2_get(eft_track(s1, s2, st2, omt2, top.A));
-                                dv[k][c] = (double)d.x; dv[k + 1][c] = (double)d.y;
-                                if (c == 2) { vz[k] = fadd_rn(d.x, qe.A[2]); vz[k + 1] = fadd_rn(d.y, qe.A[2]); }
-                            }
-                            const F2 fl = p2_get(acc);
-                            if (!(fl.x == 0.0f) || !(fl.y == 0.0f)) flagged = true;
-                        }
-                        if (flagged) mode_counts[6]++;
-                    }
                     for (int k = 0; k < P; ++k) {
                         const float s_s = (float)(xoff + k) / (float)P;
                         const double k1d = mul_rn((double)s_s, add_rn(1.0, -(double)s_s));
                         double v[3];
                         float lo, la;
                         blend_f32(q, rc, s_s, k1d, v);
-                        if (use_eft && !flagged) {
-                            // the two blends must agree bit for bit wherever the FP32 one is trusted
-                            for (int c = 0; c < 3; ++c) if (v[c] - q.A[c] != dv[k][c]) mode_counts[7]++;
-                            if ((double)vz[k] != v[2]) mode_counts[7]++;
-                            const double zd = (double)vz[k];
-                            if (q.wrap) backtransform_f32_d<kBoth, true>(q, dv[k][0], dv[k][1], dv[k][2], zd, lo, la);
-                            else if (q.mode == kLow) backtransform_f32_d<kLow, false>(q, dv[k][0], dv[k][1], dv[k][2], zd, lo, la);
-                            else if (q.mode == kHigh) backtransform_f32_d<kHigh, false>(q, dv[k][0], dv[k][1], dv[k][2], zd, lo, la);
-                            else backtransform_f32_d<kBoth, false>(q, dv[k][0], dv[k][1], dv[k][2], zd, lo, la);
-                            const long o = (s * N + j) * (long)Wf + (long)ca * P + xoff + k;
-                            out_lon[o] = lo; out_lat[o] = la;
-                            continue;
-                        }
                         if (q.mode == kSlow) { const LonLatF ll = backtransform_f32_slow((float)v[0], (float)v[1], (float)v[2]); lo = ll.lon; la = ll.lat; }
-                        else if (q.wrap) backtransform_f32<kBoth, true>(q, v, lo, la);
-                        else if (q.mode == kLow) backtransform_f32<kLow, false>(q, v, lo, la);
-                        else if (q.mode == kHigh) backtransform_f32<kHigh, false>(q, v, lo, la);
-                        else backtransform_f32<kBoth, false>(q, v, lo, la);
+                        else backtransform_f32<kBoth, true>(q, v, lo, la);
                         const long o = (s * N + j) * (long)Wf + (long)ca * P + xoff + k;
                         out_lon[o] = lo; out_lat[o] = la;
                     }
@@ -297,7 +324,8 @@ static void run_f32(const float* lon, const float* lat, const float* satz, long 
     }
 }
 
-// mode_counts[5..7]: quads on the FP32-pipe blend, flagged fine rows, pixels where it differs from blend_f32
+// mode_counts[5..7]: quads on the FP32-pipe blend, of those evaluated again with blend_f32, pixels where the
+// FP32-pipe blend differs from blend_f32 although no value was flagged (must stay 0)
 extern "C" int gtp_emul_cviirs_fast_f32(const float* lon, const float* lat, const float* satz, long n_scans,
                                         int fine_res, float* out_lon, float* out_lat, long* mode_counts)
 {
@@ -317,12 +345,22 @@ static void run_simple_f32(const float* lon, const float* lat, long n_scans, flo
 {
     using namespace gtpfast32;
     const int W = 1354, L = 10, Wf = W * P, N = L * P, H = P / 2;
+    std::vector<TieColF> col((size_t)L * W);
     for (long s = 0; s < n_scans; ++s) {
+        for (int c = 0; c < W; ++c) {
+            TieColF t;
+            for (int r = 0; r < L; ++r) {
+                const long o = (s * L + r) * W + c;
+                if (r == 0) tie_col_first<false>(t, lon[o], lat[o], 0.0f);
+                else tie_col_next<false>(t, lon[o], lat[o], 0.0f);
+                col[(size_t)r * W + c] = t;
+            }
+        }
         for (int qc = 0; qc <= W - 1; ++qc) {
             const bool extra = (qc == W - 1);
             const int ca = extra ? W - 2 : qc, cb = ca + 1, xoff = extra ? P : 0;
             for (int qr = 0; qr < L - 1; ++qr) {
-                auto geo = [&](int r, int c) { long o = (s * L + r) * W + c; return tie_geo_f32(lon[o], lat[o]); };
+                auto geo = [&](int r, int c) { return tie_col_geo(col[(size_t)r * W + c]); };
                 auto v3 = [](const TieGeoF& t) { Vec3F v; v.x = t.x; v.y = t.y; v.z = t.z; return v; };
                 const TieGeoF A = geo(qr, ca);
                 const Vec3F B = v3(geo(qr, cb)), D = v3(geo(qr + 1, ca)), C = v3(geo(qr + 1, cb));
