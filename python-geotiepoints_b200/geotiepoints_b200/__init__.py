@@ -8,3 +8,4 @@ CUDA behind the C ABI declared in ``include/gtp_b200.h``.  There is no CPU fallb
 __version__ = "0.1.0"
 
 from . import ecef, mod03, modisinterpolator, simple_modis_interpolator  # noqa: F401
+from ._capi import trim  # noqa: F401

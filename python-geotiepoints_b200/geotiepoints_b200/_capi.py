@@ -12,8 +12,10 @@ import weakref
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# GTP_B200_LIB lets a developer point at an experimental build of the same ABI
-LIB_PATH = os.environ.get("GTP_B200_LIB") or os.path.join(_HERE, "libgtp_b200.so")
+#: the in-tree build.  GTP_B200_LIB points at an A/B build of the same ABI (tools/build_variant.sh); using it
+#: is never silent: a warning at load time, and bench.py prints the path and sha256 of what it timed.
+DEFAULT_LIB_PATH = os.path.join(_HERE, "libgtp_b200.so")
+LIB_PATH = os.environ.get("GTP_B200_LIB") or DEFAULT_LIB_PATH
 
 GTP_E_WIDTH_5KM = 2
 GTP_E_NO_DEVICE = 5
@@ -76,12 +78,27 @@ def lib():
                     raise ImportError(
                         f"{LIB_PATH} is missing: build the sm_100a CUDA library first "
                         "(python -m geotiepoints_b200.build).  geotiepoints_b200 has no CPU fallback.")
+                if os.path.realpath(LIB_PATH) != os.path.realpath(DEFAULT_LIB_PATH):
+                    import warnings
+                    warnings.warn(f"geotiepoints_b200: GTP_B200_LIB is set, loading {LIB_PATH} instead of the in-tree "
+                                  f"library", RuntimeWarning, stacklevel=2)
                 handle = ctypes.CDLL(LIB_PATH)
                 for name, (restype, argtypes) in SIGNATURES.items():
                     fn = getattr(handle, name)
                     fn.restype, fn.argtypes = restype, argtypes
                 _lib = handle
     return _lib
+
+
+def library_info():
+    """Path, sha256 and version string of the loaded library (bench.py prints them with every line)."""
+    import hashlib
+    h = hashlib.sha256()
+    with open(LIB_PATH, "rb") as fh:
+        for block in iter(lambda: fh.read(1 << 20), b""):
+            h.update(block)
+    return {"path": os.path.relpath(LIB_PATH, os.path.dirname(os.path.dirname(_HERE))) if LIB_PATH.startswith(os.path.dirname(os.path.dirname(_HERE))) else LIB_PATH,
+            "sha256": h.hexdigest(), "version": lib().gtp_version().decode(), "in_tree": os.path.realpath(LIB_PATH) == os.path.realpath(DEFAULT_LIB_PATH)}
 
 
 def last_error():
@@ -120,11 +137,16 @@ class _PinnedPool:
     reused by the next call of the same shape.  Bounded by ``max_cached_bytes``.
     """
 
-    def __init__(self, max_cached_bytes=8 << 30):
+    def __init__(self, max_cached_bytes=None):
+        if max_cached_bytes is None:
+            # GTP_B200_PINNED_CACHE_MB bounds what stays cached after the arrays are gone (default 8 GiB: the
+            # lon + lat of two float64 granules at 250 m; geotiepoints_b200.trim() empties it)
+            max_cached_bytes = int(float(os.environ.get("GTP_B200_PINNED_CACHE_MB", "8192")) * (1 << 20))
         self.max_cached_bytes = max_cached_bytes
         self._free = {}
         self._cached = 0
         self._lock = threading.Lock()
+        self.pageable_fallbacks = 0
 
     def _release(self, ptr, nbytes):
         with self._lock:
@@ -145,7 +167,15 @@ class _PinnedPool:
                 self._cached -= nbytes
         if ptr is None:
             out = _vp()
-            check(lib().gtp_host_alloc(ctypes.byref(out), nbytes))
+            rc = lib().gtp_host_alloc(ctypes.byref(out), nbytes)
+            if rc != 0:
+                # no lockable memory left (ulimit -l, many results alive): give the cache back and try once
+                # more, then fall back to pageable memory - the copy is slower, the result the same
+                self.trim()
+                rc = lib().gtp_host_alloc(ctypes.byref(out), nbytes)
+            if rc != 0:
+                self.pageable_fallbacks += 1
+                return np.empty(shape, dtype)
             ptr = out.value
         buf = (ctypes.c_char * nbytes).from_address(ptr)
         arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
@@ -161,6 +191,14 @@ class _PinnedPool:
 
 
 pinned_pool = _PinnedPool()
+
+
+def trim():
+    """Give back what the library and the pinned pool keep between calls: the idle stream / scratch sets of
+    the host entry points (~300 MB of device memory each) and the cached page-locked blocks.  For long-lived
+    workers that share the GPU or the host's lockable memory with other frameworks."""
+    pinned_pool.trim()
+    check(lib().gtp_trim())
 
 
 def device_count():

@@ -372,7 +372,10 @@ GTP_FD QuadF32 quad_setup_f32(const TieGeoF& A, const Vec3F& B, const Vec3F& C, 
                                              + kAT * (fabsf(Se) + fabsf(Sh)) + 2.0f * fabsf(e0) + 2.0f * fabsf(e1)));
     const double wmax = (double)(1.0001f * (kA * fabsf(Pz) + kT * fabsf(Qz) + kAT * fabsf(Sz) + 2.0f)) * kInvEarthR;
     const bool ok = (horiz <= max_horiz) && (wmax <= max_w)
-                    && (fabsf(ce) <= 1.0f) && (fabsf(ca) <= 0.5f) && (A.cp > 1e-6);
+                    && (fabsf(ce) <= 1.0f) && (fabsf(ca) <= 0.5f) && (A.cp > 1e-6)
+                    // an anchor outside [-180, 180] x [-90, 90] (the MOD03 fill value -999): the reference folds it
+                    // through lonlat2xyz -> xyz2lonlat, the anchor-relative series would keep it
+                    && (fabs(A.lam) <= 3.1415928) && (fabs(A.phi) <= 1.5707964);
     if (!ok) { q.mode = kSlow; return q; }
 
     const double zr_lo = q.s0 - wmax, zr_hi = q.s0 + wmax;

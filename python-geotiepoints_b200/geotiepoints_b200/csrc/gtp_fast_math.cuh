@@ -466,7 +466,10 @@ GTP_FD void quad_classify(Quad& q, const TieGeo& A, const QuadSize& sz, double c
     q.small = false;
     q.ce = ce; q.ca = ca;
     // written so that any NaN (lon/lat/satz) fails the test and takes the slow path
-    const bool sane = (wmax <= kMaxRelZ) && (absd(q.ce) <= 0.25) && (absd(q.ca) <= 0.25) && (A.cp > 1e-6);
+    // ... and so that an anchor outside [-180, 180] x [-90, 90] (e.g. the MOD03 fill value -999) does too: the
+    // reference folds it through lonlat2xyz -> xyz2lonlat, the anchor-relative series would keep it
+    const bool sane = (wmax <= kMaxRelZ) && (absd(q.ce) <= 0.25) && (absd(q.ca) <= 0.25) && (A.cp > 1e-6)
+                      && (absd(A.lon) <= 180.0) && (absd(A.lat) <= 90.0);
     const bool narrow = sane && (horiz <= kMaxRelHoriz);
     // next to a pole the quad may span up to 10 % of its distance from the axis: longer series (kWide)
     const bool wide = !narrow && sane && (horiz <= kMaxRelHorizWide) && (A.cp <= kMaxCosWide);
@@ -603,7 +606,8 @@ GTP_FD void quad_classify_long(Quad& q, const TieGeo& A, const QuadSize& sz, dou
     q.small = false;
     q.ce = ce; q.ca = ca;
     const bool sane = (horiz <= kMaxRelHorizWide) && (wmax <= 0.05)
-                      && (absd(q.ce) <= 0.25) && (absd(q.ca) <= 0.25) && (A.cp > 1e-6);
+                      && (absd(q.ce) <= 0.25) && (absd(q.ca) <= 0.25) && (A.cp > 1e-6)
+                      && (absd(A.lon) <= 180.0) && (absd(A.lat) <= 90.0);      // fill values: see quad_classify
     if (!sane) { q.mode = kSlow; return; }
     const double as0 = absd(q.s0);
     const double margin = 1e-9;

@@ -14,7 +14,9 @@ output traffic of the float64 path, three times the pixel rate of the float32-fa
     lons, lats = mod03.modis_1km_to_250m(lon_f32, lat_f32, sensor_zenith_i16, zenith_scale=0.01)
 
 Inputs are numpy arrays or torch CUDA tensors (zero copy), C-contiguous, whole scans of 10 rows and
-1354 columns; ``sensor_zenith`` is float32 (degrees, or scaled) or int16.
+1354 columns; ``sensor_zenith`` is float32 (degrees, or scaled) or int16.  ``zenith_scale`` defaults to the
+MOD03 ``scale_factor`` 0.01 for int16 and to 1 for float32; fill values (-999, -32767) are taken as they are,
+like any other number (the reference has no notion of them either).
 
 ``ecef=True`` (1 km tie points) returns the Cartesian ``(x, y, z)`` in metres that the algorithm
 interpolates - see :mod:`geotiepoints_b200.ecef` - instead of their back-transform to lon / lat.
@@ -30,17 +32,17 @@ _ZEN_KIND = {"float32": 0, "int16": 1}
 _OUT_KIND = {"float32": 0, "float64": 1}
 
 
-def modis_1km_to_250m(lon1, lat1, sensor_zenith, *, zenith_scale=1.0, zenith_offset=0.0, out_dtype=np.float32, ecef=False):
+def modis_1km_to_250m(lon1, lat1, sensor_zenith, *, zenith_scale=None, zenith_offset=0.0, out_dtype=np.float32, ecef=False):
     """1 km -> 250 m from float32 lon / lat and float32 | int16 zenith angles, float64 math."""
     return _interpolate(lon1, lat1, sensor_zenith, 250, zenith_scale, zenith_offset, out_dtype, ecef=ecef)
 
 
-def modis_1km_to_500m(lon1, lat1, sensor_zenith, *, zenith_scale=1.0, zenith_offset=0.0, out_dtype=np.float32, ecef=False):
+def modis_1km_to_500m(lon1, lat1, sensor_zenith, *, zenith_scale=None, zenith_offset=0.0, out_dtype=np.float32, ecef=False):
     """1 km -> 500 m from float32 lon / lat and float32 | int16 zenith angles, float64 math."""
     return _interpolate(lon1, lat1, sensor_zenith, 500, zenith_scale, zenith_offset, out_dtype, ecef=ecef)
 
 
-def modis_5km_to_1km(lon1, lat1, sensor_zenith, *, zenith_scale=1.0, zenith_offset=0.0, out_dtype=np.float32):
+def modis_5km_to_1km(lon1, lat1, sensor_zenith, *, zenith_scale=None, zenith_offset=0.0, out_dtype=np.float32):
     """5 km (270 or 271 columns) -> 1 km from float32 lon / lat and float32 | int16 zenith angles, float64 math."""
     return _interpolate(lon1, lat1, sensor_zenith, 1000, zenith_scale, zenith_offset, out_dtype, coarse_resolution=5000)
 
@@ -69,6 +71,9 @@ def _interpolate(lon1, lat1, zen, fine_resolution, zenith_scale, zenith_offset, 
         raise TypeError("mod03: longitude and latitude must be float32 (use modisinterpolator for float64)")
     if _dtype_name(zen) not in _ZEN_KIND:
         raise TypeError("mod03: sensor_zenith must be float32 or int16")
+    if zenith_scale is None:
+        # MOD03 SensorZenith: int16 with scale_factor 0.01; float32 zenith angles are degrees already
+        zenith_scale = 0.01 if _dtype_name(zen) == "int16" else 1.0
     out_name = np.dtype(out_dtype).name
     if out_name not in _OUT_KIND:
         raise TypeError("mod03: out_dtype must be float32 or float64")

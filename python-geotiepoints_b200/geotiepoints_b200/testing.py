@@ -129,3 +129,19 @@ def punch_nan_holes(lon, lat, satz, seed=7, n=24):
     lon[0, 0] = lat[0, 0] = np.nan
     satz[rows - 1, cols - 1] = np.nan
     return lon, lat, satz
+
+
+def fill_value_granule(granule=3, n_scans=4, dtype=np.float64, fill=-999.0):
+    """A granule with the MOD03 ``_FillValue`` (-999) in its geolocation: scan 1 entirely, a block of
+    columns of scan 2 and a few single tie points of scan 3.  The reference has no notion of fill values:
+    it folds them through ``lonlat2xyz`` -> ``xyz2lonlat`` like any other angle (-999 deg comes back as
+    81 deg), and so must every path here."""
+    lon, lat, satz = modis_granule(granule, n_scans=n_scans, dtype=dtype)
+    lon, lat = lon.copy(), lat.copy()
+    lon[10:20], lat[10:20] = fill, fill
+    if n_scans > 2:
+        lon[20:30, 400:460], lat[20:30, 400:460] = fill, fill
+    if n_scans > 3:
+        for r, c in ((31, 5), (34, 700), (39, 1353), (30, 1352), (35, 0)):
+            lon[r, c], lat[r, c] = fill, fill
+    return lon, lat, satz

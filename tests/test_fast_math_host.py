@@ -324,3 +324,48 @@ def test_5km_f32_series_stress_inputs(emul, golden_inputs, name):
         with np.errstate(all="ignore"):
             exp = gtp_oracle.cviirs(lon, lat, satz, 5000, 1000, width)
         assert_parity(got_lon, got_lat, *exp, what=f"host emulation 5km({width}) f32 {name}, modes {modes}")
+
+
+# ---- fill values in the geolocation ----
+def assert_fill_parity(got, exp, rows_per_scan, what):
+    """Scans 0 (valid) and 1 (all fill) to the usual tolerances; quads that MIX valid and fill corners are
+    chords deep inside the sphere, where the reference's formulas are ill-conditioned (see
+    test_unphysical_inputs_fall_back): 1e-7 deg there (float32: the usual 1e-5 deg / 1 ulp)."""
+    from parity import compare
+    n = 2 * rows_per_scan
+    assert_parity(got[0][:n], got[1][:n], exp[0][:n], exp[1][:n], what=what + " (scans 0, 1)")
+    s = compare(got[0], got[1], *exp)
+    assert s["nan_pattern_equal"], (what, s)
+    if got[0].dtype == np.float64:
+        assert s["max_dlat"] < 1e-7 and max(s["max_dlon_outside_band"], s["max_dlon_in_band"]) < 1e-7, (what, s)
+    else:
+        assert s["n_over_tol_and_ulp"] == 0, (what, s)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["float64", "float32"])
+def test_fill_values_fold_like_the_reference(emul, dtype):
+    """-999 (the MOD03 _FillValue) in lon / lat: the reference folds it through lonlat2xyz -> xyz2lonlat;
+    the anchor-relative series must not keep it as the anchor (quads with an out-of-range anchor take the
+    rounding-faithful path)."""
+    lon, lat, satz = testing.fill_value_granule(dtype=dtype)
+    name = np.dtype(dtype).name
+    for fine in (250, 500):
+        with np.errstate(all="ignore"):
+            exp = gtp_oracle.cviirs(lon, lat, satz, 1000, fine)
+            exp_s = gtp_oracle.simple(lon, lat, 1000, fine)
+        assert np.nanmax(np.abs(exp[1])) <= 90.0 and np.nanmax(np.abs(exp[0])) <= 180.0      # the reference folds
+        if dtype == np.float64:
+            got_lon, got_lat, modes = emul(lon, lat, satz, fine)
+            got_s = emul.simple(lon, lat, fine)
+        else:
+            got_lon, got_lat, modes = emul.f32(lon, lat, satz, fine)
+            got_s = emul.simple_f32(lon, lat, fine)
+        assert modes["slow"] > 0
+        assert_fill_parity((got_lon, got_lat), exp, 10000 // fine, f"host emulation fill values -> {fine} m {name}")
+        assert_fill_parity(got_s[:2], exp_s, 10000 // fine, f"host emulation simple fill values -> {fine} m {name}")
+    for width in (271, 270):
+        lon5, lat5, satz5 = testing.subsample_5km(lon, lat, satz, width)
+        with np.errstate(all="ignore"):
+            exp5 = gtp_oracle.cviirs(lon5, lat5, satz5, 5000, 1000, width)
+        got5 = emul.five_km(lon5, lat5, satz5) if dtype == np.float64 else emul.five_km_f32(lon5, lat5, satz5)
+        assert_fill_parity(got5[:2], exp5, 10, f"host emulation 5km({width}) fill values {name}")

@@ -318,3 +318,49 @@ def test_kernels_stay_inside_their_output_buffers(config):
     for b in bufs:
         assert bool((b[:pad] == sentinel).all()) and bool((b[pad + n_out:] == sentinel).all()), "wrote outside the output"
         assert not bool((b[pad:pad + n_out] == sentinel).any()), "left output pixels unwritten"
+
+
+def _assert_fill_parity(got, exp, rows_per_scan, what):
+    """Scans 0 (valid) and 1 (all fill) to the usual tolerances; quads that mix valid and fill corners are
+    chords deep inside the sphere where the reference's own formulas are ill-conditioned: 1e-7 deg."""
+    n = 2 * rows_per_scan
+    assert_parity(got[0][:n], got[1][:n], exp[0][:n], exp[1][:n], what=what + " (scans 0, 1)")
+    s = compare(got[0], got[1], *exp)
+    assert s["nan_pattern_equal"], (what, s)
+    if got[0].dtype == np.float64:
+        assert s["max_dlat"] < 1e-7 and max(s["max_dlon_outside_band"], s["max_dlon_in_band"]) < 1e-7, (what, s)
+    else:
+        assert s["n_over_tol_and_ulp"] == 0, (what, s)
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=lambda d: np.dtype(d).name)
+def test_fill_values_fold_like_the_reference(dtype):
+    """-999 (MOD03 _FillValue) in lon / lat comes back folded (81 deg), as the reference's
+    lonlat2xyz -> xyz2lonlat does, on every fast path; int16 zenith fill (-32767) through the mod03 entry."""
+    lon, lat, satz = testing.fill_value_granule(dtype=dtype)
+    name = np.dtype(dtype).name
+    for fine in (250, 500):
+        exp = _oracle_cviirs((lon, lat, satz), 1000, fine, 0)
+        assert np.nanmax(np.abs(exp[1])) <= 90.0 and np.nanmax(np.abs(exp[0])) <= 180.0
+        got = interpolate(lon, lat, satz, coarse_resolution=1000, fine_resolution=fine)
+        _assert_fill_parity(got, exp, 10000 // fine, f"fill values cviirs 1km->{fine} {name}")
+        with np.errstate(all="ignore"):
+            exp_s = gtp_oracle.simple(lon, lat, 1000, fine)
+        got_s = simple_modis_interpolator.interpolate_geolocation_cartesian(lon, lat, coarse_resolution=1000, fine_resolution=fine)
+        _assert_fill_parity(got_s, exp_s, 10000 // fine, f"fill values simple 1km->{fine} {name}")
+    for width in (271, 270):
+        a5 = testing.subsample_5km(lon, lat, satz, width)
+        exp5 = _oracle_cviirs(a5, 5000, 1000, width)
+        got5 = interpolate(*a5, coarse_resolution=5000, fine_resolution=1000, coarse_scan_width=width)
+        _assert_fill_parity(got5, exp5, 10, f"fill values cviirs 5km({width})->1km {name}")
+
+
+def test_fill_values_mod03_types():
+    from geotiepoints_b200 import mod03
+    lon, lat, satz = testing.fill_value_granule(dtype=np.float32)
+    zen = np.round(satz.astype(np.float64) / 0.01).astype(np.int16)
+    zen[10:20] = -32767                                    # the SensorZenith fill value, taken as it is
+    satz64 = zen.astype(np.float64) * 0.01
+    exp = _oracle_cviirs((lon.astype(np.float64), lat.astype(np.float64), satz64), 1000, 250, 0)
+    got = mod03.modis_1km_to_250m(lon, lat, zen, zenith_scale=0.01, out_dtype=np.float64)
+    _assert_fill_parity(got, exp, 40, "fill values mod03 f32 + i16 -> float64")
