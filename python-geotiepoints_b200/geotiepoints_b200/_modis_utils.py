@@ -39,8 +39,15 @@ def _is_lazy(obj):
     return hasattr(obj, "compute")
 
 
-def scanline_mapblocks(func):
-    """Decorator: call ``func`` per whole-scan block for dask inputs (``:89-129``)."""
+def scanline_mapblocks(func=None, *, n_outputs=2):
+    """Decorator: call ``func`` per whole-scan block for dask inputs (``:89-129``).
+
+    ``n_outputs``: how many same-shaped arrays ``func`` returns (2 = lon / lat as in the reference; the ECEF
+    operators return 3).  A keyword argument ``out_dtype`` of ``func``, when given, is the dtype of the
+    results (``mod03``); otherwise they have the dtype of the first input, as in the reference (``:150``).
+    """
+    if func is None:
+        return functools.partial(scanline_mapblocks, n_outputs=n_outputs)
 
     @functools.wraps(func)
     def adapter(*args, coarse_resolution=None, fine_resolution=None, **kwargs):
@@ -54,7 +61,7 @@ def scanline_mapblocks(func):
 
         blocks = [a.data if hasattr(a, "dims") else a for a in args]
         blocks = _align_chunks_to_scans(blocks, rows_per_scan_for_resolution(coarse_resolution))
-        lazy = _map_scan_blocks(func, coarse_resolution, fine_resolution, *blocks, **kwargs)
+        lazy = _map_scan_blocks(func, n_outputs, coarse_resolution, fine_resolution, *blocks, **kwargs)
         if hasattr(template, "dims"):
             return [xr.DataArray(res, dims=template.dims) for res in lazy if isinstance(res, da.Array)]
         return lazy
@@ -82,20 +89,25 @@ def _align_chunks_to_scans(arrays, rows_per_scan):
     return [a.rechunk((rows, -1)) if hasattr(a, "chunks") else a for a in arrays]
 
 
-def _map_scan_blocks(func, coarse_resolution, fine_resolution, *arrays, **kwargs):
-    """``da.map_blocks`` with a leading (lon, lat) axis of length 2 (``:136-152``)."""
+def _map_scan_blocks(func, n_outputs, coarse_resolution, fine_resolution, *arrays, **kwargs):
+    """``da.map_blocks`` with a leading (lon, lat) axis of length 2 (``:136-152``).
+
+    The operator writes its outputs into the planes of one page-locked (numpy blocks) or device (torch
+    blocks) ``(n, rows, cols)`` buffer, so the stacking the reference does with ``np.concatenate``
+    (``:191-198``) is a view here, and blocks that live on the GPU stay there."""
+    from ._operator import stack
     template = next(a for a in arrays if _is_array(a))
     factor = coarse_resolution // fine_resolution
     out_rows = tuple(c * factor for c in template.chunks[0])
     out_cols = (1354 * _FINE_PIXELS_PER_1KM[fine_resolution],)
+    out_dtype = np.dtype(kwargs.get("out_dtype") or template.dtype)
 
     @functools.wraps(func)
     def stacked(*block_args, **block_kwargs):
-        lon, lat = func(*block_args, **block_kwargs)
-        return np.concatenate((np.asarray(lon)[np.newaxis], np.asarray(lat)[np.newaxis]), axis=0)
+        return stack(func(*block_args, **block_kwargs))
 
     res = da.map_blocks(stacked, *arrays,
                         coarse_resolution=coarse_resolution, fine_resolution=fine_resolution, **kwargs,
-                        new_axis=[0], chunks=(2, out_rows, out_cols), dtype=template.dtype,
-                        meta=np.empty((2, 2, 2), dtype=template.dtype))
+                        new_axis=[0], chunks=(n_outputs, out_rows, out_cols), dtype=out_dtype,
+                        meta=np.empty((2, 2, 2), dtype=out_dtype))
     return tuple(res[k] for k in range(res.shape[0]))

@@ -33,6 +33,44 @@ def _check_2d_same_shape(arrays):
     return shape
 
 
+def empty_outputs(n_out, out_shape, dtype):
+    """``n_out`` numpy outputs as the planes of ONE page-locked ``(n_out, rows, cols)`` block: the tuple the
+    reference's operators return, and - for the dask adapter, which needs them stacked
+    (``_modis_utils.pyx:191-198``) - a single array again without a copy (:func:`stack`)."""
+    block = _capi.pinned_pool.empty((n_out,) + tuple(out_shape), dtype)
+    return tuple(block[k] for k in range(n_out))
+
+
+def empty_outputs_torch(n_out, out_shape, dtype, device):
+    import torch
+    block = torch.empty((n_out,) + tuple(out_shape), dtype=dtype, device=device)
+    return tuple(block[k] for k in range(n_out))
+
+
+def stack(outputs):
+    """``(n, rows, cols)`` array of an operator's outputs.  Zero copy when they are the adjacent planes of one
+    block, which is what :func:`run` returns; any other arrays are concatenated (numpy) / stacked (torch)."""
+    first = outputs[0]
+    n = len(outputs)
+    if _is_torch_tensor(first):
+        import torch
+        same = all(o.is_contiguous() and o.shape == first.shape and o.dtype == first.dtype
+                   and o.untyped_storage().data_ptr() == first.untyped_storage().data_ptr()
+                   and o.data_ptr() == first.data_ptr() + k * first.numel() * first.element_size()
+                   for k, o in enumerate(outputs))
+        if same:
+            return torch.as_strided(first, (n,) + tuple(first.shape), (first.numel(),) + tuple(first.stride()))
+        return torch.stack(list(outputs))
+    outputs = [np.asarray(o) for o in outputs]
+    first = outputs[0]
+    same = all(o.flags.c_contiguous and o.shape == first.shape and o.dtype == first.dtype
+               and o.base is not None and o.base is first.base
+               and o.ctypes.data == first.ctypes.data + k * first.nbytes for k, o in enumerate(outputs))
+    if same:
+        return np.lib.stride_tricks.as_strided(first, shape=(n,) + first.shape, strides=(first.nbytes,) + first.strides)
+    return np.concatenate([o[np.newaxis] for o in outputs], axis=0)
+
+
 def run(kind, arrays, n_scans, out_shape, scalar_args, ecef=False):
     """Run one operator.
 
@@ -47,7 +85,7 @@ def run(kind, arrays, n_scans, out_shape, scalar_args, ecef=False):
         return _run_torch(lib, kind, arrays, n_scans, out_shape, scalar_args, ecef)
     arrays = [np.ascontiguousarray(a) for a in arrays]
     suffix = _check_same_dtype(arrays)
-    out = [_capi.pinned_pool.empty(out_shape, arrays[0].dtype) for _ in range(3 if ecef else 2)]
+    out = empty_outputs(3 if ecef else 2, out_shape, arrays[0].dtype)
     fn = getattr(lib, f"gtp_{kind}_interp_{'xyz_' if ecef else ''}host_{suffix}")
     ptrs = [a.ctypes.data for a in arrays]
     rc = fn(*ptrs, n_scans, *scalar_args, *[o.ctypes.data for o in out], -1)
@@ -65,7 +103,7 @@ def _run_torch(lib, kind, arrays, n_scans, out_shape, scalar_args, ecef=False):
     for a in arrays[1:]:
         if a.device != first.device:
             raise ValueError("all input tensors must live on the same device")
-    out = [torch.empty(out_shape, dtype=first.dtype, device=first.device) for _ in range(3 if ecef else 2)]
+    out = empty_outputs_torch(3 if ecef else 2, out_shape, first.dtype, first.device)
     stream = torch.cuda.current_stream(first.device).cuda_stream
     fn = getattr(lib, f"gtp_{kind}_interp_{'xyz_' if ecef else ''}{suffix}")
     rc = fn(*[a.data_ptr() for a in arrays], n_scans, *scalar_args,

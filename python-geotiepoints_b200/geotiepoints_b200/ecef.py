@@ -11,22 +11,38 @@ values of ``MODISInterpolator._compute_fine_xyz`` (``_modis_interpolator.pyx:346
     x, y, z = ecef.modis_1km_to_250m(lon1, lat1, satz1)
 
 Same argument rules as :mod:`geotiepoints_b200.modisinterpolator`: 2-D float32 or float64 arrays of one
-dtype, whole scans, numpy arrays (host path) or torch CUDA tensors (zero copy); dask / xarray inputs
-are converted with ``numpy.ascontiguousarray``, i.e. computed eagerly (the lazy whole-scan block mapping
-of ``scanline_mapblocks`` is wired to the lon / lat operators only).  The MOD03 on-disk
-types are served by ``mod03.modis_1km_to_250m(..., ecef=True)``.
+dtype, whole scans, numpy arrays (host path) or torch CUDA tensors (zero copy); dask arrays (bare or
+inside xarray ``DataArray``s) are mapped lazily, whole-scan block by block, by the same
+``scanline_mapblocks`` adapter as the lon / lat operators.  The MOD03 on-disk types are served by
+``mod03.modis_1km_to_250m(..., ecef=True)``.
 """
 import warnings
 
 from ._modis_interpolator import MODISInterpolator
-from ._simple_modis_interpolator import interpolate_geolocation_cartesian as _simple
+from ._modis_utils import scanline_mapblocks
+from ._simple_modis_interpolator import interpolate_geolocation_cartesian as _simple_operator
+
+
+@scanline_mapblocks(n_outputs=3)
+def _interpolate_blocks(lon1, lat1, satz1, coarse_resolution=0, fine_resolution=0, coarse_scan_width=0):
+    return MODISInterpolator(coarse_resolution, fine_resolution, coarse_scan_width or 0).interpolate_xyz(lon1, lat1, satz1)
+
+
+@scanline_mapblocks(n_outputs=3)
+def _simple_blocks(lon1, lat1, coarse_resolution=0, fine_resolution=0):
+    return _simple_operator(lon1, lat1, coarse_resolution, fine_resolution, ecef=True)
+
+
+def _simple(lon1, lat1, coarse_resolution, fine_resolution, ecef=True):
+    return _simple_blocks(lon1, lat1, coarse_resolution=coarse_resolution, fine_resolution=fine_resolution)
 
 
 def interpolate(lon1, lat1, satz1, coarse_resolution, fine_resolution, coarse_scan_width=0):
-    """ECEF counterpart of ``_modis_interpolator.interpolate`` (``:17-38``) for array inputs."""
+    """ECEF counterpart of ``_modis_interpolator.interpolate`` (``:17-38``)."""
     if coarse_resolution == 5000 and coarse_scan_width not in (0, 270, 271):
         raise NotImplementedError("Can't interpolate if 5km tiepoints have less than 270 columns.")
-    return MODISInterpolator(coarse_resolution, fine_resolution, coarse_scan_width or 0).interpolate_xyz(lon1, lat1, satz1)
+    return _interpolate_blocks(lon1, lat1, satz1, coarse_resolution=coarse_resolution, fine_resolution=fine_resolution,
+                               coarse_scan_width=coarse_scan_width)
 
 
 def modis_1km_to_250m(lon1, lat1, satz1):

@@ -26,7 +26,8 @@ import ctypes
 import numpy as np
 
 from . import _capi
-from ._operator import _is_torch_tensor
+from ._modis_utils import scanline_mapblocks
+from ._operator import _is_torch_tensor, empty_outputs, empty_outputs_torch
 
 _ZEN_KIND = {"float32": 0, "int16": 1}
 _OUT_KIND = {"float32": 0, "float64": 1}
@@ -34,27 +35,63 @@ _OUT_KIND = {"float32": 0, "float64": 1}
 
 def modis_1km_to_250m(lon1, lat1, sensor_zenith, *, zenith_scale=None, zenith_offset=0.0, out_dtype=np.float32, ecef=False):
     """1 km -> 250 m from float32 lon / lat and float32 | int16 zenith angles, float64 math."""
-    return _interpolate(lon1, lat1, sensor_zenith, 250, zenith_scale, zenith_offset, out_dtype, ecef=ecef)
+    return _dispatch(lon1, lat1, sensor_zenith, 1000, 250, zenith_scale, zenith_offset, out_dtype, ecef)
 
 
 def modis_1km_to_500m(lon1, lat1, sensor_zenith, *, zenith_scale=None, zenith_offset=0.0, out_dtype=np.float32, ecef=False):
     """1 km -> 500 m from float32 lon / lat and float32 | int16 zenith angles, float64 math."""
-    return _interpolate(lon1, lat1, sensor_zenith, 500, zenith_scale, zenith_offset, out_dtype, ecef=ecef)
+    return _dispatch(lon1, lat1, sensor_zenith, 1000, 500, zenith_scale, zenith_offset, out_dtype, ecef)
 
 
 def modis_5km_to_1km(lon1, lat1, sensor_zenith, *, zenith_scale=None, zenith_offset=0.0, out_dtype=np.float32):
     """5 km (270 or 271 columns) -> 1 km from float32 lon / lat and float32 | int16 zenith angles, float64 math."""
-    return _interpolate(lon1, lat1, sensor_zenith, 1000, zenith_scale, zenith_offset, out_dtype, coarse_resolution=5000)
+    return _dispatch(lon1, lat1, sensor_zenith, 5000, 1000, zenith_scale, zenith_offset, out_dtype, False)
 
 
 def simple_modis_1km_to_250m(lon1, lat1, *, out_dtype=np.float32, ecef=False):
     """``simple_modis_interpolator.modis_1km_to_250m`` on float32 lon / lat with float64 math."""
-    return _interpolate_simple(lon1, lat1, 4, out_dtype, ecef)
+    return _dispatch_simple(lon1, lat1, 250, out_dtype, ecef)
 
 
 def simple_modis_1km_to_500m(lon1, lat1, *, out_dtype=np.float32, ecef=False):
     """``simple_modis_interpolator.modis_1km_to_500m`` on float32 lon / lat with float64 math."""
-    return _interpolate_simple(lon1, lat1, 2, out_dtype, ecef)
+    return _dispatch_simple(lon1, lat1, 500, out_dtype, ecef)
+
+
+# dask / xarray inputs: lazily, whole-scan block by block, through the same adapter as the drop-in operators
+@scanline_mapblocks
+def _lonlat_blocks(lon1, lat1, zen, coarse_resolution=0, fine_resolution=0, zenith_scale=None, zenith_offset=0.0,
+                   out_dtype=np.float32):
+    return _interpolate(lon1, lat1, zen, fine_resolution, zenith_scale, zenith_offset, out_dtype,
+                        coarse_resolution=coarse_resolution)
+
+
+@scanline_mapblocks(n_outputs=3)
+def _xyz_blocks(lon1, lat1, zen, coarse_resolution=0, fine_resolution=0, zenith_scale=None, zenith_offset=0.0,
+                out_dtype=np.float32):
+    return _interpolate(lon1, lat1, zen, fine_resolution, zenith_scale, zenith_offset, out_dtype,
+                        coarse_resolution=coarse_resolution, ecef=True)
+
+
+@scanline_mapblocks
+def _simple_lonlat_blocks(lon1, lat1, coarse_resolution=0, fine_resolution=0, out_dtype=np.float32):
+    return _interpolate_simple(lon1, lat1, coarse_resolution // fine_resolution, out_dtype, False)
+
+
+@scanline_mapblocks(n_outputs=3)
+def _simple_xyz_blocks(lon1, lat1, coarse_resolution=0, fine_resolution=0, out_dtype=np.float32):
+    return _interpolate_simple(lon1, lat1, coarse_resolution // fine_resolution, out_dtype, True)
+
+
+def _dispatch(lon1, lat1, zen, coarse, fine, zenith_scale, zenith_offset, out_dtype, ecef):
+    fn = _xyz_blocks if ecef else _lonlat_blocks
+    return fn(lon1, lat1, zen, coarse_resolution=coarse, fine_resolution=fine, zenith_scale=zenith_scale,
+              zenith_offset=zenith_offset, out_dtype=out_dtype)
+
+
+def _dispatch_simple(lon1, lat1, fine, out_dtype, ecef):
+    fn = _simple_xyz_blocks if ecef else _simple_lonlat_blocks
+    return fn(lon1, lat1, coarse_resolution=1000, fine_resolution=fine, out_dtype=out_dtype)
 
 
 def _dtype_name(a):
@@ -106,14 +143,14 @@ def _interpolate(lon1, lat1, zen, fine_resolution, zenith_scale, zenith_offset, 
             raise TypeError("torch inputs must be CUDA tensors (numpy arrays take the host path)")
         arrays = [a.contiguous() for a in arrays]
         tdtype = torch.float32 if out_name == "float32" else torch.float64
-        out = [torch.empty(out_shape, dtype=tdtype, device=lon1.device) for _ in range(n_out)]
+        out = empty_outputs_torch(n_out, out_shape, tdtype, lon1.device)
         stream = torch.cuda.current_stream(lon1.device).cuda_stream
         rc = getattr(lib, name)(*[a.data_ptr() for a in arrays], *scalars, *[o.data_ptr() for o in out],
                                 _OUT_KIND[out_name], lon1.device.index, ctypes.c_void_p(stream))
         _capi.check(rc)
         return tuple(out)
     arrays = [np.ascontiguousarray(a) for a in arrays]
-    out = [_capi.pinned_pool.empty(out_shape, np.dtype(out_dtype)) for _ in range(n_out)]
+    out = empty_outputs(n_out, out_shape, np.dtype(out_dtype))
     rc = getattr(lib, name + "_host")(*[a.ctypes.data for a in arrays], *scalars, *[o.ctypes.data for o in out],
                                       _OUT_KIND[out_name], -1)
     _capi.check(rc)
@@ -147,14 +184,14 @@ def _interpolate_simple(lon1, lat1, res, out_dtype, ecef=False):
             raise TypeError("torch inputs must be CUDA tensors (numpy arrays take the host path)")
         arrays = [a.contiguous() for a in arrays]
         tdtype = torch.float32 if out_name == "float32" else torch.float64
-        out = [torch.empty(out_shape, dtype=tdtype, device=lon1.device) for _ in range(n_out)]
+        out = empty_outputs_torch(n_out, out_shape, tdtype, lon1.device)
         stream = torch.cuda.current_stream(lon1.device).cuda_stream
         rc = getattr(lib, name)(*[a.data_ptr() for a in arrays], rows // 10, res, *[o.data_ptr() for o in out],
                                 _OUT_KIND[out_name], lon1.device.index, ctypes.c_void_p(stream))
         _capi.check(rc)
         return tuple(out)
     arrays = [np.ascontiguousarray(a) for a in arrays]
-    out = [_capi.pinned_pool.empty(out_shape, np.dtype(out_dtype)) for _ in range(n_out)]
+    out = empty_outputs(n_out, out_shape, np.dtype(out_dtype))
     rc = getattr(lib, name + "_host")(*[a.ctypes.data for a in arrays], rows // 10, res, *[o.ctypes.data for o in out],
                                       _OUT_KIND[out_name], -1)
     _capi.check(rc)

@@ -37,14 +37,21 @@ class Array:
         return self._thunk(self)
 
     def __getitem__(self, idx):
-        assert isinstance(idx, int)
+        assert isinstance(idx, (int, np.integer))
         parent = self
         return Array(lambda _self: parent._thunk(parent)[idx], self.shape[1:], self.chunks[1:], self.dtype)
 
 
+def _is_torch(obj):
+    return type(obj).__module__.startswith("torch")
+
+
 def from_array(arr, chunks):
-    arr = np.asarray(arr)
-    return Array(lambda _self: arr, arr.shape, (chunks,) * arr.ndim if isinstance(chunks, int) else chunks, arr.dtype)
+    """numpy arrays, or torch tensors (blocks then stay torch tensors: the GPU-resident block path)."""
+    if not _is_torch(arr):
+        arr = np.asarray(arr)
+    dtype = np.dtype(str(arr.dtype).replace("torch.", ""))
+    return Array(lambda _self: arr, tuple(arr.shape), (chunks,) * arr.ndim if isinstance(chunks, int) else chunks, dtype)
 
 
 BLOCK_SHAPES = []
@@ -67,6 +74,9 @@ def map_blocks(func, *arrays, new_axis=None, chunks=None, dtype=None, meta=None,
             BLOCK_SHAPES.append(block[0].shape)
             pieces.append(func(*block, **kwargs))
             r0 += rc
+        if _is_torch(pieces[0]):
+            import torch
+            return torch.cat(pieces, dim=1)
         return np.concatenate(pieces, axis=1)
 
     return Array(thunk, out_shape, chunks, dtype)

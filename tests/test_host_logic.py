@@ -226,3 +226,20 @@ def test_scan_ranges_partition(n_scans, world):
     assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         sharding.scan_range(world, world, n_scans)
+
+
+# ---- zero-copy stacking of the operator outputs (what the dask adapter returns per block) ----
+def test_stack_is_a_view_for_planes_of_one_block():
+    from geotiepoints_b200 import _operator
+    block = np.arange(2 * 6 * 8, dtype=np.float32).reshape(2, 6, 8)
+    planes = (block[0], block[1])
+    stacked = _operator.stack(planes)
+    assert stacked.shape == (2, 6, 8) and np.shares_memory(stacked, block) and np.array_equal(stacked, block)
+    three = np.zeros((3, 4, 4))
+    assert np.shares_memory(_operator.stack(tuple(three[k] for k in range(3))), three)
+    # anything else is copied, like the reference's np.concatenate (_modis_utils.pyx:191-198)
+    a, b = np.ones((6, 8), np.float32), np.zeros((6, 8), np.float32)
+    out = _operator.stack((a, b))
+    assert out.shape == (2, 6, 8) and not np.shares_memory(out, a) and np.array_equal(out[0], a) and np.array_equal(out[1], b)
+    swapped = _operator.stack((block[1], block[0]))          # same block, wrong order: not a view
+    assert not np.shares_memory(swapped, block) and np.array_equal(swapped[0], block[1])
