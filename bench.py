@@ -88,6 +88,8 @@ def parse_args():
                     help="do not pin each rank to the CPU cores local to its GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary configurations of the default run")
+    ap.add_argument("--secondary-granules", type=int, default=16)
     return ap.parse_args()
 
 
@@ -305,6 +307,183 @@ def run_reference_arm(args, dtype):
 # ------------------------------------------------------------------------------------
 # this repository's arm
 # ------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------
+# secondary configurations (SURVEY.md 8d / BASELINE configs[2] and [4]) inside the default run
+# ------------------------------------------------------------------------------------
+SECONDARY = [("cviirs_1km_250m", "f32"), ("cviirs_1km_500m", "f64"), ("cviirs_1km_500m", "f32"),
+             ("cviirs_5km_1km", "f64"), ("cviirs_5km_1km", "f32"), ("simple_1km_250m", "f64"), ("simple_1km_250m", "f32"),
+             ("simple_1km_500m", "f64"), ("mod03_1km_250m", "f32")]
+
+
+def measure_secondary(name, dtype_name, base_in, granules, device, local_rank, peak, steps=5, warmup=3):
+    """One secondary configuration with the data resident in HBM: `steps` timed launches (CUDA events on the
+    launch stream) over `granules` synthetic granules (working set >> L2), roofline fraction from the
+    algorithmic bytes, parity of 6 scans spread over the batch against the oracle.
+    base_in: float64 (lon, lat, satz) of `granules` 1 km granules."""
+    import ctypes
+    import torch
+    from geotiepoints_b200 import _capi, testing
+    cfg = CONFIGS[name]
+    mixed = cfg["kind"] == "mixed"
+    dtype = np.float32 if (dtype_name == "f32" or mixed) else np.float64
+    arrs = base_in
+    if cfg["coarse"] == 5000:
+        arrs = testing.subsample_5km(*arrs, width=cfg["width"])
+    arrs = [np.ascontiguousarray(a.astype(dtype)) for a in arrs[:cfg["n_in"]]]
+    if mixed:
+        arrs[2] = np.round(base_in[2] / 0.01).astype(np.int16)
+    rows_per_scan = 10 if cfg["coarse"] == 1000 else 2
+    n_scans = arrs[0].shape[0] // rows_per_scan
+    out_rows_per_scan = rows_per_scan * cfg["f"]
+    tdtype = torch.float64 if dtype == np.float64 else torch.float32
+    d_in = [torch.from_numpy(a).to(device) for a in arrs]
+    outs = [torch.empty((n_scans * out_rows_per_scan, cfg["out_cols"]), dtype=tdtype, device=device) for _ in range(2)]
+    lib = _capi.lib()
+    stream = torch.cuda.current_stream(device)
+    st = ctypes.c_void_p(stream.cuda_stream)
+    ptrs = [t.data_ptr() for t in d_in]
+    optrs = [o.data_ptr() for o in outs]
+    if mixed:
+        def step():
+            _capi.check(lib.gtp_cviirs_interp_mixed(*ptrs, 1, 0.01, 0.0, n_scans, cfg["coarse"], cfg["fine"], 0, *optrs, 0, local_rank, st))
+    elif cfg["kind"] == "cviirs":
+        fn = getattr(lib, "gtp_cviirs_interp_" + dtype_name)
+
+        def step():
+            _capi.check(fn(*ptrs, n_scans, cfg["coarse"], cfg["fine"], cfg["width"], *optrs, local_rank, st))
+    else:
+        fn = getattr(lib, "gtp_simple_interp_" + dtype_name)
+
+        def step():
+            _capi.check(fn(*ptrs, n_scans, cfg["tie_cols"], cfg["coarse"] // cfg["fine"], *optrs, local_rank, st))
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(device)
+    before = _capi.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        a.record(stream)
+        step()
+        b.record(stream)
+    torch.cuda.synchronize(device)
+    launches = _capi.launch_count() - before
+    ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    px = n_scans * out_rows_per_scan * cfg["out_cols"]
+    bpp = algorithmic_bytes_per_px(np.dtype(dtype).itemsize, cfg)
+    res = {"config": name, "dtype": "f32+i16->f32 (f64 math)" if mixed else dtype_name, "value": px / (ms * 1e-3), "unit": UNIT,
+           "kernel_ms": ms, "steps": steps, "granules": granules, "gpu_launches": int(launches),
+           "algorithmic_bytes_per_px": bpp, "roofline_frac": bpp * px / (ms * 1e-3) / 1e9 / peak,
+           "working_set_gb": bpp * px / 1e9}
+    try:
+        import gtp_oracle
+        from parity import compare
+        picks = np.unique(np.linspace(0, n_scans - 1, 6).astype(np.int64))
+        in_rows = np.concatenate([np.arange(s * rows_per_scan, (s + 1) * rows_per_scan) for s in picks])
+        out_rows = np.concatenate([np.arange(s * out_rows_per_scan, (s + 1) * out_rows_per_scan) for s in picks])
+        sub = [np.ascontiguousarray(a[in_rows]) for a in arrs]
+        idx = torch.from_numpy(out_rows).to(device)
+        with np.errstate(all="ignore"):
+            if mixed:
+                exp = gtp_oracle.cviirs(sub[0].astype(np.float64), sub[1].astype(np.float64), sub[2].astype(np.float64) * 0.01,
+                                        1000, cfg["fine"], 0, n_threads=8)
+                exp = tuple(a.astype(np.float32) for a in exp)
+            elif cfg["kind"] == "cviirs":
+                exp = gtp_oracle.cviirs(*sub, cfg["coarse"], cfg["fine"], cfg["width"], n_threads=8)
+            else:
+                exp = gtp_oracle.simple(*sub, cfg["coarse"], cfg["fine"], n_threads=8)
+        par = compare(outs[0][idx].cpu().numpy(), outs[1][idx].cpu().numpy(), *exp)
+        keep = ("n", "nan_pattern_equal", "max_dlat", "max_dlon_outside_band", "max_dlon_in_band", "n_in_band",
+                "n_in_band_over_conditioning_bound", "bit_exact_fraction", "n_over_tol_and_ulp")
+        res["parity"] = {k: par[k] for k in keep if k in par}
+    except Exception as exc:
+        res["parity"] = {"error": repr(exc)}
+    del d_in, outs
+    torch.cuda.empty_cache()
+    return res
+
+
+class _LazyBlocks:
+    """Stand-in for ``dask.array`` in `e2e.dask` when dask is not installed (it is not in this image): whole-array
+    inputs with ``chunks``, ``rechunk`` and ``map_blocks(new_axis=[0])``, evaluated block by block on
+    ``compute()`` and assembled with ``np.concatenate`` as dask does.  The block results are cached so that
+    computing lons and lats evaluates every block once (what ``dask.compute(lons, lats)`` does)."""
+    def __init__(self, thunk, shape, chunks, dtype):
+        self._thunk, self.shape, self.dtype, self.ndim = thunk, tuple(shape), np.dtype(dtype), len(shape)
+        self.chunks = tuple(tuple(c) if isinstance(c, (tuple, list)) else ((n,) if c == -1 else
+                            (c,) * (n // c) + ((n % c,) if n % c else ())) for c, n in zip(chunks, shape))
+        self._cache = None
+
+    def rechunk(self, chunks):
+        return _LazyBlocks(self._thunk, self.shape, chunks, self.dtype)
+
+    def compute(self):
+        if self._cache is None:
+            self._cache = self._thunk(self)
+        return self._cache
+
+    def __getitem__(self, k):
+        parent = self
+        return _LazyBlocks(lambda _s: parent.compute()[k], self.shape[1:], self.chunks[1:], self.dtype)
+
+    @staticmethod
+    def from_array(a, chunks):
+        return _LazyBlocks(lambda _s: a, a.shape, chunks, a.dtype)
+
+    @staticmethod
+    def map_blocks(func, *arrays, new_axis=None, chunks=None, dtype=None, meta=None, **kwargs):
+        first = arrays[0]
+        chunks = tuple((c,) if isinstance(c, int) else tuple(c) for c in chunks)
+
+        def thunk(_s):
+            data = [a.compute() for a in arrays]
+            pieces, r0 = [], 0
+            for rc in first.chunks[0]:
+                pieces.append(func(*[d[r0:r0 + rc] for d in data], **kwargs))
+                r0 += rc
+            return pieces[0] if len(pieces) == 1 else np.concatenate(pieces, axis=1)
+        return _LazyBlocks(thunk, tuple(sum(c) for c in chunks), chunks, dtype)
+
+
+def e2e_lazy(h_in, steps, chunk_rows):
+    """1 km -> 250 m through the dask-shaped call: lazy inputs -> scanline_mapblocks -> compute()."""
+    from geotiepoints_b200 import _modis_utils, modisinterpolator
+    try:
+        import dask
+        import dask.array as da
+
+        def lazy(a):
+            return da.from_array(a, chunks=(chunk_rows, -1))
+
+        def compute(lons, lats):
+            return dask.compute(lons, lats, scheduler="threads")
+        kind = "dask " + dask.__version__
+    except ImportError:
+        import types
+        saved = _modis_utils.da
+        _modis_utils.da = types.SimpleNamespace(map_blocks=_LazyBlocks.map_blocks, Array=_LazyBlocks)
+
+        def lazy(a):
+            return _LazyBlocks.from_array(a, (chunk_rows, -1))
+
+        def compute(lons, lats):
+            return lons.compute(), lats.compute()
+        kind = "stand-in block scheduler (dask is not installed in this image)"
+    try:
+        res = compute(*modisinterpolator.modis_1km_to_250m(*[lazy(a) for a in h_in]))
+        del res
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            lons, lats = modisinterpolator.modis_1km_to_250m(*[lazy(a) for a in h_in])
+            res = compute(lons, lats)
+            checksum = float(res[0][-1, -1]) + float(res[1][-1, -1])
+            del res, lons, lats
+        dt = time.perf_counter() - t0
+    finally:
+        if "saved" in locals():
+            _modis_utils.da = saved
+    return dt, checksum, kind
+
+
 def run_b200_arm(args, dtype):
     import ctypes
     import torch
@@ -512,6 +691,36 @@ def run_b200_arm(args, dtype):
         dt = time.perf_counter() - t0
         dt = sharding.max_over_ranks(dt, dist if world > 1 else None)
         e2e_px = ge * px_per_granule(cfg)
+        # the same through the dask-shaped call (lazy inputs, whole-scan blocks, compute), and the float32-out
+        # (mod03) and ECEF forms of the call, which move half / 1.5 x the bytes (headline config only)
+        extra_e2e = {}
+        if headline:
+            lazy_steps = max(1, min(e2e_steps, 2))
+            ldt, lsum, lkind = e2e_lazy(h_in, lazy_steps, 4096)
+            ldt = sharding.max_over_ranks(ldt, dist if world > 1 else None)
+            extra_e2e["dask"] = {"value": e2e_px * world * lazy_steps / ldt, "unit": UNIT, "ms_per_step": 1e3 * ldt / lazy_steps,
+                                 "steps": lazy_steps, "scheduler": lkind, "chunks": "4096 rows (rechunked to 4090 = whole scans) x full width",
+                                 "sample": "modisinterpolator.modis_1km_to_250m on lazy inputs + compute of lons and lats; "
+                                           "includes the assembly of the blocks into the result arrays", "checksum": lsum}
+            from geotiepoints_b200 import ecef as ecef_api, mod03
+            m_in = [_capi.pinned_pool.empty((rows, cfg["tie_cols"]), dt_) for dt_ in (np.float32, np.float32, np.int16)]
+            m_in[0][...] = h_in[0]; m_in[1][...] = h_in[1]; m_in[2][...] = np.round(np.asarray(h_in[2], np.float64) / 0.01)
+            for key, call, nbytes_out in (
+                    ("mod03_f32", lambda: mod03.modis_1km_to_250m(*m_in), 2 * 4),
+                    ("ecef", lambda: ecef_api.modis_1km_to_250m(*h_in), 3 * itemsize)):
+                res = call()
+                del res
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(lazy_steps):
+                    res = call()
+                    csum = float(res[0][-1, -1]) + float(res[-1][-1, -1])
+                    del res
+                torch.cuda.synchronize(device)
+                xdt = sharding.max_over_ranks(time.perf_counter() - t0, dist if world > 1 else None)
+                extra_e2e[key] = {"value": e2e_px * world * lazy_steps / xdt, "unit": UNIT, "ms_per_step": 1e3 * xdt / lazy_steps,
+                                  "steps": lazy_steps, "d2h_bytes_per_step": int(nbytes_out * e2e_px), "checksum": csum}
+            del m_in
         e2e = {"value": e2e_px * world * e2e_steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(sum(a.dtype.itemsize for a in host_in) * rows * cfg["tie_cols"]),
                "d2h_bytes_per_step": int(n_out * e2e_px * itemsize),
@@ -521,6 +730,7 @@ def run_b200_arm(args, dtype):
                          f"({'geotiepoints_b200.modisinterpolator.modis_1km_to_250m' if headline else args.config}), "
                          f"pinned host inputs, pinned host outputs",
                "checksum": checksum}
+        e2e.update(extra_e2e)
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -567,11 +777,29 @@ def run_b200_arm(args, dtype):
                          "px_per_launch": int(px_per_rank_step)},
             "parity": parity,
         }
+        line["config"]["library"] = _capi.library_info()       # what was timed: path + sha256 of the loaded .so
         if sustained is not None:
             sus_value = px_per_rank_step * world / (sustained["ms_per_step"] * 1e-3)
             sustained.update({"value": sus_value, "unit": UNIT,
                               "roofline_frac": bpp * px_per_rank_step / (sustained["ms_per_step"] * 1e-3) / 1e9 / peak})
             line["sustained"] = sustained
+            line["roofline"]["sustained"] = sustained            # also here: the driver's summaries keep known keys only
+        if world == 1 and headline and not args.no_secondary and args.kernel == "auto":
+            # BASELINE configs[2] / [4] and the float32 paths, a few timed launches each (data resident in HBM)
+            del d_in[:], outs[:]
+            torch.cuda.empty_cache()
+            secondary = []
+            for name, dn in SECONDARY:
+                # 5 km -> 1 km granules are 16 x smaller than 1 km -> 250 m ones: the whole batch, so that a
+                # launch is not over before the GPU is full
+                gs = G if CONFIGS[name]["coarse"] == 5000 else min(G, args.secondary_granules)
+                base = [np.asarray(a[:gs * TIE_ROWS], np.float64) for a in host_in]
+                try:
+                    secondary.append(measure_secondary(name, dn, base, gs, device, local_rank, peak))
+                except Exception as exc:
+                    secondary.append({"config": name, "dtype": dn, "error": repr(exc)})
+            line["secondary"] = secondary
+            line["roofline"]["secondary"] = secondary
         if e2e is not None:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline and headline:

@@ -144,17 +144,28 @@ class _PinnedPool:
             max_cached_bytes = int(float(os.environ.get("GTP_B200_PINNED_CACHE_MB", "8192")) * (1 << 20))
         self.max_cached_bytes = max_cached_bytes
         self._free = {}
+        self._order = []               # (nbytes, ptr) of the cached blocks, oldest first
         self._cached = 0
         self._lock = threading.Lock()
         self.pageable_fallbacks = 0
 
     def _release(self, ptr, nbytes):
+        evicted = []
         with self._lock:
-            if self._cached + nbytes <= self.max_cached_bytes:
+            if nbytes > self.max_cached_bytes:
+                evicted.append(ptr)
+            else:
+                # make room by dropping the blocks that have been idle longest (sizes nobody asks for any more)
+                while self._cached + nbytes > self.max_cached_bytes and self._order:
+                    old_bytes, old_ptr = self._order.pop(0)
+                    self._free[old_bytes].remove(old_ptr)
+                    self._cached -= old_bytes
+                    evicted.append(old_ptr)
                 self._free.setdefault(nbytes, []).append(ptr)
+                self._order.append((nbytes, ptr))
                 self._cached += nbytes
-                return
-        lib().gtp_host_free(ptr)
+        for p in evicted:
+            lib().gtp_host_free(p)
 
     def empty(self, shape, dtype):
         dtype = np.dtype(dtype)
@@ -164,6 +175,7 @@ class _PinnedPool:
             blocks = self._free.get(nbytes)
             if blocks:
                 ptr = blocks.pop()
+                self._order.remove((nbytes, ptr))
                 self._cached -= nbytes
         if ptr is None:
             out = _vp()
@@ -184,7 +196,7 @@ class _PinnedPool:
 
     def trim(self):
         with self._lock:
-            blocks, self._free, self._cached = self._free, {}, 0
+            blocks, self._free, self._cached, self._order = self._free, {}, 0, []
         for ptrs in blocks.values():
             for ptr in ptrs:
                 lib().gtp_host_free(ptr)
