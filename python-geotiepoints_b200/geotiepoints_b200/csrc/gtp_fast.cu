@@ -50,14 +50,10 @@ __device__ __forceinline__ void quad_rows(const Quad& q, const double (&a_col)[P
         const RowCoef rc = row_setup(q, s_t, s_t * (1.0 - s_t));
         double vlon[P], vlat[P];
 #pragma unroll
-#ifdef GTP_EXP_NO_MATH        // power experiment: keep the HBM writes, drop the per-pixel math
-        for (int k = 0; k < P; ++k) { vlon[k] = a_col[k] + rc.Ve; vlat[k] = a_col[k] - rc.Ue; }
-#else
         for (int k = 0; k < P; ++k) {
             if (MODE == kWide) pixel_eval_wide(q, rc, a_col[k], vlon[k], vlat[k]);
             else pixel_eval<MODE, WRAP>(q, rc, a_col[k], vlon[k], vlat[k]);
         }
-#endif
         store_px<P>(out_lon + out_idx, vlon);
         store_px<P>(out_lat + out_idx, vlat);
         out_idx += kPitch;
@@ -131,11 +127,7 @@ modis_fast_1km_f64_kernel(const TIn* __restrict__ lon, const TIn* __restrict__ l
     Vec3 topB = {0.0, 0.0, 0.0};
     double top_ce = 0.0, top_ca = 0.0;
     __shared__ double stage[2][3][kThreads];     // double-buffered next-row inputs, one slot per thread
-#ifdef GTP_FAST_NO_PARK
-    constexpr bool kPark = false;
-#else
     constexpr bool kPark = (P == 4);
-#endif
     __shared__ double park[kPark ? 14 : 1][kThreads];      // per-thread parking slots (see the row loops)
     stage_fetch(&stage[0][0][threadIdx.x], lon, tie_idx);
     stage_fetch(&stage[0][1][threadIdx.x], lat, tie_idx);

@@ -12,9 +12,6 @@ __device__ __forceinline__ void store_px(double* p, const double (&v)[P]);
 template <>
 __device__ __forceinline__ void store_px<4>(double* p, const double (&v)[4])
 {
-#ifdef GTP_EXP_NO_STORE      // power experiment: keep the math, drop the HBM writes
-    if (v[0] != 1234.56789) return;
-#endif
     asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
 }
 
