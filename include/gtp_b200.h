@@ -177,6 +177,25 @@ int gtp_simple_interp_xyz_mixed(const float* lon, const float* lat, int64_t n_sc
 int gtp_simple_interp_xyz_mixed_host(const float* lon, const float* lat, int64_t n_scans, int res_factor,
                                      void* out_x, void* out_y, void* out_z, int out_kind, int device);
 
+/* ---- legacy spline interpolators ------------------------------------------
+ * Replace geotiepoints.modis5kmto1km / modis1kmto500m / modis1kmto250m
+ * (/root/reference/geotiepoints/__init__.py:49-152): GeoInterpolator (geointerpolator.py:10-75) over
+ * Interpolator (interpolator.py:54-229) with along-track order 1, cross-track order 3, chunk_size = one
+ * scan, fill_borders("y", "x"), i.e. scipy's RectBivariateSpline(kx = 1, ky = 3, s = 0) on the Cartesian
+ * tie points.  float64 lon / lat in degrees, whole scans:
+ *   GTP_LEGACY_5KM_1KM    (2 n_scans, 271)   -> (10 n_scans, 1354)
+ *   GTP_LEGACY_1KM_500M   (10 n_scans, 1354) -> (20 n_scans, 2708)
+ *   GTP_LEGACY_1KM_250M   (10 n_scans, 1354) -> (40 n_scans, 5416)
+ * The device form takes device pointers and allocates its scratch (48 bytes per tie point) stream-ordered
+ * (cudaMallocAsync) on `stream`; the host form copies in chunks like the other host entry points. */
+#define GTP_LEGACY_5KM_1KM 0
+#define GTP_LEGACY_1KM_500M 1
+#define GTP_LEGACY_1KM_250M 2
+int gtp_legacy_interp_f64(const double* lon, const double* lat, int64_t n_scans, int kind,
+                          double* out_lon, double* out_lat, int device, void* stream);
+int gtp_legacy_interp_host_f64(const double* lon, const double* lat, int64_t n_scans, int kind,
+                               double* out_lon, double* out_lat, int device);
+
 /* The host entry points keep up to 4 idle sets of (3 streams + chunk scratch, ~300 MB of
  * device memory each) per process for the next call; gtp_trim() frees them. */
 int gtp_trim(void);

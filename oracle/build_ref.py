@@ -23,6 +23,12 @@ into the repository; every output lands in the git-ignored ``oracle/_ref/``):
   so the cast is lossless.  Every f64 CVIIRS parity number in this repo that names
   "reference" means this twin, and says so.
 
+* ``oracle/_ref/geotiepoints/{interpolator,geointerpolator}.py`` and ``legacy.py``: the pure-Python
+  modules of the LEGACY spline API (``geotiepoints/__init__.py:49-152``,
+  ``interpolator.py``, ``geointerpolator.py``), copied as they are; ``legacy.py`` is the reference's
+  ``__init__.py`` under another name (the package's ``__init__`` stays empty, see above) with the two
+  ``version`` lines at its end left out.  ``oracle/legacy_oracle.py`` is pinned against them.
+
 Run:  python oracle/build_ref.py [--reference /root/reference]
 It is a no-op (exit 0) when the reference tree is absent, e.g. on the GPU box,
 where the prebuilt ``oracle/_ref`` that travelled with the snapshot is used.
@@ -111,6 +117,15 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     _build_pkg(ref_pkg, "geotiepoints", patch_f64=False)
     _build_pkg(ref_pkg, "geotiepoints_f64", patch_f64=True)
+    # legacy spline API: pure Python, staged beside the stock extensions
+    dst = os.path.join(OUT, "geotiepoints")
+    for name in ("interpolator.py", "geointerpolator.py"):
+        shutil.copy(os.path.join(ref_pkg, name), dst)
+    src = open(os.path.join(ref_pkg, "__init__.py")).read()
+    tail = "from . import version\n__version__ = version.get_versions()['version']\n"
+    if src.count(tail) != 1:
+        raise SystemExit("legacy staging: the version lines at the end of geotiepoints/__init__.py moved")
+    open(os.path.join(dst, "legacy.py"), "w").write(src.replace(tail, ""))
     with open(os.path.join(OUT, "BUILD_INFO.txt"), "w") as fh:
         import Cython, numpy, scipy
         fh.write(f"reference={args.reference}\ncython={Cython.__version__}\nnumpy={numpy.__version__}\n"

@@ -62,6 +62,8 @@ SIGNATURES["gtp_simple_interp_mixed_host"] = (_int, [_vp, _vp, _i64, _int, _vp, 
 SIGNATURES["gtp_cviirs_interp_generic_f64"] = SIGNATURES["gtp_cviirs_interp_f64"]
 SIGNATURES["gtp_simple_interp_generic_f64"] = SIGNATURES["gtp_simple_interp_f64"]
 SIGNATURES["gtp_cviirs_interp_generic_f32"] = SIGNATURES["gtp_cviirs_interp_f32"]
+SIGNATURES["gtp_legacy_interp_f64"] = (_int, [_vp, _vp, _i64, _int, _vp, _vp, _int, _vp])
+SIGNATURES["gtp_legacy_interp_host_f64"] = (_int, [_vp, _vp, _i64, _int, _vp, _vp, _int])
 
 
 class GtpError(RuntimeError):

@@ -725,6 +725,49 @@ int gtp_simple_interp_xyz_mixed_host(const float* lon, const float* lat, int64_t
                           out_x, out_y, out_z, out_kind, device);
 }
 
+// ---- legacy spline interpolators ----
+namespace {
+int legacy_device(const double* lon, const double* lat, int64_t n_scans, int kind, double* out_lon, double* out_lat,
+                  int device, void* stream)
+{
+    if (kind < GTP_LEGACY_5KM_1KM || kind > GTP_LEGACY_1KM_250M) return fail(GTP_E_RESOLUTION, "legacy interpolator: unknown kind%s");
+    if (n_scans < 0) return fail(GTP_E_SHAPE, "n_scans must be >= 0%s");
+    if (n_scans == 0) return GTP_OK;
+    if (!lon || !lat || !out_lon || !out_lat) return fail(GTP_E_NULL, "null buffer%s");
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) { cudaGetLastError(); return fail(GTP_E_NO_DEVICE, "no usable CUDA device: %s", cudaGetErrorString(guard.err)); }
+    void* ws = nullptr;
+    cudaError_t e = cudaMallocAsync(&ws, gtp_legacy_workspace_bytes(kind, n_scans), (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "legacy workspace");
+    e = gtp_launch_legacy_f64(lon, lat, out_lon, out_lat, n_scans, kind, ws, (cudaStream_t)stream);
+    const cudaError_t ef = cudaFreeAsync(ws, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "legacy launch");
+    if (ef != cudaSuccess) return cuda_fail(ef, "legacy workspace free");
+    g_launches.fetch_add(3, std::memory_order_relaxed);
+    return GTP_OK;
+}
+}  // namespace
+
+int gtp_legacy_interp_f64(const double* lon, const double* lat, int64_t n_scans, int kind,
+                          double* out_lon, double* out_lat, int device, void* stream)
+{ return legacy_device(lon, lat, n_scans, kind, out_lon, out_lat, device, stream); }
+
+int gtp_legacy_interp_host_f64(const double* lon, const double* lat, int64_t n_scans, int kind,
+                               double* out_lon, double* out_lat, int device)
+{
+    if (kind < GTP_LEGACY_5KM_1KM || kind > GTP_LEGACY_1KM_250M) return fail(GTP_E_RESOLUTION, "legacy interpolator: unknown kind%s");
+    if (n_scans < 0) return fail(GTP_E_SHAPE, "n_scans must be >= 0%s");
+    if (n_scans == 0) return GTP_OK;
+    if (!lon || !lat || !out_lon || !out_lat) return fail(GTP_E_NULL, "null buffer%s");
+    int L, W, nf, Wf;
+    gtp_legacy_shape(kind, &L, &W, &nf, &Wf);
+    const double* const in[2] = {lon, lat};
+    return host_pipeline<double, 2>(in, out_lon, out_lat, n_scans, (int64_t)L * W, (int64_t)nf * Wf, device,
+        [&](double* const* d_in, double* d_lon, double* d_lat, int64_t ns, cudaStream_t st) {
+            return legacy_device(d_in[0], d_in[1], ns, kind, d_lon, d_lat, -1, (void*)st);
+        });
+}
+
 int gtp_trim(void)
 {
     std::vector<HostPipe*> pipes;

@@ -60,3 +60,9 @@ bool gtp_cviirs_fast_f32_supported(const CviirsCfg& cfg);
 cudaError_t gtp_launch_simple_fast_f32(const float* lon, const float* lat, float* out_lon, float* out_lat,
                                        long long n_scans, int res, cudaStream_t stream);
 bool gtp_simple_fast_f32_supported(int width, int res);
+
+// gtp_legacy.cu: the reference's legacy spline interpolators (kind = GTP_LEGACY_*), float64
+size_t gtp_legacy_workspace_bytes(int kind, long long n_scans);
+void gtp_legacy_shape(int kind, int* tie_rows_per_scan, int* tie_cols, int* fine_rows_per_scan, int* fine_cols);
+cudaError_t gtp_launch_legacy_f64(const double* lon, const double* lat, double* out_lon, double* out_lat,
+                                  long long n_scans, int kind, void* workspace, cudaStream_t stream);
