@@ -48,6 +48,9 @@ CONFIGS = {
     "mod03_1km_250m": dict(kind="mixed", coarse=1000, fine=250, width=0, n_in=3, tie_rows=2030, tie_cols=1354, f=4, out_cols=5416),
     # extension: ECEF x / y / z instead of lon / lat (no back-transform, three outputs)
     "ecef_1km_250m": dict(kind="cviirs", ecef=True, coarse=1000, fine=250, width=0, n_in=3, tie_rows=2030, tie_cols=1354, f=4, out_cols=5416),
+    # the legacy spline API (geotiepoints.modis1kmto250m / modis5kmto1km), float64, lon + lat only
+    "legacy_1km_250m": dict(kind="legacy", code=2, coarse=1000, fine=250, width=0, n_in=2, tie_rows=2030, tie_cols=1354, f=4, out_cols=5416),
+    "legacy_5km_1km": dict(kind="legacy", code=0, coarse=5000, fine=1000, width=271, n_in=2, tie_rows=406, tie_cols=271, f=5, out_cols=1354),
     "mod03_ecef_1km_250m": dict(kind="mixed", ecef=True, coarse=1000, fine=250, width=0, n_in=3, tie_rows=2030, tie_cols=1354, f=4, out_cols=5416),
 }
 TIE_ROWS, TIE_COLS = 2030, 1354
@@ -88,6 +91,7 @@ def parse_args():
                     help="do not pin each rank to the CPU cores local to its GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-relay", action="store_true", help="N > 1: do not try the NVLink relay of the device-to-host copies")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary configurations of the default run")
     ap.add_argument("--secondary-granules", type=int, default=16)
     return ap.parse_args()
@@ -312,7 +316,7 @@ def run_reference_arm(args, dtype):
 # ------------------------------------------------------------------------------------
 SECONDARY = [("cviirs_1km_250m", "f32"), ("cviirs_1km_500m", "f64"), ("cviirs_1km_500m", "f32"),
              ("cviirs_5km_1km", "f64"), ("cviirs_5km_1km", "f32"), ("simple_1km_250m", "f64"), ("simple_1km_250m", "f32"),
-             ("simple_1km_500m", "f64"), ("mod03_1km_250m", "f32")]
+             ("simple_1km_500m", "f64"), ("mod03_1km_250m", "f32"), ("legacy_1km_250m", "f64"), ("legacy_5km_1km", "f64")]
 
 
 def measure_secondary(name, dtype_name, base_in, granules, device, local_rank, peak, steps=5, warmup=3):
@@ -327,7 +331,9 @@ def measure_secondary(name, dtype_name, base_in, granules, device, local_rank, p
     mixed = cfg["kind"] == "mixed"
     dtype = np.float32 if (dtype_name == "f32" or mixed) else np.float64
     arrs = base_in
-    if cfg["coarse"] == 5000:
+    if cfg["kind"] == "legacy" and cfg["coarse"] == 5000:
+        arrs = [a[2::5, 2::5] for a in arrs]                   # geotiepoints/tests: 5 km tie points of a 1 km granule
+    elif cfg["coarse"] == 5000:
         arrs = testing.subsample_5km(*arrs, width=cfg["width"])
     arrs = [np.ascontiguousarray(a.astype(dtype)) for a in arrs[:cfg["n_in"]]]
     if mixed:
@@ -346,6 +352,9 @@ def measure_secondary(name, dtype_name, base_in, granules, device, local_rank, p
     if mixed:
         def step():
             _capi.check(lib.gtp_cviirs_interp_mixed(*ptrs, 1, 0.01, 0.0, n_scans, cfg["coarse"], cfg["fine"], 0, *optrs, 0, local_rank, st))
+    elif cfg["kind"] == "legacy":
+        def step():
+            _capi.check(lib.gtp_legacy_interp_f64(*ptrs, n_scans, cfg["code"], *optrs, local_rank, st))
     elif cfg["kind"] == "cviirs":
         fn = getattr(lib, "gtp_cviirs_interp_" + dtype_name)
 
@@ -387,6 +396,9 @@ def measure_secondary(name, dtype_name, base_in, granules, device, local_rank, p
                 exp = gtp_oracle.cviirs(sub[0].astype(np.float64), sub[1].astype(np.float64), sub[2].astype(np.float64) * 0.01,
                                         1000, cfg["fine"], 0, n_threads=8)
                 exp = tuple(a.astype(np.float32) for a in exp)
+            elif cfg["kind"] == "legacy":
+                import legacy_oracle
+                exp = legacy_oracle.interpolate(*sub, {0: "5km_1km", 1: "1km_500m", 2: "1km_250m"}[cfg["code"]])
             elif cfg["kind"] == "cviirs":
                 exp = gtp_oracle.cviirs(*sub, cfg["coarse"], cfg["fine"], cfg["width"], n_threads=8)
             else:
@@ -505,6 +517,8 @@ def run_b200_arm(args, dtype):
         dist.init_process_group("nccl", device_id=device)
 
     cfg = CONFIGS[args.config]
+    if cfg["kind"] == "legacy":
+        raise SystemExit("the legacy_* configurations are measured inside the default run (`secondary`), not as --config")
     headline = args.config == "cviirs_1km_250m"
     mixed = cfg["kind"] == "mixed"
     ecef = bool(cfg.get("ecef"))
@@ -691,6 +705,49 @@ def run_b200_arm(args, dtype):
         dt = time.perf_counter() - t0
         dt = sharding.max_over_ranks(dt, dist if world > 1 else None)
         e2e_px = ge * px_per_granule(cfg)
+        # -- NVLink relay of the device-to-host copies (world > 1): PCIe root ports of a multi-GPU host are not
+        # equally fast; ranks on slow ports send their results through a GPU on a fast one (gtp_set_d2h_relay)
+        relay_info, relay_on = None, False
+        if world > 1 and headline and not args.no_relay:
+            probe_d = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+            probe_h = _capi.pinned_pool.empty((256 << 20,), np.uint8)
+            probe_t = torch.from_numpy(probe_h)
+            probe_t.copy_(probe_d, non_blocking=True)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(4):
+                probe_t.copy_(probe_d, non_blocking=True)
+            torch.cuda.synchronize(device)
+            my_rate = 4 * (256 << 20) / (time.perf_counter() - t0) / 1e9
+            rates_t = [torch.zeros(1, dtype=torch.float64, device=device) for _ in range(world)]
+            dist.all_gather(rates_t, torch.tensor([my_rate], dtype=torch.float64, device=device))
+            rates = [float(r.item()) for r in rates_t]
+            del probe_d, probe_t, probe_h
+            fast = [r for r in range(world) if rates[r] >= 0.8 * max(rates)]
+            slow = [r for r in range(world) if r not in fast]
+            relay_of = {r: fast[i % len(fast)] for i, r in enumerate(slow)}
+            relay_info = {"d2h_gbs_per_rank_all_copying": [round(r, 1) for r in rates],
+                          "relay_of_rank": {str(k): v for k, v in relay_of.items()},
+                          "how": "ranks whose concurrent pinned D2H rate is < 0.8 x the best send their results over NVLink to a "
+                                 "staging buffer on a fast-port GPU and copy to the host from there (gtp_set_d2h_relay)"
+                                 if slow else "all ports within 20 % of each other: no relay"}
+            if slow:
+                _capi.set_d2h_relay(relay_of.get(rank))
+                res = public_api(*h_in)
+                del res
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(e2e_steps):
+                    res = public_api(*h_in)
+                    rsum = float(res[0][-1, -1]) + float(res[1][-1, -1])
+                    del res
+                torch.cuda.synchronize(device)
+                rdt = sharding.max_over_ranks(time.perf_counter() - t0, dist if world > 1 else None)
+                relay_info.update({"value": e2e_px * world * e2e_steps / rdt, "unit": UNIT, "ms_per_step": 1e3 * rdt / e2e_steps,
+                                   "steps": e2e_steps, "checksum_equal": rsum == checksum})
+                relay_on = relay_info["checksum_equal"] and rdt < dt
+                if not relay_on:
+                    _capi.set_d2h_relay(None)
         # the same through the dask-shaped call (lazy inputs, whole-scan blocks, compute), and the float32-out
         # (mod03) and ECEF forms of the call, which move half / 1.5 x the bytes (headline config only)
         extra_e2e = {}
@@ -731,6 +788,15 @@ def run_b200_arm(args, dtype):
                          f"pinned host inputs, pinned host outputs",
                "checksum": checksum}
         e2e.update(extra_e2e)
+        if relay_info is not None:
+            e2e["relay"] = relay_info
+            if "value" in relay_info:
+                e2e["direct"] = {"value": e2e["value"], "ms_per_step": e2e["ms_per_step"]}
+                if relay_on:
+                    e2e["value"], e2e["ms_per_step"] = relay_info["value"], relay_info["ms_per_step"]
+                    e2e["sample"] += ("; device-to-host copies of the slow-port ranks relayed over NVLink (e2e.relay; e2e.direct = "
+                                      "without; e2e.dask / mod03_f32 / ecef measured with the relay on)")
+            _capi.set_d2h_relay(None)
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")

@@ -200,6 +200,16 @@ int gtp_legacy_interp_host_f64(const double* lon, const double* lat, int64_t n_s
  * device memory each) per process for the next call; gtp_trim() frees them. */
 int gtp_trim(void);
 
+/* Device-to-host relay of the host entry points (process-wide; -1 = off, the default).  On a multi-GPU host
+ * whose PCIe root ports are not equally fast, a process may route its results over NVLink through a
+ * staging buffer on `device` (peer access required) and copy them to the host from there:
+ *   kernel on GPU a -> cudaMemcpyPeerAsync a -> `device` -> cudaMemcpyAsync `device` -> host.
+ * Results are bit-identical; only the path of the bytes changes.  Measured on the 8 x B200 hosts of this
+ * pool (profiles/r02_pcie_probe2_n8.txt): GPUs 0-3 get 11 GB/s each and GPUs 4-7 18 GB/s each when all
+ * eight copy at once (118 GB/s), while GPUs 4-7 alone sustain 177 GB/s. */
+int gtp_set_d2h_relay(int device);
+int gtp_get_d2h_relay(void);
+
 /* page-locked host memory for the host entry points */
 int gtp_host_alloc(void** ptr, uint64_t bytes);
 int gtp_host_free(void* ptr);

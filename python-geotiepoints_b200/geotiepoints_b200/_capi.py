@@ -37,6 +37,8 @@ SIGNATURES = {
     "gtp_host_alloc": (_int, [ctypes.POINTER(_vp), ctypes.c_uint64]),
     "gtp_host_free": (_int, [_vp]),
     "gtp_trim": (_int, []),
+    "gtp_set_d2h_relay": (_int, [_int]),
+    "gtp_get_d2h_relay": (_int, []),
 }
 for _suf in ("f32", "f64"):
     SIGNATURES[f"gtp_cviirs_interp_{_suf}"] = (_int, [_vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _int, _vp])
@@ -213,6 +215,12 @@ def trim():
     workers that share the GPU or the host's lockable memory with other frameworks."""
     pinned_pool.trim()
     check(lib().gtp_trim())
+
+
+def set_d2h_relay(device):
+    """Route the device-to-host copies of the numpy paths of this process through GPU ``device`` (NVLink peer copy
+    + D2H from there); ``None`` or -1 switches it off.  See ``gtp_set_d2h_relay`` in include/gtp_b200.h."""
+    check(lib().gtp_set_d2h_relay(-1 if device is None else int(device)))
 
 
 def device_count():

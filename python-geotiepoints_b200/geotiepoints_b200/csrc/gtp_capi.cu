@@ -137,11 +137,73 @@ int64_t chunk_out_bytes()
     return bytes;
 }
 
+// D2H relay (gtp_set_d2h_relay): on multi-GPU hosts whose PCIe root ports are not equally fast (measured on the
+// 8 x B200 boxes of this pool: GPUs 0-3 share ~74 GB/s of device-to-host bandwidth, GPUs 4-7 get 44 GB/s
+// each, and with all eight copying the host takes 118 GB/s in total; profiles/r02_pcie_probe2_n8.txt) a rank
+// may send its results over NVLink to a staging buffer on a GPU with a faster port and copy them to the host
+// from there.  -1 = off.
+std::atomic<int> g_relay_device{-1};
+
 struct HostPipe {
     int device = -1;
     cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr};
     char* scratch[kStreams] = {nullptr, nullptr, nullptr};
     size_t capacity[kStreams] = {0, 0, 0};
+    // relay side: streams, staging buffers and events on the relay device
+    int relay_device = -1;
+    cudaStream_t relay_streams[kStreams] = {nullptr, nullptr, nullptr};
+    char* relay_buf[kStreams] = {nullptr, nullptr, nullptr};
+    size_t relay_cap[kStreams] = {0, 0, 0};
+    cudaEvent_t copied[kStreams] = {nullptr, nullptr, nullptr};      // on the source stream: peer copy done
+    cudaEvent_t drained[kStreams] = {nullptr, nullptr, nullptr};     // on the relay stream: staging buffer read
+    bool drained_valid[kStreams] = {false, false, false};
+
+    // called with the SOURCE device current; leaves it current
+    cudaError_t reserve_relay(int s, size_t bytes, int relay)
+    {
+        cudaError_t e = cudaSuccess;
+        if (relay_device != relay) { destroy_relay(); relay_device = relay; }
+        if (!copied[s]) { e = cudaEventCreateWithFlags(&copied[s], cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+        int can = 0;
+        e = cudaDeviceCanAccessPeer(&can, device, relay);
+        if (e != cudaSuccess) return e;
+        if (!can) return cudaErrorPeerAccessUnsupported;
+        e = cudaDeviceEnablePeerAccess(relay, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+        if (e != cudaSuccess) return e;
+        e = cudaSetDevice(relay);
+        if (e != cudaSuccess) return e;
+        if (!relay_streams[s]) e = cudaStreamCreateWithFlags(&relay_streams[s], cudaStreamNonBlocking);
+        if (e == cudaSuccess && !drained[s]) e = cudaEventCreateWithFlags(&drained[s], cudaEventDisableTiming);
+        if (e == cudaSuccess && relay_cap[s] < bytes) {
+            if (relay_buf[s]) { cudaFree(relay_buf[s]); relay_buf[s] = nullptr; relay_cap[s] = 0; }
+            e = cudaMalloc((void**)&relay_buf[s], bytes);
+            if (e == cudaSuccess) relay_cap[s] = bytes;
+        }
+        const cudaError_t back = cudaSetDevice(device);
+        return e != cudaSuccess ? e : back;
+    }
+    void destroy_relay()
+    {
+        if (relay_device >= 0) {
+            int cur = -1;
+            cudaGetDevice(&cur);
+            if (cudaSetDevice(relay_device) == cudaSuccess) {
+                for (int s = 0; s < kStreams; ++s) {
+                    if (relay_buf[s]) cudaFree(relay_buf[s]);
+                    if (relay_streams[s]) cudaStreamDestroy(relay_streams[s]);
+                    if (drained[s]) cudaEventDestroy(drained[s]);
+                }
+            }
+            cudaGetLastError();
+            if (cur >= 0) cudaSetDevice(cur);
+        }
+        for (int s = 0; s < kStreams; ++s) {
+            relay_buf[s] = nullptr; relay_streams[s] = nullptr; drained[s] = nullptr; relay_cap[s] = 0; drained_valid[s] = false;
+            if (copied[s]) { cudaEventDestroy(copied[s]); copied[s] = nullptr; }
+        }
+        relay_device = -1;
+    }
 
     cudaError_t reserve(int s, size_t bytes)
     {
@@ -157,6 +219,7 @@ struct HostPipe {
     }
     void destroy()
     {
+        destroy_relay();
         for (int s = 0; s < kStreams; ++s) {
             if (scratch[s]) cudaFree(scratch[s]);
             if (streams[s]) cudaStreamDestroy(streams[s]);
@@ -227,10 +290,14 @@ int host_pipeline_n(const void* const* in, const size_t* in_bytes, int n_in, voi
     HostPipe* pipe = acquire_pipe(current);
     void* d_in[kStreams][kMaxInputs] = {};
     void* d_out[kStreams][kMaxOutputs] = {};
+    int relay = g_relay_device.load(std::memory_order_relaxed);
+    if (relay == current) relay = -1;
+    if (relay < 0 && pipe->relay_device >= 0) pipe->destroy_relay();
     for (int s = 0; s < n_streams; ++s) {
         GTP_CUDA_TRY(pipe->reserve(s, in_off[n_in] + n_out * out_chunk), "scratch alloc");
         for (int a = 0; a < n_in; ++a) d_in[s][a] = pipe->scratch[s] + in_off[a];
         for (int a = 0; a < n_out; ++a) d_out[s][a] = pipe->scratch[s] + in_off[n_in] + a * out_chunk;
+        if (relay >= 0) GTP_CUDA_TRY(pipe->reserve_relay(s, n_out * out_chunk, relay), "D2H relay set-up");
     }
     for (int64_t k = 0; k < n_chunks; ++k) {
         const int s = (int)(k % n_streams);
@@ -241,15 +308,39 @@ int host_pipeline_n(const void* const* in, const size_t* in_bytes, int n_in, voi
                                          cudaMemcpyHostToDevice, st), "H2D");
         status = launch(d_in[s], d_out[s], ns, st);
         if (status != GTP_OK) goto done;
-        for (int a = 0; a < n_out; ++a)
-            GTP_CUDA_TRY(cudaMemcpyAsync((char*)out[a] + (size_t)s0 * out_bytes, d_out[s][a], (size_t)ns * out_bytes,
-                                         cudaMemcpyDeviceToHost, st), "D2H");
+        if (relay < 0) {
+            for (int a = 0; a < n_out; ++a)
+                GTP_CUDA_TRY(cudaMemcpyAsync((char*)out[a] + (size_t)s0 * out_bytes, d_out[s][a], (size_t)ns * out_bytes,
+                                             cudaMemcpyDeviceToHost, st), "D2H");
+        } else {
+            // results -> staging buffer on the relay GPU over NVLink (ordered on this stream), then, on the relay
+            // GPU's stream, staging buffer -> host; the staging buffer is free again when `drained` fires
+            if (pipe->drained_valid[s]) GTP_CUDA_TRY(cudaStreamWaitEvent(st, pipe->drained[s], 0), "relay wait");
+            for (int a = 0; a < n_out; ++a)
+                GTP_CUDA_TRY(cudaMemcpyPeerAsync(pipe->relay_buf[s] + a * out_chunk, relay, d_out[s][a], current,
+                                                 (size_t)ns * out_bytes, st), "peer copy to the relay GPU");
+            GTP_CUDA_TRY(cudaEventRecord(pipe->copied[s], st), "relay event");
+            GTP_CUDA_TRY(cudaSetDevice(relay), "relay device");
+            cudaError_t re = cudaStreamWaitEvent(pipe->relay_streams[s], pipe->copied[s], 0);
+            for (int a = 0; a < n_out && re == cudaSuccess; ++a)
+                re = cudaMemcpyAsync((char*)out[a] + (size_t)s0 * out_bytes, pipe->relay_buf[s] + a * out_chunk,
+                                     (size_t)ns * out_bytes, cudaMemcpyDeviceToHost, pipe->relay_streams[s]);
+            if (re == cudaSuccess) re = cudaEventRecord(pipe->drained[s], pipe->relay_streams[s]);
+            const cudaError_t back = cudaSetDevice(current);
+            GTP_CUDA_TRY(re, "D2H from the relay GPU");
+            GTP_CUDA_TRY(back, "relay device");
+            pipe->drained_valid[s] = true;
+        }
     }
 done:
     bool healthy = true;
     for (int s = 0; s < kStreams; ++s) {
         if (!pipe->streams[s]) continue;
         cudaError_t e = cudaStreamSynchronize(pipe->streams[s]);
+        if (e == cudaSuccess && pipe->relay_streams[s]) {
+            e = cudaStreamSynchronize(pipe->relay_streams[s]);      // a stream handle carries its device
+            pipe->drained_valid[s] = false;
+        }
         if (e != cudaSuccess) {
             healthy = false;
             if (status == GTP_OK) status = cuda_fail(e, "pipeline sync");
@@ -767,6 +858,19 @@ int gtp_legacy_interp_host_f64(const double* lon, const double* lat, int64_t n_s
             return legacy_device(d_in[0], d_in[1], ns, kind, d_lon, d_lat, -1, (void*)st);
         });
 }
+
+int gtp_set_d2h_relay(int device)
+{
+    if (device >= 0) {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return fail(GTP_E_NO_DEVICE, "no usable CUDA device%s"); }
+        if (device >= n) return fail(GTP_E_SHAPE, "gtp_set_d2h_relay: no such device%s");
+    }
+    g_relay_device.store(device < 0 ? -1 : device, std::memory_order_relaxed);
+    return GTP_OK;
+}
+
+int gtp_get_d2h_relay(void) { return g_relay_device.load(std::memory_order_relaxed); }
 
 int gtp_trim(void)
 {
