@@ -82,3 +82,19 @@ with np.errstate(all="ignore"):
     report("mod03 1km->250m f32+i16 -> f64", mod03.modis_1km_to_250m(*f, zen, zenith_scale=0.01, out_dtype=np.float64), exp)
     report("mod03 1km->250m f32+i16 -> f32", mod03.modis_1km_to_250m(*f, zen, zenith_scale=0.01),
            tuple(x.astype(np.float32) for x in exp))
+    # the legacy spline interpolators against the numpy restatement (oracle/legacy_oracle.py)
+    import legacy_oracle
+    from geotiepoints_b200 import legacy
+    report("legacy 1km->250m float64", legacy.modis1kmto250m(lon, lat), legacy_oracle.interpolate(lon, lat, "1km_250m"))
+    report("legacy 1km->500m float64", legacy.modis1kmto500m(lon, lat), legacy_oracle.interpolate(lon, lat, "1km_500m"))
+    subs = [testing.modis_granule(g) for g in range(0, 288, 24)]
+    l5 = [np.ascontiguousarray(np.concatenate([s[k][2::5, 2::5] for s in subs])) for k in range(2)]
+    report("legacy 5km->1km float64", legacy.modis5kmto1km(*l5), legacy_oracle.interpolate(*l5, "5km_1km"))
+    # exact-equality counts of the float32 paths (the verdict's "array_equal" question): pixels that differ at all
+    for fine, fn in ((250, modisinterpolator.modis_1km_to_250m), (500, modisinterpolator.modis_1km_to_500m)):
+        a = [x.astype(np.float32) for x in (lon, lat, satz)]
+        got, exp = fn(*a), gtp_oracle.cviirs(*a, 1000, fine, 0, n_threads=16)
+        nd = int(((got[0] != exp[0]) | (got[1] != exp[1])).sum())
+        d = np.maximum(np.abs(got[0].astype(np.float64) - exp[0]), np.abs(got[1].astype(np.float64) - exp[1]))
+        print(f"cviirs 1km->{fine}m float32: {nd} of {got[0].size} pixels differ from the oracle at all "
+              f"({nd / got[0].size:.2e}); of those beyond 1e-6 deg: {int((d > 1e-6).sum())}, max {d.max():.3g} deg", flush=True)
