@@ -827,6 +827,16 @@ int legacy_device(const double* lon, const double* lat, int64_t n_scans, int kin
     if (!lon || !lat || !out_lon || !out_lat) return fail(GTP_E_NULL, "null buffer%s");
     DeviceGuard guard(device);
     if (guard.err != cudaSuccess) { cudaGetLastError(); return fail(GTP_E_NO_DEVICE, "no usable CUDA device: %s", cudaGetErrorString(guard.err)); }
+    // stream-ordered scratch from the device's default pool; keep freed blocks in the pool (the default gives
+    // them back at every synchronisation and a cudaMalloc of a few GB costs more than the kernels) - gtp_trim()
+    // empties it again
+    int cur = -1;
+    cudaMemPool_t pool = nullptr;
+    if (cudaGetDevice(&cur) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, cur) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
     void* ws = nullptr;
     cudaError_t e = cudaMallocAsync(&ws, gtp_legacy_workspace_bytes(kind, n_scans), (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "legacy workspace");
@@ -834,7 +844,7 @@ int legacy_device(const double* lon, const double* lat, int64_t n_scans, int kin
     const cudaError_t ef = cudaFreeAsync(ws, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "legacy launch");
     if (ef != cudaSuccess) return cuda_fail(ef, "legacy workspace free");
-    g_launches.fetch_add(3, std::memory_order_relaxed);
+    g_launches.fetch_add(4, std::memory_order_relaxed);
     return GTP_OK;
 }
 }  // namespace
@@ -880,6 +890,16 @@ int gtp_trim(void)
         pipes.swap(g_idle_pipes);
     }
     int status = GTP_OK;
+    {   // the stream-ordered scratch of the legacy interpolators (default pool of every device)
+        int n = 0, cur = -1;
+        if (cudaGetDeviceCount(&n) == cudaSuccess && cudaGetDevice(&cur) == cudaSuccess) {
+            for (int d = 0; d < n; ++d) {
+                cudaMemPool_t pool = nullptr;
+                if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+            }
+        }
+        cudaGetLastError();
+    }
     for (HostPipe* p : pipes) {
         DeviceGuard guard(p->device);
         if (guard.err != cudaSuccess) { cudaGetLastError(); status = fail(GTP_E_NO_DEVICE, "no usable CUDA device: %s", cudaGetErrorString(guard.err)); }

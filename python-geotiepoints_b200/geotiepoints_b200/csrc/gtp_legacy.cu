@@ -12,22 +12,24 @@
 // Everything but the column spline is linear in the data with weights that do not depend on the column, so
 // the border rows are never formed: a fine row is the linear blend (inside the scan) or extrapolation
 // (above the first / below the last tie row of the scan) of two of the scan's tie rows, applied AFTER the
-// column spline.  Three launches per call:
+// column spline.  Four launches per call:
 //   1. legacy_coef_kernel (one thread): the forward-elimination coefficients of the not-a-knot tridiagonal
 //      system - they depend on the column positions only;
-//   2. legacy_rows_kernel: one thread per (tie row, Cartesian component): xyz of the row incl. the border
-//      column(s), then the Thomas algorithm for the second derivatives M.  1355 dependent steps per thread;
-//      the whole pass moves 48 B per tie point (3 B per 250 m output pixel) and is latency-, not
-//      bandwidth-bound: ~60 us whatever the batch size up to ~40 granules;
+//   2. legacy_xyz_kernel: lon / lat -> xyz of every tie point into Y[component][point][tie row] (32 x 32 tiles
+//      through shared memory: coalesced on both sides); legacy_thomas_kernel: one thread per (component, tie
+//      row): the border column(s), then the Thomas algorithm for the second derivatives M - ~2700 dependent
+//      steps per thread, neighbouring threads on neighbouring addresses.  48 B per tie point (3 B per 250 m
+//      output pixel); latency-, not bandwidth-bound;
 //   3. legacy_eval_kernel: one thread per (scan, fine column): walks down the scan's tie rows, evaluates
 //      the cubic of its column interval per tie row (y, M of the two interval ends: loads that a warp shares),
 //      blends / extrapolates along the rows and back-transforms with the reference's formulas
 //      (geointerpolator.py:63-75).  Coalesced 8-byte stores, 256 B per warp and output array.
-// The back-transform is the rounding-faithful one (library acos / asin / sqrt, ~370 FP64-pipe slots per
-// pixel): this first version is FP64-bound like gtp_generic.cu, not HBM-bound.
+// The back-transform is anchor-relative (legacy_backtransform_fast below; the reference's formulas with
+// library acos / asin / sqrt only next to the poles and for out-of-range anchors).
 #include <cuda_runtime.h>
 #include <math.h>
 #include "gtp_kernels.h"
+#include "gtp_fast_math.cuh"
 
 namespace {
 
@@ -96,65 +98,103 @@ __global__ void legacy_coef_kernel(double* __restrict__ coef, int kind)
     }
 }
 
-// one thread per (tie row, component): Y[row][comp][n] and M[row][comp][n]
+// Layout of the scratch arrays Y (Cartesian tie points incl. the border columns) and M (second derivatives):
+// [component][spline point][tie row], tie row fastest - the tridiagonal solves walk along the spline points
+// with one thread per tie row, so neighbouring threads touch neighbouring addresses.
+__device__ __forceinline__ long long ym_index(int comp, int point, long long row, int n, long long n_rows)
+{
+    return ((long long)comp * n + point) * n_rows + row;
+}
+
+// lonlat2xyz (geointerpolator.py:52-60) of every tie point; 32 x 32 tiles through shared memory so that both
+// the row-major reads of lon / lat and the row-fastest writes of Y are coalesced
+__global__ void __launch_bounds__(256)
+legacy_xyz_kernel(const double* __restrict__ lon, const double* __restrict__ lat, double* __restrict__ Y,
+                  long long n_rows, int kind)
+{
+    const LegacyGeom g = legacy_geom(kind);
+    __shared__ double tile[3][32][33];
+    const int tiles_x = (g.W + 31) / 32;
+    const long long tile_y = blockIdx.x / tiles_x;
+    const int col0 = (int)(blockIdx.x - tile_y * tiles_x) * 32;
+    const long long row0 = tile_y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const long long row = row0 + ty + 8 * k;
+        const int col = col0 + tx;
+        if (row < n_rows && col < g.W) {
+            const double lo = lon[row * g.W + col] * GTP_DEG2RAD, la = lat[row * g.W + col] * GTP_DEG2RAD;
+            double sl, cl, sp, cp;
+            sincos(lo, &sl, &cl);
+            sincos(la, &sp, &cp);
+            const double rc = kR * cp;
+            tile[0][tx][ty + 8 * k] = rc * cl;
+            tile[1][tx][ty + 8 * k] = rc * sl;
+            tile[2][tx][ty + 8 * k] = kR * sp;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int col = col0 + ty + 8 * k;
+        const long long row = row0 + tx;
+        if (row < n_rows && col < g.W) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) Y[ym_index(c, col + g.first, row, g.n, n_rows)] = tile[c][ty + 8 * k][tx];
+        }
+    }
+}
+
+// one thread per (component, tie row): the border columns, then the Thomas algorithm for M
 __global__ void __launch_bounds__(128)
-legacy_rows_kernel(const double* __restrict__ lon, const double* __restrict__ lat, const double* __restrict__ coef,
-                   double* __restrict__ Y, double* __restrict__ M, long long n_rows, int kind)
+legacy_thomas_kernel(const double* __restrict__ coef, double* __restrict__ Y, double* __restrict__ M,
+                     long long n_rows, int kind)
 {
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t >= n_rows * 3) return;
     const LegacyGeom g = legacy_geom(kind);
-    const long long row = t / 3;
-    const int comp = (int)(t - row * 3);
-    const int n = g.n, m = n - 2, W = g.W;
-    const double* plon = lon + row * W;
-    const double* plat = lat + row * W;
-    double* y = Y + t * n;
-    double* mm = M + t * n;
-    // pass 0: lonlat2xyz (geointerpolator.py:52-60), this thread's component only
-    for (int c = 0; c < W; ++c) {
-        const double lo = plon[c] * GTP_DEG2RAD, la = plat[c] * GTP_DEG2RAD;
-        double v;
-        if (comp == 2) v = kR * sin(la);
-        else {
-            const double rc = kR * cos(la);
-            v = (comp == 0) ? rc * cos(lo) : rc * sin(lo);
-        }
-        y[c + g.first] = v;
-    }
+    const int comp = (int)(t / n_rows);
+    const long long row = t - (long long)comp * n_rows;
+    const int n = g.n, m = n - 2;
+    double* y = Y + ym_index(comp, 0, row, n, n_rows);
+    double* mm = M + ym_index(comp, 0, row, n, n_rows);
+    const long long st = n_rows;                                   // stride between consecutive spline points
     // border columns (interpolator.py:100-148, _linear_extrapolate :33-51)
     if (g.first) {
         const double p0 = aug_col(g, 1), p1 = aug_col(g, 2), x = aug_col(g, 0);
-        y[0] = y[2] + (x - p1) / (p0 - p1) * (y[1] - y[2]);
+        y[0] = y[2 * st] + (x - p1) / (p0 - p1) * (y[st] - y[2 * st]);
     }
     {
         const double p0 = aug_col(g, n - 3), p1 = aug_col(g, n - 2), x = aug_col(g, n - 1);
-        y[n - 1] = y[n - 2] + (x - p1) / (p0 - p1) * (y[n - 3] - y[n - 2]);
+        y[(n - 1) * st] = y[(n - 2) * st] + (x - p1) / (p0 - p1) * (y[(n - 3) * st] - y[(n - 2) * st]);
     }
     // Thomas algorithm: forward elimination (dp kept in mm[1 .. m]), back substitution
     const double* cp = coef;
     const double* iden = coef + m;
     const double* low = coef + 2 * m;
-    double y0 = y[0], y1 = y[1], dp_prev = 0.0;
+    double y0 = y[0], y1 = y[st], dp_prev = 0.0;
     double x0 = aug_col(g, 0), x1 = aug_col(g, 1);
+#pragma unroll 4
     for (int k = 0; k < m; ++k) {
-        const double y2 = y[k + 2], x2 = aug_col(g, k + 2);
+        const double y2 = y[(k + 2) * st], x2 = aug_col(g, k + 2);
         const double rhs = 6.0 * ((y2 - y1) / (x2 - x1) - (y1 - y0) / (x1 - x0));
         const double dp = (rhs - low[k] * dp_prev) * iden[k];
-        mm[k + 1] = dp;
+        mm[(k + 1) * st] = dp;
         dp_prev = dp; y0 = y1; y1 = y2; x0 = x1; x1 = x2;
     }
-    double u_next = mm[m];                      // M_{n-2}
+    double u_next = mm[m * st];                 // M_{n-2}
+#pragma unroll 4
     for (int k = m - 2; k >= 0; --k) {
-        const double u = mm[k + 1] - cp[k] * u_next;
-        mm[k + 1] = u;
+        const double u = mm[(k + 1) * st] - cp[k] * u_next;
+        mm[(k + 1) * st] = u;
         u_next = u;
     }
     {
         const double h0 = aug_col(g, 1) - aug_col(g, 0), h1 = aug_col(g, 2) - aug_col(g, 1);
-        mm[0] = ((h0 + h1) * mm[1] - h0 * mm[2]) / h1;
+        mm[0] = ((h0 + h1) * mm[st] - h0 * mm[2 * st]) / h1;
         const double g0 = aug_col(g, n - 1) - aug_col(g, n - 2), g1 = aug_col(g, n - 2) - aug_col(g, n - 3);
-        mm[n - 1] = ((g0 + g1) * mm[n - 2] - g0 * mm[n - 3]) / g1;
+        mm[(n - 1) * st] = ((g0 + g1) * mm[(n - 2) * st] - g0 * mm[(n - 3) * st]) / g1;
     }
 }
 
@@ -172,9 +212,90 @@ __device__ __forceinline__ void legacy_backtransform(double x, double y, double 
     }
 }
 
+// Anchor-relative back-transform (the idea of gtp_fast_math.cuh, here from a displacement): every fine pixel
+// lies within ~1.5 tie intervals of a tie point A whose lon / lat are INPUTS.  With (e, h) the displacement
+// in A's horizontal frame scaled by 1 / rho_A and dz the one along the polar axis:
+//   lon = lon_A + atan(e / (1 + h)),   lat = lat_A + series in dz / R (|z| < 0.8 R) or in rho / rho_A - 1.
+// ~30 FP64 instructions per pixel instead of ~370 for acos / asin / sqrt / two divisions, accurate to
+// ~1e-13 deg while |e|, |h| <= 0.01 and |dz| / R <= 2e-3 (checked per pixel; beyond that - next to the poles -
+// and for anchors outside [-180, 180] x [-90, 90] the reference's formulas are evaluated as they are).
+struct LegacyAnchor {
+    double x, y, z, ue0, ue1, lon0, lat0;
+    double a1, a2, a3, a4, a5;          // latitude series in dz (metres), low latitudes
+    double b1, b2, b3, b4, b5;          // ... in v = rho / rho_A - 1, high latitudes
+    bool ok, low, high;
+};
+
+__device__ __forceinline__ LegacyAnchor legacy_anchor(double lon, double lat, double x, double y, double z)
+{
+    using namespace gtpfast;
+    LegacyAnchor a;
+    a.x = x; a.y = y; a.z = z; a.lon0 = lon; a.lat0 = lat;
+    double ir;
+    const double rho = fast_sqrt_rsqrt(fma(x, x, y * y), ir);
+    const double cl = x * ir, sl = y * ir;
+    a.ue0 = -sl * ir; a.ue1 = cl * ir;
+    const double s = z * kInvEarthR, c = rho * kInvEarthR;            // sin / cos of the latitude of A
+    a.ok = (fabs(lon) <= 180.0) && (fabs(lat) <= 90.0) && (c > 1e-6);
+    a.low = fabs(s) < 0.81; a.high = fabs(s) > 0.79;
+    a.a1 = a.a2 = a.a3 = a.a4 = a.a5 = 0.0;
+    a.b1 = a.b2 = a.b3 = a.b4 = a.b5 = 0.0;
+    const double s2 = s * s, c2 = c * c;
+    if (a.low) {                        // d^k/dz^k of asin(z / R) at z_A, 1 / R^k folded in
+        const double inv_c = kEarthR * ir, ur = inv_c * inv_c * kInvEarthR;
+        double m = inv_c * (kRad2Deg * kInvEarthR);
+        a.a1 = m;
+        m *= ur; a.a2 = 0.5 * s * m;
+        m *= ur; a.a3 = fma(2.0, s2, 1.0) * kSixth * m;
+        m *= ur; a.a4 = s * fma(2.0, s2, 3.0) * 0.125 * m;
+        m *= ur; a.a5 = fma(s2, fma(8.0, s2, 24.0), 3.0) * k1_40 * m;
+    }
+    if (a.high) {                       // sign(z) acos(c (1 + v)) around v = 0; sin|lat_A| = |s|
+        const double sa = fabs(s), inv_s = fast_rcp(sa), u = inv_s * inv_s;
+        const double sign = (z < 0.0) ? -1.0 : 1.0;
+        double m = inv_s * c * (-sign * kRad2Deg);
+        a.b1 = m;
+        m *= u * c; a.b2 = 0.5 * c * m;
+        m *= u * c; a.b3 = fma(2.0, c2, 1.0) * kSixth * m;
+        m *= u * c; a.b4 = c * fma(2.0, c2, 3.0) * 0.125 * m;
+        m *= u * c; a.b5 = fma(c2, fma(8.0, c2, 24.0), 3.0) * k1_40 * m;
+    }
+    return a;
+}
+
+__device__ __forceinline__ void legacy_backtransform_fast(const LegacyAnchor& a, double x, double y, double z,
+                                                          double& lon, double& lat)
+{
+    using namespace gtpfast;
+    const double dx = x - a.x, dy = y - a.y, dz = z - a.z;
+    const double e = fma(a.ue0, dx, a.ue1 * dy);
+    const double h = fma(a.ue1, dx, -a.ue0 * dy);
+    const double nz = z * kInvEarthR;
+    const bool use_low = fabs(nz) < 0.8;                              // the reference's own test (geointerpolator.py:71)
+    const bool fits = a.ok && (fabs(e) <= 0.01) && (fabs(h) <= 0.01) && (fabs(dz) <= 2e-3 * GTP_EARTH_RADIUS)
+                      && (use_low ? a.low : a.high);
+    if (!fits) { legacy_backtransform(x, y, z, lon, lat); return; }
+    const double g = 1.0 + h, h2 = h * h;
+    double rcp = 1.0 - h;                                             // 1 / (1 + h) = (1 - h)(1 + h^2)(1 + h^4) + O(h^8)
+    rcp = fma(h2, rcp, rcp);
+    rcp = fma(h2 * h2, rcp, rcp);
+    const double t = e * rcp, t2 = t * t;
+    const double at = fma(t * t2, fma(t2, fma(t2, -1.0 / 7.0, 0.2), -kThird), t);
+    double lo = fma(at, kRad2Deg, a.lon0);
+    if (lo > 180.0) lo -= 360.0;
+    else if (lo < -180.0) lo += 360.0;
+    lon = lo;
+    if (use_low) lat = fma(dz, fma(dz, fma(dz, fma(dz, fma(dz, a.a5, a.a4), a.a3), a.a2), a.a1), a.lat0);
+    else {
+        const double v = fma(g, t2 * fma(t2, fma(t2, 0.0625, -0.125), 0.5), h);       // rho / rho_A - 1
+        lat = fma(v, fma(v, fma(v, fma(v, fma(v, a.b5, a.b4), a.b3), a.b2), a.b1), a.lat0);
+    }
+}
+
 // one thread per (scan, fine column)
 __global__ void __launch_bounds__(128)
-legacy_eval_kernel(const double* __restrict__ Y, const double* __restrict__ M, double* __restrict__ out_lon,
+legacy_eval_kernel(const double* __restrict__ lon_in, const double* __restrict__ lat_in,
+                   const double* __restrict__ Y, const double* __restrict__ M, double* __restrict__ out_lon,
                    double* __restrict__ out_lat, long long n_scans, int kind)
 {
     const LegacyGeom g = legacy_geom(kind);
@@ -186,8 +307,7 @@ legacy_eval_kernel(const double* __restrict__ Y, const double* __restrict__ M, d
     const int i = col_interval(g, j);
     const double xa = aug_col(g, i), h = aug_col(g, i + 1) - xa, t = fine_col(g, j) - xa;
     const double inv_h = 1.0 / h, h6 = h / 6.0, inv_6h = 1.0 / (6.0 * h);
-    const double* y = Y + (scan * g.L * 3) * n + i;
-    const double* mm = M + (scan * g.L * 3) * n + i;
+    const long long n_rows = n_scans * g.L, row0 = scan * g.L;
     double* olon = out_lon + scan * (long long)g.nf * g.Wf + j;
     double* olat = out_lat + scan * (long long)g.nf * g.Wf + j;
 
@@ -195,8 +315,8 @@ legacy_eval_kernel(const double* __restrict__ Y, const double* __restrict__ M, d
     auto spline_row = [&](int r, double (&v)[3]) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const long long o = ((long long)r * 3 + c) * n;
-            const double y0 = y[o], y1 = y[o + 1], m0 = mm[o], m1 = mm[o + 1];
+            const long long o = ym_index(c, i, row0 + r, n, n_rows);
+            const double y0 = Y[o], y1 = Y[o + n_rows], m0 = M[o], m1 = M[o + n_rows];
             const double b = (y1 - y0) * inv_h - h6 * (2.0 * m0 + m1);
             v[c] = y0 + t * (b + t * (0.5 * m0 + t * ((m1 - m0) * inv_6h)));
         }
@@ -204,10 +324,16 @@ legacy_eval_kernel(const double* __restrict__ Y, const double* __restrict__ M, d
     // fine row jr of the scan sits at tie-row coordinate pos(jr); rows above the first / below the last tie
     // row extrapolate the first / last pair (fill_borders('y'), interpolator.py:150-197)
     const int f = g.nf / g.L;                                       // fine rows per tie row: 5 | 2 | 4
+    // the anchor of a tie-row pair: the tie point at the left end of this column interval in the upper row
+    const int ia = (g.first && i == 0) ? 1 : i;                     // 5 km: the border column is not a tie point
+    const int tie_col = ia - g.first;
     double top[3], bot[3];
     spline_row(0, top);
     int jr = 0;
     for (int r = 0; r + 1 < g.L; ++r) {
+        const long long tie = (scan * g.L + r) * g.W + tie_col;
+        const LegacyAnchor anchor = legacy_anchor(lon_in[tie], lat_in[tie], Y[ym_index(0, ia, row0 + r, n, n_rows)],
+                                                  Y[ym_index(1, ia, row0 + r, n, n_rows)], Y[ym_index(2, ia, row0 + r, n, n_rows)]);
         spline_row(r + 1, bot);
         // tie rows sit at fine-row index r f + off: off = 2 (5 km), 0.5 (500 m), 1.5 (250 m)
         const double off = (g.kind == 0) ? 2.0 : (g.kind == 1 ? 0.5 : 1.5);
@@ -218,7 +344,7 @@ legacy_eval_kernel(const double* __restrict__ Y, const double* __restrict__ M, d
             const double yy = top[1] + w * (bot[1] - top[1]);
             const double z = top[2] + w * (bot[2] - top[2]);
             double lo, la;
-            legacy_backtransform(x, yy, z, lo, la);
+            legacy_backtransform_fast(anchor, x, yy, z, lo, la);
             __stcs(olon + (long long)jr * g.Wf, lo);
             __stcs(olat + (long long)jr * g.Wf, la);
         }
@@ -251,10 +377,13 @@ cudaError_t gtp_launch_legacy_f64(const double* lon, const double* lat, double* 
     double* M = Y + rows * 3 * g.n;
     double* coef = M + rows * 3 * g.n;
     legacy_coef_kernel<<<1, 1, 0, stream>>>(coef, kind);
+    const long long tiles = ((rows + 31) / 32) * ((g.W + 31) / 32);
+    if (tiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    legacy_xyz_kernel<<<(unsigned)tiles, 256, 0, stream>>>(lon, lat, Y, rows, kind);
     const long long threads = rows * 3;
-    legacy_rows_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(lon, lat, coef, Y, M, rows, kind);
+    legacy_thomas_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(coef, Y, M, rows, kind);
     const long long blocks = n_scans * ((g.Wf + 127) / 128);
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    legacy_eval_kernel<<<(unsigned)blocks, 128, 0, stream>>>(Y, M, out_lon, out_lat, n_scans, kind);
+    legacy_eval_kernel<<<(unsigned)blocks, 128, 0, stream>>>(lon, lat, Y, M, out_lon, out_lat, n_scans, kind);
     return cudaGetLastError();
 }
