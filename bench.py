@@ -51,6 +51,10 @@ CONFIGS = {
     # the legacy spline API (geotiepoints.modis1kmto250m / modis5kmto1km), float64, lon + lat only
     "legacy_1km_250m": dict(kind="legacy", code=2, coarse=1000, fine=250, width=0, n_in=2, tie_rows=2030, tie_cols=1354, f=4, out_cols=5416),
     "legacy_5km_1km": dict(kind="legacy", code=0, coarse=5000, fine=1000, width=271, n_in=2, tie_rows=406, tie_cols=271, f=5, out_cols=1354),
+    # VII tie_points_geo_interpolation on Cartesian coordinates; the 1 km lon / lat of the synthetic granules
+    # serve as tie points (10 tie rows per scan, factor 4): (2030, 1354) -> (203 * 9 * 4, 1353 * 4) per granule
+    "vii_geo_cartesian": dict(kind="vii", coarse=1000, fine=250, width=0, n_in=2, tie_rows=2030, tie_cols=1354, f=4, out_cols=5412,
+                              out_rows=203 * 36),
     "mod03_ecef_1km_250m": dict(kind="mixed", ecef=True, coarse=1000, fine=250, width=0, n_in=3, tie_rows=2030, tie_cols=1354, f=4, out_cols=5416),
 }
 TIE_ROWS, TIE_COLS = 2030, 1354
@@ -59,7 +63,7 @@ PX_PER_GRANULE = OUT_ROWS * OUT_COLS
 
 
 def px_per_granule(cfg):
-    return cfg["tie_rows"] * cfg["f"] * cfg["out_cols"]
+    return cfg.get("out_rows", cfg["tie_rows"] * cfg["f"]) * cfg["out_cols"]
 
 
 def algorithmic_bytes_per_px(itemsize, cfg=None):
@@ -316,7 +320,8 @@ def run_reference_arm(args, dtype):
 # ------------------------------------------------------------------------------------
 SECONDARY = [("cviirs_1km_250m", "f32"), ("cviirs_1km_500m", "f64"), ("cviirs_1km_500m", "f32"),
              ("cviirs_5km_1km", "f64"), ("cviirs_5km_1km", "f32"), ("simple_1km_250m", "f64"), ("simple_1km_250m", "f32"),
-             ("simple_1km_500m", "f64"), ("mod03_1km_250m", "f32"), ("legacy_1km_250m", "f64"), ("legacy_5km_1km", "f64")]
+             ("simple_1km_500m", "f64"), ("mod03_1km_250m", "f32"), ("legacy_1km_250m", "f64"), ("legacy_5km_1km", "f64"),
+             ("vii_geo_cartesian", "f64")]
 
 
 def measure_secondary(name, dtype_name, base_in, granules, device, local_rank, peak, steps=5, warmup=3):
@@ -340,7 +345,7 @@ def measure_secondary(name, dtype_name, base_in, granules, device, local_rank, p
         arrs[2] = np.round(base_in[2] / 0.01).astype(np.int16)
     rows_per_scan = 10 if cfg["coarse"] == 1000 else 2
     n_scans = arrs[0].shape[0] // rows_per_scan
-    out_rows_per_scan = rows_per_scan * cfg["f"]
+    out_rows_per_scan = (rows_per_scan - 1) * cfg["f"] if cfg["kind"] == "vii" else rows_per_scan * cfg["f"]
     tdtype = torch.float64 if dtype == np.float64 else torch.float32
     d_in = [torch.from_numpy(a).to(device) for a in arrs]
     outs = [torch.empty((n_scans * out_rows_per_scan, cfg["out_cols"]), dtype=tdtype, device=device) for _ in range(2)]
@@ -355,6 +360,9 @@ def measure_secondary(name, dtype_name, base_in, granules, device, local_rank, p
     elif cfg["kind"] == "legacy":
         def step():
             _capi.check(lib.gtp_legacy_interp_f64(*ptrs, n_scans, cfg["code"], *optrs, local_rank, st))
+    elif cfg["kind"] == "vii":
+        def step():
+            _capi.check(lib.gtp_vii_geo_interp_f64(*ptrs, n_scans * 10, cfg["tie_cols"], 10, cfg["f"], 1, 0.8, *optrs, local_rank, st))
     elif cfg["kind"] == "cviirs":
         fn = getattr(lib, "gtp_cviirs_interp_" + dtype_name)
 
@@ -396,6 +404,10 @@ def measure_secondary(name, dtype_name, base_in, granules, device, local_rank, p
                 exp = gtp_oracle.cviirs(sub[0].astype(np.float64), sub[1].astype(np.float64), sub[2].astype(np.float64) * 0.01,
                                         1000, cfg["fine"], 0, n_threads=8)
                 exp = tuple(a.astype(np.float32) for a in exp)
+            elif cfg["kind"] == "vii":
+                import vii_oracle
+                xyz = vii_oracle.tie_points_interpolation(list(vii_oracle.lonlat2xyz(*sub)), 10, cfg["f"])
+                exp = vii_oracle.xyz2lonlat(*xyz, 0.8)
             elif cfg["kind"] == "legacy":
                 import legacy_oracle
                 exp = legacy_oracle.interpolate(*sub, {0: "5km_1km", 1: "1km_500m", 2: "1km_250m"}[cfg["code"]])
@@ -517,8 +529,8 @@ def run_b200_arm(args, dtype):
         dist.init_process_group("nccl", device_id=device)
 
     cfg = CONFIGS[args.config]
-    if cfg["kind"] == "legacy":
-        raise SystemExit("the legacy_* configurations are measured inside the default run (`secondary`), not as --config")
+    if cfg["kind"] in ("legacy", "vii"):
+        raise SystemExit("the legacy_* / vii_* configurations are measured inside the default run (`secondary`), not as --config")
     headline = args.config == "cviirs_1km_250m"
     mixed = cfg["kind"] == "mixed"
     ecef = bool(cfg.get("ecef"))

@@ -196,6 +196,24 @@ int gtp_legacy_interp_f64(const double* lon, const double* lat, int64_t n_scans,
 int gtp_legacy_interp_host_f64(const double* lon, const double* lat, int64_t n_scans, int kind,
                                double* out_lon, double* out_lat, int device);
 
+/* ---- VII (EPS-SG METimage) tie-point interpolation -----------------------------
+ * Replace geotiepoints.viiinterpolator.tie_points_interpolation (viiinterpolator.py:23-79, one array per
+ * call) and tie_points_geo_interpolation (:83-134).  `data` is (n_tie_alt, n_tie_act) float64, C-contiguous,
+ * n_tie_alt a multiple of scan_alt_tie_points (else GTP_E_SHAPE - the reference's ValueError); the result is
+ * (n_tie_alt / S * (S - 1) * factor, (n_tie_act - 1) * factor).  `cartesian` is the reference's decision
+ * (:108: any |lat| > lat_threshold_use_cartesian or a longitude span > 180 deg), taken by the caller, who has
+ * the arrays; z_threshold = z_threshold_use_xy (:86). */
+int gtp_vii_interp_f64(const double* data, int64_t n_tie_alt, int64_t n_tie_act, int scan_alt_tie_points,
+                       int tie_points_factor, double* out, int device, void* stream);
+int gtp_vii_interp_host_f64(const double* data, int64_t n_tie_alt, int64_t n_tie_act, int scan_alt_tie_points,
+                            int tie_points_factor, double* out, int device);
+int gtp_vii_geo_interp_f64(const double* lon, const double* lat, int64_t n_tie_alt, int64_t n_tie_act,
+                           int scan_alt_tie_points, int tie_points_factor, int cartesian, double z_threshold,
+                           double* out_lon, double* out_lat, int device, void* stream);
+int gtp_vii_geo_interp_host_f64(const double* lon, const double* lat, int64_t n_tie_alt, int64_t n_tie_act,
+                                int scan_alt_tie_points, int tie_points_factor, int cartesian, double z_threshold,
+                                double* out_lon, double* out_lat, int device);
+
 /* The host entry points keep up to 4 idle sets of (3 streams + chunk scratch, ~300 MB of
  * device memory each) per process for the next call; gtp_trim() frees them. */
 int gtp_trim(void);

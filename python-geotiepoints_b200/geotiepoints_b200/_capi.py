@@ -66,6 +66,10 @@ SIGNATURES["gtp_simple_interp_generic_f64"] = SIGNATURES["gtp_simple_interp_f64"
 SIGNATURES["gtp_cviirs_interp_generic_f32"] = SIGNATURES["gtp_cviirs_interp_f32"]
 SIGNATURES["gtp_legacy_interp_f64"] = (_int, [_vp, _vp, _i64, _int, _vp, _vp, _int, _vp])
 SIGNATURES["gtp_legacy_interp_host_f64"] = (_int, [_vp, _vp, _i64, _int, _vp, _vp, _int])
+SIGNATURES["gtp_vii_interp_f64"] = (_int, [_vp, _i64, _i64, _int, _int, _vp, _int, _vp])
+SIGNATURES["gtp_vii_interp_host_f64"] = (_int, [_vp, _i64, _i64, _int, _int, _vp, _int])
+SIGNATURES["gtp_vii_geo_interp_f64"] = (_int, [_vp, _vp, _i64, _i64, _int, _int, _int, _dbl, _vp, _vp, _int, _vp])
+SIGNATURES["gtp_vii_geo_interp_host_f64"] = (_int, [_vp, _vp, _i64, _i64, _int, _int, _int, _dbl, _vp, _vp, _int])
 
 
 class GtpError(RuntimeError):

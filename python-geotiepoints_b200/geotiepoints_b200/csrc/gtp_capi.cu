@@ -818,6 +818,20 @@ int gtp_simple_interp_xyz_mixed_host(const float* lon, const float* lat, int64_t
 
 // ---- legacy spline interpolators ----
 namespace {
+// Stream-ordered scratch (cudaMallocAsync) comes from the current device's default pool; keep freed blocks in
+// the pool: the default gives them back at every synchronisation, and a cudaMalloc of a few GB costs more than
+// the kernels.  gtp_trim() empties the pool again.
+void keep_pooled_scratch()
+{
+    int cur = -1;
+    cudaMemPool_t pool = nullptr;
+    if (cudaGetDevice(&cur) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, cur) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+}
+
 int legacy_device(const double* lon, const double* lat, int64_t n_scans, int kind, double* out_lon, double* out_lat,
                   int device, void* stream)
 {
@@ -827,16 +841,7 @@ int legacy_device(const double* lon, const double* lat, int64_t n_scans, int kin
     if (!lon || !lat || !out_lon || !out_lat) return fail(GTP_E_NULL, "null buffer%s");
     DeviceGuard guard(device);
     if (guard.err != cudaSuccess) { cudaGetLastError(); return fail(GTP_E_NO_DEVICE, "no usable CUDA device: %s", cudaGetErrorString(guard.err)); }
-    // stream-ordered scratch from the device's default pool; keep freed blocks in the pool (the default gives
-    // them back at every synchronisation and a cudaMalloc of a few GB costs more than the kernels) - gtp_trim()
-    // empties it again
-    int cur = -1;
-    cudaMemPool_t pool = nullptr;
-    if (cudaGetDevice(&cur) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, cur) == cudaSuccess) {
-        uint64_t keep = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    cudaGetLastError();
+    keep_pooled_scratch();
     void* ws = nullptr;
     cudaError_t e = cudaMallocAsync(&ws, gtp_legacy_workspace_bytes(kind, n_scans), (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "legacy workspace");
@@ -868,6 +873,83 @@ int gtp_legacy_interp_host_f64(const double* lon, const double* lat, int64_t n_s
             return legacy_device(d_in[0], d_in[1], ns, kind, d_lon, d_lat, -1, (void*)st);
         });
 }
+
+// ---- VII tie-point interpolation ----
+namespace {
+int vii_check(const void* a, const void* out, int64_t n_alt, int64_t n_act, int S, int F)
+{
+    if (S < 2 || F < 1 || n_act < 2 || n_alt < 0) return fail(GTP_E_SHAPE, "VII: need scan_alt_tie_points >= 2, tie_points_factor >= 1, >= 2 tie columns%s");
+    if (n_alt % S != 0) return fail(GTP_E_SHAPE, "The number of tie points in the along-route dimension must be a multiple of scan_alt_tie_points%s");
+    if (n_alt > 0 && (!a || !out)) return fail(GTP_E_NULL, "null buffer%s");
+    return GTP_OK;
+}
+
+// cartesian < 0: one array (b, out_b unused); 0: two arrays interpolated as they are; 1: lon / lat through xyz
+int vii_device(const double* a, const double* b, int64_t n_alt, int64_t n_act, int S, int F, int cartesian, double z_threshold,
+               double* out_a, double* out_b, int device, void* stream)
+{
+    int rc = vii_check(a, out_a, n_alt, n_act, S, F);
+    if (rc != GTP_OK || n_alt == 0) return rc;
+    if (cartesian >= 0 && (!b || !out_b)) return fail(GTP_E_NULL, "null buffer%s");
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) { cudaGetLastError(); return fail(GTP_E_NO_DEVICE, "no usable CUDA device: %s", cudaGetErrorString(guard.err)); }
+    cudaError_t e;
+    if (cartesian == 1) {
+        keep_pooled_scratch();
+        void* ws = nullptr;
+        e = cudaMallocAsync(&ws, gtp_vii_workspace_bytes(n_alt, n_act), (cudaStream_t)stream);
+        if (e != cudaSuccess) return cuda_fail(e, "VII workspace");
+        e = gtp_launch_vii_geo_cartesian(a, b, out_a, out_b, n_alt, n_act, S, F, z_threshold, ws, (cudaStream_t)stream);
+        cudaFreeAsync(ws, (cudaStream_t)stream);
+        g_launches.fetch_add(2, std::memory_order_relaxed);
+    } else {
+        e = gtp_launch_vii_interp(a, cartesian < 0 ? nullptr : b, out_a, cartesian < 0 ? nullptr : out_b, n_alt, n_act, S, F, (cudaStream_t)stream);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "VII launch");
+    return GTP_OK;
+}
+
+int vii_host(const double* a, const double* b, int64_t n_alt, int64_t n_act, int S, int F, int cartesian, double z_threshold,
+             double* out_a, double* out_b, int device)
+{
+    int rc = vii_check(a, out_a, n_alt, n_act, S, F);
+    if (rc != GTP_OK || n_alt == 0) return rc;
+    if (cartesian >= 0 && (!b || !out_b)) return fail(GTP_E_NULL, "null buffer%s");
+    const int64_t n_scans = n_alt / S, in_per_scan = (int64_t)S * n_act, out_per_scan = (int64_t)(S - 1) * F * (n_act - 1) * F;
+    if (cartesian < 0) {
+        const void* in_v[1] = {a};
+        const size_t in_b[1] = {(size_t)in_per_scan * 8};
+        void* const out_v[1] = {out_a};
+        return host_pipeline_n(in_v, in_b, 1, out_v, 1, (size_t)out_per_scan * 8, n_scans, device,
+            [&](void* const* d_in, void* const* d_out, int64_t ns, cudaStream_t st) {
+                return vii_device((const double*)d_in[0], nullptr, ns * S, n_act, S, F, -1, z_threshold, (double*)d_out[0], nullptr, -1, (void*)st);
+            });
+    }
+    const double* const in[2] = {a, b};
+    return host_pipeline<double, 2>(in, out_a, out_b, n_scans, in_per_scan, out_per_scan, device,
+        [&](double* const* d_in, double* d_a, double* d_b, int64_t ns, cudaStream_t st) {
+            return vii_device(d_in[0], d_in[1], ns * S, n_act, S, F, cartesian, z_threshold, d_a, d_b, -1, (void*)st);
+        });
+}
+}  // namespace
+
+int gtp_vii_interp_f64(const double* data, int64_t n_tie_alt, int64_t n_tie_act, int scan_alt_tie_points, int tie_points_factor,
+                       double* out, int device, void* stream)
+{ return vii_device(data, nullptr, n_tie_alt, n_tie_act, scan_alt_tie_points, tie_points_factor, -1, 0.8, out, nullptr, device, stream); }
+
+int gtp_vii_interp_host_f64(const double* data, int64_t n_tie_alt, int64_t n_tie_act, int scan_alt_tie_points, int tie_points_factor,
+                            double* out, int device)
+{ return vii_host(data, nullptr, n_tie_alt, n_tie_act, scan_alt_tie_points, tie_points_factor, -1, 0.8, out, nullptr, device); }
+
+int gtp_vii_geo_interp_f64(const double* lon, const double* lat, int64_t n_tie_alt, int64_t n_tie_act, int scan_alt_tie_points,
+                           int tie_points_factor, int cartesian, double z_threshold, double* out_lon, double* out_lat,
+                           int device, void* stream)
+{ return vii_device(lon, lat, n_tie_alt, n_tie_act, scan_alt_tie_points, tie_points_factor, cartesian ? 1 : 0, z_threshold, out_lon, out_lat, device, stream); }
+
+int gtp_vii_geo_interp_host_f64(const double* lon, const double* lat, int64_t n_tie_alt, int64_t n_tie_act, int scan_alt_tie_points,
+                                int tie_points_factor, int cartesian, double z_threshold, double* out_lon, double* out_lat, int device)
+{ return vii_host(lon, lat, n_tie_alt, n_tie_act, scan_alt_tie_points, tie_points_factor, cartesian ? 1 : 0, z_threshold, out_lon, out_lat, device); }
 
 int gtp_set_d2h_relay(int device)
 {

@@ -66,3 +66,11 @@ size_t gtp_legacy_workspace_bytes(int kind, long long n_scans);
 void gtp_legacy_shape(int kind, int* tie_rows_per_scan, int* tie_cols, int* fine_rows_per_scan, int* fine_cols);
 cudaError_t gtp_launch_legacy_f64(const double* lon, const double* lat, double* out_lon, double* out_lat,
                                   long long n_scans, int kind, void* workspace, cudaStream_t stream);
+
+// gtp_vii.cu: VII tie-point interpolation (geotiepoints/viiinterpolator.py), float64
+size_t gtp_vii_workspace_bytes(long long n_alt, long long n_act);
+cudaError_t gtp_launch_vii_interp(const double* a, const double* b, double* out_a, double* out_b,
+                                  long long n_alt, long long n_act, int S, int F, cudaStream_t stream);
+cudaError_t gtp_launch_vii_geo_cartesian(const double* lon, const double* lat, double* out_lon, double* out_lat,
+                                         long long n_alt, long long n_act, int S, int F, double z_threshold,
+                                         void* workspace, cudaStream_t stream);
