@@ -29,7 +29,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include "gtp_kernels.h"
-#include "gtp_fast_math.cuh"
+#include "gtp_anchor_bt.cuh"
 
 namespace {
 
@@ -198,100 +198,6 @@ legacy_thomas_kernel(const double* __restrict__ coef, double* __restrict__ Y, do
     }
 }
 
-// xyz -> lon / lat as geointerpolator.py:63-75 (thr = 0.8)
-__device__ __forceinline__ void legacy_backtransform(double x, double y, double z, double& lon, double& lat)
-{
-    const double rho = sqrt(x * x + y * y);
-    const double sy = (y > 0.0) ? 1.0 : ((y < 0.0) ? -1.0 : ((y == 0.0) ? 0.0 : y));
-    lon = (acos(x / rho) * GTP_RAD2DEG) * sy;
-    const double nz = z / kR;
-    if (fabs(nz) < 0.8) lat = 90.0 - acos(nz) * GTP_RAD2DEG;
-    else {
-        const double sz = (z > 0.0) ? 1.0 : ((z < 0.0) ? -1.0 : ((z == 0.0) ? 0.0 : z));
-        lat = sz * (90.0 - asin(rho / kR) * GTP_RAD2DEG);
-    }
-}
-
-// Anchor-relative back-transform (the idea of gtp_fast_math.cuh, here from a displacement): every fine pixel
-// lies within ~1.5 tie intervals of a tie point A whose lon / lat are INPUTS.  With (e, h) the displacement
-// in A's horizontal frame scaled by 1 / rho_A and dz the one along the polar axis:
-//   lon = lon_A + atan(e / (1 + h)),   lat = lat_A + series in dz / R (|z| < 0.8 R) or in rho / rho_A - 1.
-// ~30 FP64 instructions per pixel instead of ~370 for acos / asin / sqrt / two divisions, accurate to
-// ~1e-13 deg while |e|, |h| <= 0.01 and |dz| / R <= 2e-3 (checked per pixel; beyond that - next to the poles -
-// and for anchors outside [-180, 180] x [-90, 90] the reference's formulas are evaluated as they are).
-struct LegacyAnchor {
-    double x, y, z, ue0, ue1, lon0, lat0;
-    double a1, a2, a3, a4, a5;          // latitude series in dz (metres), low latitudes
-    double b1, b2, b3, b4, b5;          // ... in v = rho / rho_A - 1, high latitudes
-    bool ok, low, high;
-};
-
-__device__ __forceinline__ LegacyAnchor legacy_anchor(double lon, double lat, double x, double y, double z)
-{
-    using namespace gtpfast;
-    LegacyAnchor a;
-    a.x = x; a.y = y; a.z = z; a.lon0 = lon; a.lat0 = lat;
-    double ir;
-    const double rho = fast_sqrt_rsqrt(fma(x, x, y * y), ir);
-    const double cl = x * ir, sl = y * ir;
-    a.ue0 = -sl * ir; a.ue1 = cl * ir;
-    const double s = z * kInvEarthR, c = rho * kInvEarthR;            // sin / cos of the latitude of A
-    a.ok = (fabs(lon) <= 180.0) && (fabs(lat) <= 90.0) && (c > 1e-6);
-    a.low = fabs(s) < 0.81; a.high = fabs(s) > 0.79;
-    a.a1 = a.a2 = a.a3 = a.a4 = a.a5 = 0.0;
-    a.b1 = a.b2 = a.b3 = a.b4 = a.b5 = 0.0;
-    const double s2 = s * s, c2 = c * c;
-    if (a.low) {                        // d^k/dz^k of asin(z / R) at z_A, 1 / R^k folded in
-        const double inv_c = kEarthR * ir, ur = inv_c * inv_c * kInvEarthR;
-        double m = inv_c * (kRad2Deg * kInvEarthR);
-        a.a1 = m;
-        m *= ur; a.a2 = 0.5 * s * m;
-        m *= ur; a.a3 = fma(2.0, s2, 1.0) * kSixth * m;
-        m *= ur; a.a4 = s * fma(2.0, s2, 3.0) * 0.125 * m;
-        m *= ur; a.a5 = fma(s2, fma(8.0, s2, 24.0), 3.0) * k1_40 * m;
-    }
-    if (a.high) {                       // sign(z) acos(c (1 + v)) around v = 0; sin|lat_A| = |s|
-        const double sa = fabs(s), inv_s = fast_rcp(sa), u = inv_s * inv_s;
-        const double sign = (z < 0.0) ? -1.0 : 1.0;
-        double m = inv_s * c * (-sign * kRad2Deg);
-        a.b1 = m;
-        m *= u * c; a.b2 = 0.5 * c * m;
-        m *= u * c; a.b3 = fma(2.0, c2, 1.0) * kSixth * m;
-        m *= u * c; a.b4 = c * fma(2.0, c2, 3.0) * 0.125 * m;
-        m *= u * c; a.b5 = fma(c2, fma(8.0, c2, 24.0), 3.0) * k1_40 * m;
-    }
-    return a;
-}
-
-__device__ __forceinline__ void legacy_backtransform_fast(const LegacyAnchor& a, double x, double y, double z,
-                                                          double& lon, double& lat)
-{
-    using namespace gtpfast;
-    const double dx = x - a.x, dy = y - a.y, dz = z - a.z;
-    const double e = fma(a.ue0, dx, a.ue1 * dy);
-    const double h = fma(a.ue1, dx, -a.ue0 * dy);
-    const double nz = z * kInvEarthR;
-    const bool use_low = fabs(nz) < 0.8;                              // the reference's own test (geointerpolator.py:71)
-    const bool fits = a.ok && (fabs(e) <= 0.01) && (fabs(h) <= 0.01) && (fabs(dz) <= 2e-3 * GTP_EARTH_RADIUS)
-                      && (use_low ? a.low : a.high);
-    if (!fits) { legacy_backtransform(x, y, z, lon, lat); return; }
-    const double g = 1.0 + h, h2 = h * h;
-    double rcp = 1.0 - h;                                             // 1 / (1 + h) = (1 - h)(1 + h^2)(1 + h^4) + O(h^8)
-    rcp = fma(h2, rcp, rcp);
-    rcp = fma(h2 * h2, rcp, rcp);
-    const double t = e * rcp, t2 = t * t;
-    const double at = fma(t * t2, fma(t2, fma(t2, -1.0 / 7.0, 0.2), -kThird), t);
-    double lo = fma(at, kRad2Deg, a.lon0);
-    if (lo > 180.0) lo -= 360.0;
-    else if (lo < -180.0) lo += 360.0;
-    lon = lo;
-    if (use_low) lat = fma(dz, fma(dz, fma(dz, fma(dz, fma(dz, a.a5, a.a4), a.a3), a.a2), a.a1), a.lat0);
-    else {
-        const double v = fma(g, t2 * fma(t2, fma(t2, 0.0625, -0.125), 0.5), h);       // rho / rho_A - 1
-        lat = fma(v, fma(v, fma(v, fma(v, fma(v, a.b5, a.b4), a.b3), a.b2), a.b1), a.lat0);
-    }
-}
-
 // one thread per (scan, fine column)
 __global__ void __launch_bounds__(128)
 legacy_eval_kernel(const double* __restrict__ lon_in, const double* __restrict__ lat_in,
@@ -332,7 +238,7 @@ legacy_eval_kernel(const double* __restrict__ lon_in, const double* __restrict__
     int jr = 0;
     for (int r = 0; r + 1 < g.L; ++r) {
         const long long tie = (scan * g.L + r) * g.W + tie_col;
-        const LegacyAnchor anchor = legacy_anchor(lon_in[tie], lat_in[tie], Y[ym_index(0, ia, row0 + r, n, n_rows)],
+        const AnchorBT anchor = anchor_bt_setup(kR, lon_in[tie], lat_in[tie], Y[ym_index(0, ia, row0 + r, n, n_rows)],
                                                   Y[ym_index(1, ia, row0 + r, n, n_rows)], Y[ym_index(2, ia, row0 + r, n, n_rows)]);
         spline_row(r + 1, bot);
         // tie rows sit at fine-row index r f + off: off = 2 (5 km), 0.5 (500 m), 1.5 (250 m)
@@ -344,7 +250,7 @@ legacy_eval_kernel(const double* __restrict__ lon_in, const double* __restrict__
             const double yy = top[1] + w * (bot[1] - top[1]);
             const double z = top[2] + w * (bot[2] - top[2]);
             double lo, la;
-            legacy_backtransform_fast(anchor, x, yy, z, lo, la);
+            anchor_bt_eval(anchor, kR, 0.8, x, yy, z, lo, la);
             __stcs(olon + (long long)jr * g.Wf, lo);
             __stcs(olat + (long long)jr * g.Wf, la);
         }

@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include "gtp_kernels.h"
+#include "gtp_anchor_bt.cuh"
 
 namespace {
 
@@ -76,8 +77,8 @@ vii_xyz_kernel(const double* __restrict__ lon, const double* __restrict__ lat, d
 }
 
 __global__ void __launch_bounds__(256)
-vii_geo_cartesian_kernel(const double* __restrict__ xyz, double* __restrict__ out_lon, double* __restrict__ out_lat,
-                         ViiGeom g, long long n_px, double z_threshold)
+vii_geo_cartesian_kernel(const double* __restrict__ lon_in, const double* __restrict__ lat_in, const double* __restrict__ xyz,
+                         double* __restrict__ out_lon, double* __restrict__ out_lat, ViiGeom g, long long n_px, double z_threshold)
 {
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t >= n_px) return;
@@ -86,17 +87,10 @@ vii_geo_cartesian_kernel(const double* __restrict__ xyz, double* __restrict__ ou
     vii_locate(g, p, q, tie, wr, wc);
     const long long n = g.n_alt * g.n_act;
     const double x = vii_blend(xyz, g, tie, wr, wc), y = vii_blend(xyz + n, g, tie, wr, wc), z = vii_blend(xyz + 2 * n, g, tie, wr, wc);
-    // _xyz2lonlat, :157-178
-    const double r = sqrt(x * x + y * y);
-    const double thr_z = z_threshold * kMeanR;
-    const double sy = (y > 0.0) ? 1.0 : ((y < 0.0) ? -1.0 : ((y == 0.0) ? 0.0 : y));
-    const double lon = (acos(x / r) * GTP_RAD2DEG) * sy;
-    double lat;
-    if (z < thr_z && z > -thr_z) lat = 90.0 - acos(z / kMeanR) * GTP_RAD2DEG;
-    else {
-        const double sz = (z > 0.0) ? 1.0 : ((z < 0.0) ? -1.0 : ((z == 0.0) ? 0.0 : z));
-        lat = sz * (90.0 - asin(r / kMeanR) * GTP_RAD2DEG);
-    }
+    // _xyz2lonlat (:157-178), anchor-relative around the pixel's upper-left tie point (gtp_anchor_bt.cuh)
+    const AnchorBT anchor = anchor_bt_setup(kMeanR, lon_in[tie], lat_in[tie], xyz[tie], xyz[n + tie], xyz[2 * n + tie], z_threshold);
+    double lon, lat;
+    anchor_bt_eval(anchor, kMeanR, z_threshold, x, y, z, lon, lat);
     __stcs(out_lon + t, lon);
     __stcs(out_lat + t, lat);
 }
@@ -138,6 +132,6 @@ cudaError_t gtp_launch_vii_geo_cartesian(const double* lon, const double* lat, d
     const long long blocks = (n_px + 255) / 256;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     vii_xyz_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(lon, lat, (double*)workspace, n);
-    vii_geo_cartesian_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const double*)workspace, out_lon, out_lat, g, n_px, z_threshold);
+    vii_geo_cartesian_kernel<<<(unsigned)blocks, 256, 0, stream>>>(lon, lat, (const double*)workspace, out_lon, out_lat, g, n_px, z_threshold);
     return cudaGetLastError();
 }
