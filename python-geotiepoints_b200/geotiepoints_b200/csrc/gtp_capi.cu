@@ -77,6 +77,8 @@ int cviirs_device(const T* lon, const T* lat, const T* satz, int64_t n_scans, in
     } else {
         if (allow_fast && gtp_cviirs_fast_f32_supported(cfg))
             e = gtp_launch_cviirs_fast_f32(lon, lat, satz, out_lon, out_lat, n_scans, cfg, (cudaStream_t)stream);
+        else if (allow_fast && gtp_cviirs_fast5_f32_supported(cfg))
+            e = gtp_launch_cviirs_fast5_f32(lon, lat, satz, out_lon, out_lat, n_scans, cfg, (cudaStream_t)stream);
         else
             e = gtp_launch_cviirs_generic<T>(lon, lat, satz, out_lon, out_lat, n_scans, cfg, (cudaStream_t)stream, allow_fast);
     }

@@ -555,6 +555,36 @@ GTP_FD QuadEft quad_eft_setup(const Vec3F& A, const Vec3F& B, const Vec3F& C, co
     return q;
 }
 
+// The FP32-pipe blend of ONE pixel (gtp_fast5_f32.cu: a thread per quad, 5 km -> 1 km).  The two lanes hold
+// (x, y) of the upper edge, (x, y) of the lower edge, and - for z - (upper edge, lower edge).  At 5 km the
+// along-track weight s_t = (j - 2) / 5 is not a dyadic fraction, so the second blend (:398) is an edge blend of
+// its own: (1.0 - s_t) s1 + (float)(s_t s2) = s1 + s_t (s2 - s1) - ep with s2 - s1 exact (Sterbenz).
+// Returns the displacement of the fine xyz from corner A (exact); acc collects the rounding-boundary flags.
+struct QuadEftP2 { EdgeP2 top, bot, zz; float A[3]; };
+
+GTP_FD QuadEftP2 quad_eft_pack(const QuadEft& q)
+{
+    QuadEftP2 e;
+    e.top.A = p2_make(q.A[0], q.A[1]); e.top.B = p2_make(q.B[0], q.B[1]); e.top.d = p2_make(q.dAB[0], q.dAB[1]);
+    e.bot.A = p2_make(q.D[0], q.D[1]); e.bot.B = p2_make(q.C[0], q.C[1]); e.bot.d = p2_make(q.dDC[0], q.dDC[1]);
+    e.zz.A = p2_make(q.A[2], q.D[2]); e.zz.B = p2_make(q.B[2], q.C[2]); e.zz.d = p2_make(q.dAB[2], q.dDC[2]);
+    e.A[0] = q.A[0]; e.A[1] = q.A[1]; e.A[2] = q.A[2];
+    return e;
+}
+
+GTP_FD void eft_pixel(const QuadEftP2& q, float a, P2 t2, P2 nt2, P2& acc, float (&d)[3])
+{
+    const P2 a2 = p2_dup(a), na2 = p2_dup(-a), m1 = p2_dup(-1.0f);
+    const P2 s1 = eft_edge(a2, na2, q.top, acc), s2 = eft_edge(a2, na2, q.bot, acc);
+    const F2 sz = p2_get(eft_edge(a2, na2, q.zz, acc));
+    EdgeP2 track;
+    track.A = s1; track.B = s2; track.d = p2_fma(s1, m1, s2);
+    const F2 vxy = p2_get(eft_edge(t2, nt2, track, acc));
+    track.A = p2_dup(sz.x); track.B = p2_dup(sz.y); track.d = p2_dup(fsub_rn(sz.y, sz.x));
+    const F2 vz = p2_get(eft_edge(t2, nt2, track, acc));
+    d[0] = fsub_rn(vxy.x, q.A[0]); d[1] = fsub_rn(vxy.y, q.A[1]); d[2] = fsub_rn(vz.x, q.A[2]);
+}
+
 // xyz2lonlat of the float32 xyz, anchor-relative in double, result rounded to float (:51-65)
 // (dx, dy, dz) = the float32 xyz minus corner A (exact either way), zd = the float32 z
 template <int MODE, bool WRAP>

@@ -74,3 +74,8 @@ cudaError_t gtp_launch_vii_interp(const double* a, const double* b, double* out_
 cudaError_t gtp_launch_vii_geo_cartesian(const double* lon, const double* lat, double* out_lon, double* out_lat,
                                          long long n_alt, long long n_act, int S, int F, double z_threshold,
                                          void* workspace, cudaStream_t stream);
+
+// gtp_fast5_f32.cu: float32 5 km (270 | 271 columns) -> 1 km fast path
+bool gtp_cviirs_fast5_f32_supported(const CviirsCfg& cfg);
+cudaError_t gtp_launch_cviirs_fast5_f32(const float* lon, const float* lat, const float* satz, float* out_lon, float* out_lat,
+                                        long long n_scans, const CviirsCfg& cfg, cudaStream_t stream);

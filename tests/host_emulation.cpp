@@ -401,42 +401,73 @@ extern "C" int gtp_emul_simple_fast_f32(const float* lon, const float* lat, long
     return 0;
 }
 
-// ---- float32 5 km -> 1 km: the series back-transform of the strip kernel (gtp_generic.cu, use_series) ----
-// the reference's float32 blend (blend_f32 has the same rounding points as the kernel's) followed by the
-// anchor-relative back-transform with the 5 km acceptance limits
+// ---- float32 5 km -> 1 km fast path (csrc/gtp_fast5_f32.cu) ----------------------------------------------
+// like the kernel: tie column walked from the upper to the lower tie row, quad_exp_ali_col, the blend on the
+// FP32 pipe (eft_pixel) for plain low / high latitude quads - the whole quad again with blend_f32 when a value
+// sat on a rounding boundary -, blend_f32 for the rest.  mode_counts[4]: pixels whose FP32-pipe blend differs from
+// blend_f32 without having been flagged (must stay 0); [5]: quads on the FP32 pipe.
 extern "C" int gtp_emul_cviirs5_series_f32(const float* lon, const float* lat, const float* satz, long n_scans,
                                            int W, float* out_lon, float* out_lat, long* mode_counts)
 {
     using namespace gtpfast32;
-    for (int k = 0; k < 5; ++k) mode_counts[k] = 0;
+    for (int k = 0; k < 6; ++k) mode_counts[k] = 0;
     if (W != 270 && W != 271) return 1;
     const int Wf = 1354, nq = W - 1;
+    std::vector<TieColF> top(W), bot(W);
     for (long s = 0; s < n_scans; ++s) {
+        for (int c = 0; c < W; ++c) {
+            TieColF t;
+            const long o = (s * 2) * W + c;
+            tie_col_first<true>(t, lon[o], lat[o], satz[o]);
+            top[c] = t;
+            tie_col_next<false>(t, lon[o + W], lat[o + W], 0.0f);
+            bot[c] = t;
+        }
         for (int qc = 0; qc < nq; ++qc) {
-            auto geo = [&](int r, int c) { long o = (s * 2 + r) * W + c; return tie_geo_f32(lon[o], lat[o]); };
-            auto v3 = [](const TieGeoF& t) { Vec3F v; v.x = t.x; v.y = t.y; v.z = t.z; return v; };
-            const TieGeoF A = geo(0, qc);
-            const Vec3F B = v3(geo(0, qc + 1)), D = v3(geo(1, qc)), C = v3(geo(1, qc + 1));
-            const TieZenF za = tie_zen_f32(satz[(s * 2) * W + qc]), zb = tie_zen_f32(satz[(s * 2) * W + qc + 1]);
+            const TieGeoF A = tie_col_geo(top[qc]);
+            const Vec3F B = tie_col_xyz(top[qc + 1]), D = tie_col_xyz(bot[qc]), C = tie_col_xyz(bot[qc + 1]);
+            const TieZenF za = tie_col_zen(top[qc]), zb = tie_col_zen(top[qc + 1]);
             float ce, cal;
-            quad_exp_ali_f32(za, zb.phi, zb.theta, 5, ce, cal);
+            quad_exp_ali_col(top[qc], za, zb.phi, zb.theta, 5, ce, cal);
             const QuadF32 q = quad_setup_f32(A, B, C, D, ce, cal, kMaxRelHoriz5, kMaxRelZ5);
+            Vec3F Av; Av.x = A.x; Av.y = A.y; Av.z = A.z;
+            const QuadEft qe0 = quad_eft_setup(Av, B, C, D, (qc == nq - 1) ? 32.0f : 8.0f);
+            const QuadEftP2 qe = quad_eft_pack(qe0);
             mode_counts[q.mode]++;
             const int i0 = (qc == 0) ? 0 : 2 + 5 * qc, i1 = (qc == nq - 1) ? Wf : 2 + 5 * qc + 5;
-            for (int j = 0; j < 10; ++j) {
-                const float s_t = (float)(j - 2) / 5.0f;
-                const RowF32 rc = row_setup_f32(q, s_t);
-                for (int i = i0; i < i1; ++i) {
-                    const float s_s = (float)coord_x_5km(i, W) / 5.0f;
-                    const double k1d = mul_rn((double)s_s, add_rn(1.0, -(double)s_s));
-                    double v[3];
-                    float lo, la;
-                    blend_f32(q, rc, s_s, k1d, v);
-                    if (q.mode == kSlow) { const LonLatF ll = backtransform_f32_slow((float)v[0], (float)v[1], (float)v[2]); lo = ll.lon; la = ll.lat; }
-                    else backtransform_f32<kBoth, true>(q, v, lo, la);
-                    const long o = (s * 10 + j) * (long)Wf + i;
-                    out_lon[o] = lo; out_lat[o] = la;
+            bool eft = q.mode != kSlow && qe0.ok && !q.wrap && q.mode != kBoth;
+            if (eft) mode_counts[5]++;
+            for (int pass = 0; pass < 2; ++pass) {
+                P2 acc = p2_dup(0.0f);
+                for (int j = 0; j < 10; ++j) {
+                    const float s_t = (float)(j - 2) / 5.0f;
+                    const RowF32 rc = row_setup_f32(q, s_t);
+                    const P2 t2 = p2_dup(s_t), nt2 = p2_dup(-s_t);
+                    for (int i = i0; i < i1; ++i) {
+                        const float s_s = (float)coord_x_5km(i, W) / 5.0f;
+                        const double k1d = mul_rn((double)s_s, add_rn(1.0, -(double)s_s));
+                        double v[3];
+                        float lo, la;
+                        blend_f32(q, rc, s_s, k1d, v);
+                        if (eft) {
+                            const float a = (float)add_rn(add_rn((double)s_s, mul_rn(k1d, (double)q.ce)), rc.row_ca);
+                            float d[3];
+                            const P2 before = acc;
+                            eft_pixel(qe, a, t2, nt2, acc, d);
+                            const F2 f0 = p2_get(before), f1 = p2_get(acc);
+                            if (f0.x == f1.x && f0.y == f1.y
+                                && ((double)d[0] != v[0] - q.A[0] || (double)d[1] != v[1] - q.A[1] || (double)d[2] != v[2] - q.A[2])) mode_counts[4]++;
+                            if (q.mode == kHigh) backtransform_f32_d<kHigh, false>(q, (double)d[0], (double)d[1], (double)d[2], 0.0, lo, la);
+                            else backtransform_f32_d<kLow, false>(q, (double)d[0], (double)d[1], (double)d[2], 0.0, lo, la);
+                        } else if (q.mode == kSlow) { const LonLatF ll = backtransform_f32_slow((float)v[0], (float)v[1], (float)v[2]); lo = ll.lon; la = ll.lat; }
+                        else backtransform_f32<kBoth, true>(q, v, lo, la);
+                        const long o = (s * 10 + j) * (long)Wf + i;
+                        out_lon[o] = lo; out_lat[o] = la;
+                    }
                 }
+                const F2 fl = p2_get(acc);
+                if (!eft || ((fl.x == 0.0f) && (fl.y == 0.0f))) break;
+                eft = false;            // flagged: the literal arithmetic for the whole quad
             }
         }
     }

@@ -310,8 +310,11 @@ def test_5km_f32_series_matches_oracle(emul, granule, width):
         exp = gtp_oracle.cviirs(lon, lat, satz, 5000, 1000, width, n_threads=8)
     s = assert_parity(got_lon, got_lat, *exp, what=f"host emulation 5km({width}) f32 granule {granule}, modes {modes}")
     assert s["bit_exact_fraction"] > 0.999, (s, modes)
+    # modes["small"] counts pixels whose FP32-pipe blend (eft_pixel) differs from blend_f32 without having been flagged
+    assert modes["small"] == 0, modes
     if granule in (0, 3, 287):          # away from the poles the series takes (nearly) every quad
-        assert modes["slow"] < 0.02 * sum(modes.values()), modes
+        assert modes["slow"] < 0.02 * (modes["slow"] + modes["low"] + modes["high"] + modes["both"]), modes
+        assert modes["wide"] > 0.8 * (modes["low"] + modes["high"] + modes["both"]), modes       # quads on the FP32 pipe
 
 
 @pytest.mark.parametrize("name", ["real", "antimeridian", "pole", "south_pole", "prime_meridian", "lat_switch",
