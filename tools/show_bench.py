@@ -12,7 +12,7 @@ print("clocks", d.get("clocks"))
 print("library", d["config"].get("library"))
 e = d.get("e2e") or {}
 print("e2e", {k: (f"{v['value']:.4g}" if isinstance(v, dict) and "value" in v else v) for k, v in e.items()
-              if k in ("value", "dask", "mod03_f32", "ecef", "h2d_bytes_per_step", "d2h_bytes_per_step")})
+              if k in ("value", "dask", "dask_one_array", "direct", "mod03_f32", "ecef", "h2d_bytes_per_step", "d2h_bytes_per_step")})
 for s in d.get("secondary") or []:
     p = s.get("parity") or {}
     print(f"  {s.get('config'):18s} {str(s.get('dtype')):24s} {s.get('value', 0):.4g} px/s  frac {s.get('roofline_frac', 0):.3f}  "
