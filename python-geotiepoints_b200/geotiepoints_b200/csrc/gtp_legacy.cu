@@ -20,12 +20,14 @@
 //      row): the border column(s), then the Thomas algorithm for the second derivatives M - ~2700 dependent
 //      steps per thread, neighbouring threads on neighbouring addresses.  48 B per tie point (3 B per 250 m
 //      output pixel); latency-, not bandwidth-bound;
-//   3. legacy_eval_kernel: one thread per (scan, fine column): walks down the scan's tie rows, evaluates
-//      the cubic of its column interval per tie row (y, M of the two interval ends: loads that a warp shares),
-//      blends / extrapolates along the rows and back-transforms with the reference's formulas
-//      (geointerpolator.py:63-75).  Coalesced 8-byte stores, 256 B per warp and output array.
+//   3. legacy_eval_1km_kernel<P> (1 km -> 250 / 500 m): one thread per (scan, tie-column interval) = P fine
+//      columns: per tie row one cubic (y, M of the two interval ends) evaluated at t = k / P, per tie-row pair
+//      one anchor, rows blended / extrapolated linearly, anchor-relative back-transform, one 256-bit (128-bit)
+//      streaming store per fine row and output array.  legacy_eval_kernel (5 km -> 1 km, or outputs not aligned
+//      for the vector stores): the same with one thread per (scan, fine column) and 8-byte stores.
 // The back-transform is anchor-relative (legacy_backtransform_fast below; the reference's formulas with
 // library acos / asin / sqrt only next to the poles and for out-of-range anchors).
+#include <cstdint>
 #include <cuda_runtime.h>
 #include <math.h>
 #include "gtp_kernels.h"
@@ -169,26 +171,50 @@ legacy_thomas_kernel(const double* __restrict__ coef, double* __restrict__ Y, do
         const double p0 = aug_col(g, n - 3), p1 = aug_col(g, n - 2), x = aug_col(g, n - 1);
         y[(n - 1) * st] = y[(n - 2) * st] + (x - p1) / (p0 - p1) * (y[(n - 3) * st] - y[(n - 2) * st]);
     }
-    // Thomas algorithm: forward elimination (dp kept in mm[1 .. m]), back substitution
+    // Thomas algorithm: forward elimination (dp kept in mm[1 .. m]), back substitution.  Eight steps at a time:
+    // their loads are issued together (every step touches another cache line, tie row fastest), then the
+    // dependent recurrence runs out of registers - one memory latency per eight steps instead of per step.
     const double* cp = coef;
     const double* iden = coef + m;
     const double* low = coef + 2 * m;
+    constexpr int kBatch = 8;
     double y0 = y[0], y1 = y[st], dp_prev = 0.0;
-    double x0 = aug_col(g, 0), x1 = aug_col(g, 1);
-#pragma unroll 4
-    for (int k = 0; k < m; ++k) {
-        const double y2 = y[(k + 2) * st], x2 = aug_col(g, k + 2);
-        const double rhs = 6.0 * ((y2 - y1) / (x2 - x1) - (y1 - y0) / (x1 - x0));
-        const double dp = (rhs - low[k] * dp_prev) * iden[k];
-        mm[(k + 1) * st] = dp;
-        dp_prev = dp; y0 = y1; y1 = y2; x0 = x1; x1 = x2;
+    for (int k0 = 0; k0 < m; k0 += kBatch) {
+        double yb[kBatch], lb[kBatch], ib[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            const int k = min(k0 + u, m - 1);
+            yb[u] = y[(long long)(k + 2) * st]; lb[u] = low[k]; ib[u] = iden[k];
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            const int k = k0 + u;
+            if (k < m) {
+                const double x0 = aug_col(g, k), x1 = aug_col(g, k + 1), x2 = aug_col(g, k + 2);
+                const double rhs = 6.0 * ((yb[u] - y1) / (x2 - x1) - (y1 - y0) / (x1 - x0));
+                const double dp = (rhs - lb[u] * dp_prev) * ib[u];
+                mm[(long long)(k + 1) * st] = dp;
+                dp_prev = dp; y0 = y1; y1 = yb[u];
+            }
+        }
     }
-    double u_next = mm[m * st];                 // M_{n-2}
-#pragma unroll 4
-    for (int k = m - 2; k >= 0; --k) {
-        const double u = mm[(k + 1) * st] - cp[k] * u_next;
-        mm[(k + 1) * st] = u;
-        u_next = u;
+    double u_next = dp_prev;                    // M_{n-2} = the last dp
+    for (int k0 = m - 2; k0 >= 0; k0 -= kBatch) {
+        double db[kBatch], cb[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            const int k = max(k0 - u, 0);
+            db[u] = mm[(long long)(k + 1) * st]; cb[u] = cp[k];
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            const int k = k0 - u;
+            if (k >= 0) {
+                const double v = db[u] - cb[u] * u_next;
+                mm[(long long)(k + 1) * st] = v;
+                u_next = v;
+            }
+        }
     }
     {
         const double h0 = aug_col(g, 1) - aug_col(g, 0), h1 = aug_col(g, 2) - aug_col(g, 1);
@@ -258,6 +284,85 @@ legacy_eval_kernel(const double* __restrict__ lon_in, const double* __restrict__
     }
 }
 
+// 1 km -> 250 m / 500 m: one thread per (scan, tie-column interval) = P fine columns.  The cubic's coefficients
+// (per tie row and component) and the anchor (per tie-row pair) are set up once per interval instead of once
+// per fine column, and a fine row leaves as one 256-bit (128-bit) store per output array.
+template <int P>
+__device__ __forceinline__ void store_fine(double* p, const double (&v)[P]);
+template <>
+__device__ __forceinline__ void store_fine<4>(double* p, const double (&v)[4])
+{
+    asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+}
+template <>
+__device__ __forceinline__ void store_fine<2>(double* p, const double (&v)[2])
+{
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v[0]), "d"(v[1]) : "memory");
+}
+
+template <int P>
+__global__ void __launch_bounds__(128)
+legacy_eval_1km_kernel(const double* __restrict__ lon_in, const double* __restrict__ lat_in,
+                       const double* __restrict__ Y, const double* __restrict__ M, double* __restrict__ out_lon,
+                       double* __restrict__ out_lat, long long n_scans)
+{
+    const LegacyGeom g = legacy_geom(P == 4 ? 2 : 1);
+    constexpr int kIntervals = 1354;                                 // tie columns = intervals (the last one ends at the border column)
+    const int blocks_per_scan = (kIntervals + blockDim.x - 1) / blockDim.x;
+    const long long scan = blockIdx.x / blocks_per_scan;
+    const int i = (int)(blockIdx.x - scan * blocks_per_scan) * blockDim.x + threadIdx.x;
+    if (scan >= n_scans || i >= kIntervals) return;
+    const int n = g.n;
+    const double h = aug_col(g, i + 1) - (double)i;                  // 1, or 0.75 | 0.5 in the last interval
+    const double inv_h = 1.0 / h, h6 = h / 6.0, inv_6h = 1.0 / (6.0 * h);
+    const long long n_rows = n_scans * g.L, row0 = scan * g.L;
+    double* olon = out_lon + scan * (long long)g.nf * g.Wf + (long long)i * P;
+    double* olat = out_lat + scan * (long long)g.nf * g.Wf + (long long)i * P;
+
+    // the cubic of this interval for one tie row at the P fine columns t = k / P (three components)
+    auto spline_row = [&](int r, double (&v)[3][P]) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const long long o = ym_index(c, i, row0 + r, n, n_rows);
+            const double y0 = Y[o], y1 = Y[o + n_rows], m0 = M[o], m1 = M[o + n_rows];
+            const double b = (y1 - y0) * inv_h - h6 * (2.0 * m0 + m1), c2 = 0.5 * m0, c3 = (m1 - m0) * inv_6h;
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                const double t = (double)k / (double)P;
+                v[c][k] = y0 + t * (b + t * (c2 + t * c3));
+            }
+        }
+    };
+    constexpr double off = (P == 4) ? 1.5 : 0.5;                     // tie row r sits at fine-row index r P + off
+    double top[3][P], bot[3][P];
+    spline_row(0, top);
+    int jr = 0;
+    for (int r = 0; r + 1 < g.L; ++r) {
+        const long long tie = (scan * g.L + r) * g.W + i;
+        const AnchorBT anchor = anchor_bt_setup(kR, lon_in[tie], lat_in[tie], Y[ym_index(0, i, row0 + r, n, n_rows)],
+                                                Y[ym_index(1, i, row0 + r, n, n_rows)], Y[ym_index(2, i, row0 + r, n, n_rows)]);
+        spline_row(r + 1, bot);
+        const int j_end = (r + 2 == g.L) ? g.nf : (int)((r + 1) * P + off) + 1;
+        for (; jr < j_end; ++jr) {
+            const double w = ((double)jr - off) / (double)P - (double)r;
+            double lo[P], la[P];
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                const double x = top[0][k] + w * (bot[0][k] - top[0][k]);
+                const double yy = top[1][k] + w * (bot[1][k] - top[1][k]);
+                const double z = top[2][k] + w * (bot[2][k] - top[2][k]);
+                anchor_bt_eval(anchor, kR, 0.8, x, yy, z, lo[k], la[k]);
+            }
+            store_fine<P>(olon + (long long)jr * g.Wf, lo);
+            store_fine<P>(olat + (long long)jr * g.Wf, la);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int k = 0; k < P; ++k) top[c][k] = bot[c][k];
+    }
+}
+
 }  // namespace
 
 size_t gtp_legacy_workspace_bytes(int kind, long long n_scans)
@@ -288,6 +393,15 @@ cudaError_t gtp_launch_legacy_f64(const double* lon, const double* lat, double* 
     legacy_xyz_kernel<<<(unsigned)tiles, 256, 0, stream>>>(lon, lat, Y, rows, kind);
     const long long threads = rows * 3;
     legacy_thomas_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(coef, Y, M, rows, kind);
+    // 1 km kinds with outputs aligned for the vector stores: a thread per tie-column interval; else per fine column
+    const uintptr_t align = (kind == 2) ? 31 : 15;
+    if (kind != 0 && ((((uintptr_t)out_lon | (uintptr_t)out_lat) & align) == 0)) {
+        const long long blocks = n_scans * ((1354 + 127) / 128);
+        if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+        if (kind == 2) legacy_eval_1km_kernel<4><<<(unsigned)blocks, 128, 0, stream>>>(lon, lat, Y, M, out_lon, out_lat, n_scans);
+        else legacy_eval_1km_kernel<2><<<(unsigned)blocks, 128, 0, stream>>>(lon, lat, Y, M, out_lon, out_lat, n_scans);
+        return cudaGetLastError();
+    }
     const long long blocks = n_scans * ((g.Wf + 127) / 128);
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     legacy_eval_kernel<<<(unsigned)blocks, 128, 0, stream>>>(lon, lat, Y, M, out_lon, out_lat, n_scans, kind);
