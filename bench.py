@@ -55,6 +55,9 @@ CONFIGS = {
     # serve as tie points (10 tie rows per scan, factor 4): (2030, 1354) -> (203 * 9 * 4, 1353 * 4) per granule
     "vii_geo_cartesian": dict(kind="vii", coarse=1000, fine=250, width=0, n_in=2, tie_rows=2030, tie_cols=1354, f=4, out_cols=5412,
                               out_rows=203 * 36),
+    # SURVEY 8f-4, third item: GeoGridInterpolator (default method "linear", extrapolating) with the 1 km lon / lat of the
+    # synthetic granules as tie points at fine rows 4 r + 1.5 and fine columns 4 c: (2030, 1354) -> (8120, 5416) per granule
+    "geogrid_linear": dict(kind="grid", coarse=1000, fine=250, width=0, n_in=2, tie_rows=2030, tie_cols=1354, f=4, out_cols=5416),
     "mod03_ecef_1km_250m": dict(kind="mixed", ecef=True, coarse=1000, fine=250, width=0, n_in=3, tie_rows=2030, tie_cols=1354, f=4, out_cols=5416),
 }
 TIE_ROWS, TIE_COLS = 2030, 1354
@@ -321,7 +324,7 @@ def run_reference_arm(args, dtype):
 SECONDARY = [("cviirs_1km_250m", "f32"), ("cviirs_1km_500m", "f64"), ("cviirs_1km_500m", "f32"),
              ("cviirs_5km_1km", "f64"), ("cviirs_5km_1km", "f32"), ("simple_1km_250m", "f64"), ("simple_1km_250m", "f32"),
              ("simple_1km_500m", "f64"), ("mod03_1km_250m", "f32"), ("legacy_1km_250m", "f64"), ("legacy_5km_1km", "f64"),
-             ("vii_geo_cartesian", "f64")]
+             ("vii_geo_cartesian", "f64"), ("geogrid_linear", "f64")]
 
 
 def measure_secondary(name, dtype_name, base_in, granules, device, local_rank, peak, steps=5, warmup=3):
@@ -363,6 +366,15 @@ def measure_secondary(name, dtype_name, base_in, granules, device, local_rank, p
     elif cfg["kind"] == "vii":
         def step():
             _capi.check(lib.gtp_vii_geo_interp_f64(*ptrs, n_scans * 10, cfg["tie_cols"], 10, cfg["f"], 1, 0.8, *optrs, local_rank, st))
+    elif cfg["kind"] == "grid":
+        n_tie = n_scans * 10
+        grid_axes = [4.0 * np.arange(n_tie) + 1.5, 4.0 * np.arange(cfg["tie_cols"]), np.arange(4.0 * n_tie), np.arange(4.0 * cfg["tie_cols"])]
+        d_axes = [torch.from_numpy(a).to(device) for a in grid_axes]
+        ty, tx, fy, fx = [t.data_ptr() for t in d_axes]
+
+        def step():
+            _capi.check(lib.gtp_geogrid_interp_f64(ty, n_tie, tx, cfg["tie_cols"], *ptrs, fy, 4 * n_tie, fx, 4 * cfg["tie_cols"],
+                                                   1, 1, 0, float("nan"), *optrs, local_rank, st))
     elif cfg["kind"] == "cviirs":
         fn = getattr(lib, "gtp_cviirs_interp_" + dtype_name)
 
@@ -400,7 +412,15 @@ def measure_secondary(name, dtype_name, base_in, granules, device, local_rank, p
         sub = [np.ascontiguousarray(a[in_rows]) for a in arrs]
         idx = torch.from_numpy(out_rows).to(device)
         with np.errstate(all="ignore"):
-            if mixed:
+            if cfg["kind"] == "grid":                          # the fine rows of a "scan" also see the tie rows next to it
+                import grid_oracle
+                parts = []
+                for s_ in picks:
+                    r0, r1 = max(10 * s_ - 1, 0), min(10 * s_ + 11, n_tie)
+                    parts.append(grid_oracle.geogrid_interpolate(grid_axes[0][r0:r1], grid_axes[1], arrs[0][r0:r1], arrs[1][r0:r1],
+                                                                 grid_axes[2][40 * s_:40 * s_ + 40], grid_axes[3]))
+                exp = tuple(np.concatenate([p_[k] for p_ in parts]) for k in (0, 1))
+            elif mixed:
                 exp = gtp_oracle.cviirs(sub[0].astype(np.float64), sub[1].astype(np.float64), sub[2].astype(np.float64) * 0.01,
                                         1000, cfg["fine"], 0, n_threads=8)
                 exp = tuple(a.astype(np.float32) for a in exp)
@@ -539,8 +559,8 @@ def run_b200_arm(args, dtype):
         dist.init_process_group("nccl", device_id=device)
 
     cfg = CONFIGS[args.config]
-    if cfg["kind"] in ("legacy", "vii"):
-        raise SystemExit("the legacy_* / vii_* configurations are measured inside the default run (`secondary`), not as --config")
+    if cfg["kind"] in ("legacy", "vii", "grid"):
+        raise SystemExit("the legacy_* / vii_* / geogrid_* configurations are measured inside the default run (`secondary`), not as --config")
     headline = args.config == "cviirs_1km_250m"
     mixed = cfg["kind"] == "mixed"
     ecef = bool(cfg.get("ecef"))

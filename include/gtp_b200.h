@@ -214,6 +214,45 @@ int gtp_vii_geo_interp_host_f64(const double* lon, const double* lat, int64_t n_
                                 int scan_alt_tie_points, int tie_points_factor, int cartesian, double z_threshold,
                                 double* out_lon, double* out_lat, int device);
 
+/* ---- generic rectilinear-grid interpolators (third item) ------------------------
+ * Replace what geotiepoints.interpolator.SingleGridInterpolator / SingleSplineInterpolator
+ * (/root/reference/geotiepoints/interpolator.py:232-340: scipy's RegularGridInterpolator /
+ * RectBivariateSpline(s = 0)) and geointerpolator.GeoGridInterpolator / GeoSplineInterpolator
+ * (geointerpolator.py:76-113: the same on the Cartesian x / y / z of lon / lat, then xyz2lonlat :63-75) compute.
+ * Tie points: `values` = n_arrays planes of (n_tie_y, n_tie_x) float64 on the rectilinear grid tie_y x tie_x
+ * (strictly ascending; descending grids are flipped by the caller, as scipy does).  Result: n_arrays planes of
+ * (n_fine_y, n_fine_x) at the product of the two fine coordinate vectors.  Per axis one scheme:
+ *   GTP_GRID_NEAREST, GTP_GRID_LINEAR ("linear" / "slinear" / spline order 1),
+ *   GTP_GRID_CUBIC (interpolating cubic spline, not-a-knot ends: "cubic" / spline order 3; needs >= 4 tie points).
+ * Fine coordinates outside the tie-point range: GTP_GRID_OOB_EXTRAPOLATE (scipy's fill_value = None: the end
+ * polynomial continues), GTP_GRID_OOB_FILL (`fill_value`, scipy's bounds_error = False; the geo form
+ * back-transforms x = y = z = fill_value like the reference does), GTP_GRID_OOB_CLAMP (the end value: FITPACK
+ * clamps the arguments of RectBivariateSpline).  bounds_error = True is the caller's check.
+ * Device forms take device pointers for every array (coordinate vectors included) and allocate their scratch
+ * stream-ordered; host forms stage everything through device memory and return when the results are there. */
+#define GTP_GRID_NEAREST 0
+#define GTP_GRID_LINEAR 1
+#define GTP_GRID_CUBIC 3
+#define GTP_GRID_OOB_EXTRAPOLATE 0
+#define GTP_GRID_OOB_FILL 1
+#define GTP_GRID_OOB_CLAMP 2
+int gtp_grid_interp_f64(const double* tie_y, int64_t n_tie_y, const double* tie_x, int64_t n_tie_x,
+                        const double* values, int n_arrays, const double* fine_y, int64_t n_fine_y,
+                        const double* fine_x, int64_t n_fine_x, int method_y, int method_x, int oob_mode,
+                        double fill_value, double* out, int device, void* stream);
+int gtp_grid_interp_host_f64(const double* tie_y, int64_t n_tie_y, const double* tie_x, int64_t n_tie_x,
+                             const double* values, int n_arrays, const double* fine_y, int64_t n_fine_y,
+                             const double* fine_x, int64_t n_fine_x, int method_y, int method_x, int oob_mode,
+                             double fill_value, double* out, int device);
+int gtp_geogrid_interp_f64(const double* tie_y, int64_t n_tie_y, const double* tie_x, int64_t n_tie_x,
+                           const double* lon, const double* lat, const double* fine_y, int64_t n_fine_y,
+                           const double* fine_x, int64_t n_fine_x, int method_y, int method_x, int oob_mode,
+                           double fill_value, double* out_lon, double* out_lat, int device, void* stream);
+int gtp_geogrid_interp_host_f64(const double* tie_y, int64_t n_tie_y, const double* tie_x, int64_t n_tie_x,
+                                const double* lon, const double* lat, const double* fine_y, int64_t n_fine_y,
+                                const double* fine_x, int64_t n_fine_x, int method_y, int method_x, int oob_mode,
+                                double fill_value, double* out_lon, double* out_lat, int device);
+
 /* The host entry points keep up to 4 idle sets of (3 streams + chunk scratch, ~300 MB of
  * device memory each) per process for the next call; gtp_trim() frees them. */
 int gtp_trim(void);

@@ -69,6 +69,10 @@ SIGNATURES["gtp_legacy_interp_host_f64"] = (_int, [_vp, _vp, _i64, _int, _vp, _v
 SIGNATURES["gtp_vii_interp_f64"] = (_int, [_vp, _i64, _i64, _int, _int, _vp, _int, _vp])
 SIGNATURES["gtp_vii_interp_host_f64"] = (_int, [_vp, _i64, _i64, _int, _int, _vp, _int])
 SIGNATURES["gtp_vii_geo_interp_f64"] = (_int, [_vp, _vp, _i64, _i64, _int, _int, _int, _dbl, _vp, _vp, _int, _vp])
+SIGNATURES["gtp_grid_interp_f64"] = (_int, [_vp, _i64, _vp, _i64, _vp, _int, _vp, _i64, _vp, _i64, _int, _int, _int, _dbl, _vp, _int, _vp])
+SIGNATURES["gtp_grid_interp_host_f64"] = (_int, [_vp, _i64, _vp, _i64, _vp, _int, _vp, _i64, _vp, _i64, _int, _int, _int, _dbl, _vp, _int])
+SIGNATURES["gtp_geogrid_interp_f64"] = (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _int, _int, _int, _dbl, _vp, _vp, _int, _vp])
+SIGNATURES["gtp_geogrid_interp_host_f64"] = (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _int, _int, _int, _dbl, _vp, _vp, _int])
 SIGNATURES["gtp_vii_geo_interp_host_f64"] = (_int, [_vp, _vp, _i64, _i64, _int, _int, _int, _dbl, _vp, _vp, _int])
 
 

@@ -953,6 +953,122 @@ int gtp_vii_geo_interp_host_f64(const double* lon, const double* lat, int64_t n_
                                 int tie_points_factor, int cartesian, double z_threshold, double* out_lon, double* out_lat, int device)
 { return vii_host(lon, lat, n_tie_alt, n_tie_act, scan_alt_tie_points, tie_points_factor, cartesian ? 1 : 0, z_threshold, out_lon, out_lat, device); }
 
+// ---- generic rectilinear-grid interpolators (third item) ----
+namespace {
+int grid_check(int64_t ny, int64_t nx, int n_arrays, int64_t my, int64_t mx, int method_y, int method_x, int oob_mode)
+{
+    auto known = [](int m) { return m == GTP_GRID_NEAREST || m == GTP_GRID_LINEAR || m == GTP_GRID_CUBIC; };
+    if (!known(method_y) || !known(method_x)) return fail(GTP_E_RESOLUTION, "grid interpolator: unknown scheme%s");
+    if (oob_mode < GTP_GRID_OOB_EXTRAPOLATE || oob_mode > GTP_GRID_OOB_CLAMP) return fail(GTP_E_RESOLUTION, "grid interpolator: unknown out-of-range mode%s");
+    if (n_arrays < 1 || my < 0 || mx < 0) return fail(GTP_E_SHAPE, "grid interpolator: negative size%s");
+    if (ny < 2 || nx < 2 || ny > 0x7fffffff || nx > 0x7fffffff) return fail(GTP_E_SHAPE, "grid interpolator: need at least 2 tie points per dimension%s");
+    if ((method_y == GTP_GRID_CUBIC && ny < 4) || (method_x == GTP_GRID_CUBIC && nx < 4))
+        return fail(GTP_E_SHAPE, "grid interpolator: the cubic scheme needs at least 4 tie points%s");
+    return GTP_OK;
+}
+
+// geo: values = lon, values2 = lat, out / out2 = lon / lat
+int grid_device(const double* tie_y, int64_t ny, const double* tie_x, int64_t nx, const double* values, const double* values2,
+                int n_arrays, bool geo, const double* fine_y, int64_t my, const double* fine_x, int64_t mx, int method_y,
+                int method_x, int oob_mode, double fill, double* out, double* out2, int device, void* stream)
+{
+    int rc = grid_check(ny, nx, n_arrays, my, mx, method_y, method_x, oob_mode);
+    if (rc != GTP_OK) return rc;
+    if (my == 0 || mx == 0) return GTP_OK;
+    if (!tie_y || !tie_x || !values || !fine_y || !fine_x || !out || (geo && (!values2 || !out2))) return fail(GTP_E_NULL, "null buffer%s");
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) { cudaGetLastError(); return fail(GTP_E_NO_DEVICE, "no usable CUDA device: %s", cudaGetErrorString(guard.err)); }
+    keep_pooled_scratch();
+    void* ws = nullptr;
+    cudaError_t e = cudaMallocAsync(&ws, gtp_grid_workspace_bytes((int)ny, (int)nx, my, mx, geo ? 3 : n_arrays, geo, method_y, method_x), (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "grid workspace");
+    int launches = 0;
+    e = gtp_launch_grid(tie_y, (int)ny, tie_x, (int)nx, values, values2, n_arrays, geo, fine_y, my, fine_x, mx, method_y, method_x,
+                        oob_mode, fill, out, out2, ws, (cudaStream_t)stream, &launches);
+    const cudaError_t ef = cudaFreeAsync(ws, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "grid launch");
+    if (ef != cudaSuccess) return cuda_fail(ef, "grid workspace free");
+    g_launches.fetch_add((uint64_t)launches, std::memory_order_relaxed);
+    return GTP_OK;
+}
+
+// everything staged through stream-ordered device memory on a stream of its own; returns when the results are in `out`
+int grid_host(const double* tie_y, int64_t ny, const double* tie_x, int64_t nx, const double* values, const double* values2,
+              int n_arrays, bool geo, const double* fine_y, int64_t my, const double* fine_x, int64_t mx, int method_y,
+              int method_x, int oob_mode, double fill, double* out, double* out2, int device)
+{
+    int rc = grid_check(ny, nx, n_arrays, my, mx, method_y, method_x, oob_mode);
+    if (rc != GTP_OK) return rc;
+    if (my == 0 || mx == 0) return GTP_OK;
+    if (!tie_y || !tie_x || !values || !fine_y || !fine_x || !out || (geo && (!values2 || !out2))) return fail(GTP_E_NULL, "null buffer%s");
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) { cudaGetLastError(); return fail(GTP_E_NO_DEVICE, "no usable CUDA device: %s", cudaGetErrorString(guard.err)); }
+    keep_pooled_scratch();
+    cudaStream_t st = nullptr;
+    cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return cuda_fail(e, "grid stream");
+    const size_t tie_b = (size_t)ny * nx * 8, out_b = (size_t)my * mx * 8;
+    const int n_in = geo ? 2 : n_arrays, n_out = geo ? 2 : n_arrays;
+    const size_t total = (size_t)(ny + nx + my + mx) * 8 + 64 + (size_t)n_in * tie_b + (size_t)n_out * out_b;
+    char* base = nullptr;
+    e = cudaMallocAsync((void**)&base, total, st);
+    if (e != cudaSuccess) { cudaStreamDestroy(st); return cuda_fail(e, "grid staging"); }
+    char* p = base;
+    auto put = [&](const void* src, size_t bytes) -> double* {
+        double* d = (double*)p;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st);
+        p += (bytes + 15) & ~(size_t)15;
+        return d;
+    };
+    const double* d_ty = put(tie_y, (size_t)ny * 8);
+    const double* d_tx = put(tie_x, (size_t)nx * 8);
+    const double* d_fy = put(fine_y, (size_t)my * 8);
+    const double* d_fx = put(fine_x, (size_t)mx * 8);
+    const double *d_v = nullptr, *d_v2 = nullptr;
+    if (geo) { d_v = put(values, tie_b); d_v2 = put(values2, tie_b); }
+    else d_v = put(values, (size_t)n_arrays * tie_b);
+    double* d_out = (double*)p;
+    double* d_out2 = geo ? d_out + (size_t)my * mx : nullptr;
+    if (e == cudaSuccess) {
+        rc = grid_device(d_ty, ny, d_tx, nx, d_v, d_v2, n_arrays, geo, d_fy, my, d_fx, mx, method_y, method_x, oob_mode, fill,
+                         d_out, d_out2, -1, (void*)st);
+        if (rc == GTP_OK) {
+            if (geo) {
+                e = cudaMemcpyAsync(out, d_out, out_b, cudaMemcpyDeviceToHost, st);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(out2, d_out2, out_b, cudaMemcpyDeviceToHost, st);
+            } else e = cudaMemcpyAsync(out, d_out, (size_t)n_arrays * out_b, cudaMemcpyDeviceToHost, st);
+        }
+    }
+    cudaFreeAsync(base, st);
+    const cudaError_t es = cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    if (rc != GTP_OK) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "grid copy");
+    if (es != cudaSuccess) return cuda_fail(es, "grid synchronize");
+    return GTP_OK;
+}
+}  // namespace
+
+int gtp_grid_interp_f64(const double* tie_y, int64_t n_tie_y, const double* tie_x, int64_t n_tie_x, const double* values, int n_arrays,
+                        const double* fine_y, int64_t n_fine_y, const double* fine_x, int64_t n_fine_x, int method_y, int method_x,
+                        int oob_mode, double fill_value, double* out, int device, void* stream)
+{ return grid_device(tie_y, n_tie_y, tie_x, n_tie_x, values, nullptr, n_arrays, false, fine_y, n_fine_y, fine_x, n_fine_x, method_y, method_x, oob_mode, fill_value, out, nullptr, device, stream); }
+
+int gtp_grid_interp_host_f64(const double* tie_y, int64_t n_tie_y, const double* tie_x, int64_t n_tie_x, const double* values, int n_arrays,
+                             const double* fine_y, int64_t n_fine_y, const double* fine_x, int64_t n_fine_x, int method_y, int method_x,
+                             int oob_mode, double fill_value, double* out, int device)
+{ return grid_host(tie_y, n_tie_y, tie_x, n_tie_x, values, nullptr, n_arrays, false, fine_y, n_fine_y, fine_x, n_fine_x, method_y, method_x, oob_mode, fill_value, out, nullptr, device); }
+
+int gtp_geogrid_interp_f64(const double* tie_y, int64_t n_tie_y, const double* tie_x, int64_t n_tie_x, const double* lon, const double* lat,
+                           const double* fine_y, int64_t n_fine_y, const double* fine_x, int64_t n_fine_x, int method_y, int method_x,
+                           int oob_mode, double fill_value, double* out_lon, double* out_lat, int device, void* stream)
+{ return grid_device(tie_y, n_tie_y, tie_x, n_tie_x, lon, lat, 1, true, fine_y, n_fine_y, fine_x, n_fine_x, method_y, method_x, oob_mode, fill_value, out_lon, out_lat, device, stream); }
+
+int gtp_geogrid_interp_host_f64(const double* tie_y, int64_t n_tie_y, const double* tie_x, int64_t n_tie_x, const double* lon, const double* lat,
+                                const double* fine_y, int64_t n_fine_y, const double* fine_x, int64_t n_fine_x, int method_y, int method_x,
+                                int oob_mode, double fill_value, double* out_lon, double* out_lat, int device)
+{ return grid_host(tie_y, n_tie_y, tie_x, n_tie_x, lon, lat, 1, true, fine_y, n_fine_y, fine_x, n_fine_x, method_y, method_x, oob_mode, fill_value, out_lon, out_lat, device); }
+
 int gtp_set_d2h_relay(int device)
 {
     if (device >= 0) {

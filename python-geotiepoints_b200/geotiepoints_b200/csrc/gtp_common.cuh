@@ -23,6 +23,16 @@
 #define GTP_DEG2RAD (GTP_PI / 180.0)
 #define GTP_RAD2DEG (180.0 / GTP_PI)
 
+// per-axis scheme and out-of-range handling of the generic grid interpolators (include/gtp_b200.h has the same)
+#ifndef GTP_GRID_NEAREST
+#define GTP_GRID_NEAREST 0
+#define GTP_GRID_LINEAR 1
+#define GTP_GRID_CUBIC 3
+#define GTP_GRID_OOB_EXTRAPOLATE 0
+#define GTP_GRID_OOB_FILL 1
+#define GTP_GRID_OOB_CLAMP 2
+#endif
+
 struct CviirsCfg {
     int L;    // tie-point rows per scan: 10 (1 km) or 2 (5 km)   :111-115
     int W;    // tie-point columns: 1354 | 271 | 270              :113-119

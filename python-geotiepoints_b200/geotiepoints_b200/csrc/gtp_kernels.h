@@ -75,6 +75,13 @@ cudaError_t gtp_launch_vii_geo_cartesian(const double* lon, const double* lat, d
                                          long long n_alt, long long n_act, int S, int F, double z_threshold,
                                          void* workspace, cudaStream_t stream);
 
+// gtp_grid.cu: generic rectilinear-grid interpolators (geotiepoints/interpolator.py:232-378, geointerpolator.py:76-113)
+size_t gtp_grid_workspace_bytes(int ny, int nx, long long my, long long mx, int n_comp, int geo, int method_y, int method_x);
+cudaError_t gtp_launch_grid(const double* tie_y, int ny, const double* tie_x, int nx, const double* values,
+                            const double* values2, int n_comp, int geo, const double* fine_y, long long my,
+                            const double* fine_x, long long mx, int method_y, int method_x, int oob_mode, double fill,
+                            double* out, double* out2, void* workspace, cudaStream_t stream, int* launches);
+
 // gtp_fast5_f32.cu: float32 5 km (270 | 271 columns) -> 1 km fast path
 bool gtp_cviirs_fast5_f32_supported(const CviirsCfg& cfg);
 cudaError_t gtp_launch_cviirs_fast5_f32(const float* lon, const float* lat, const float* satz, float* out_lon, float* out_lat,
