@@ -50,6 +50,7 @@ struct GridArgs {
     AxisLoc y, x;
     const double* lon;          // GEO: the tie points themselves (anchors)
     const double* lat;
+    const double* anchors;      // GEO: kAnchorPacked doubles per tie point (grid_xyz_kernel)
     double* out;                // [component][fine row][fine column]; GEO: lon plane
     double* out2;               // GEO: lat plane
     int fill_oob;               // out-of-range pixels get `fill`
@@ -86,7 +87,8 @@ grid_locate_kernel(const double* __restrict__ tie, int n, const double* __restri
 }
 
 __global__ void __launch_bounds__(256)
-grid_xyz_kernel(const double* __restrict__ lon, const double* __restrict__ lat, double* __restrict__ xyz, long long n)
+grid_xyz_kernel(const double* __restrict__ lon, const double* __restrict__ lat, double* __restrict__ xyz,
+                double* __restrict__ anchors, long long n)
 {
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t >= n) return;
@@ -94,7 +96,10 @@ grid_xyz_kernel(const double* __restrict__ lon, const double* __restrict__ lat, 
     sincos(lon[t] * GTP_DEG2RAD, &sl, &cl);                          // lonlat2xyz, geointerpolator.py:52-60
     sincos(lat[t] * GTP_DEG2RAD, &sp, &cp);
     const double rc = kR * cp;
-    xyz[t] = rc * cl; xyz[n + t] = rc * sl; xyz[2 * n + t] = kR * sp;
+    const double x = rc * cl, y = rc * sl, z = kR * sp;
+    xyz[t] = x; xyz[n + t] = y; xyz[2 * n + t] = z;
+    // the tie point as an anchor of the back-transform, prepared once for all the pixels around it
+    anchor_bt_pack(anchor_bt_setup(kR, lon[t], lat[t], x, y, z), kR, 0.8, anchors + kAnchorPacked * t);
 }
 
 // coef[0 .. m): upper / den, [m .. 2m): 1 / den, [2m .. 3m): lower of the not-a-knot system, m = n - 2 unknowns
@@ -184,14 +189,11 @@ template <int MX>
 __global__ void __launch_bounds__(256)
 grid_rows_kernel(GridArgs a, double* __restrict__ Z)
 {
-    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long per_comp = (long long)a.ny * a.mx;
-    if (t >= per_comp * a.n_comp) return;
-    const int c = (int)(t / per_comp);
-    const long long rem = t - c * per_comp;
-    const int r = (int)(rem / a.mx);
-    const long long j = rem - (long long)r * a.mx;
-    Z[t] = row_value<MX>(a, c, r, a.x.idx[j], a.x.d[j], a.x.h[j], a.x.u[j]);
+    // blockIdx.x: (component, tie row); blockIdx.y: 256 fine columns
+    const int c = (int)(blockIdx.x / (unsigned)a.ny), r = (int)(blockIdx.x - (unsigned)c * (unsigned)a.ny);
+    const long long j = blockIdx.y * (long long)blockDim.x + threadIdx.x;
+    if (j >= a.mx) return;
+    Z[((long long)c * a.ny + r) * a.mx + j] = row_value<MX>(a, c, r, a.x.idx[j], a.x.d[j], a.x.h[j], a.x.u[j]);
 }
 
 template <int MX, int MY>
@@ -211,10 +213,10 @@ template <int MX, int MY, bool GEO>
 __global__ void __launch_bounds__(256)
 grid_eval_kernel(GridArgs a)
 {
-    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long n_px = a.my * a.mx;
-    if (t >= n_px) return;
-    const long long i = t / a.mx, j = t - i * a.mx;
+    // a CTA row per fine row (blockIdx.x), 256 fine columns per CTA (blockIdx.y): no 64-bit division per pixel
+    const long long i = blockIdx.x, j = blockIdx.y * (long long)blockDim.x + threadIdx.x;
+    if (j >= a.mx) return;
+    const long long n_px = a.my * a.mx, t = i * a.mx + j;
     const int iy = a.y.idx[i], ix = a.x.idx[j];
     const double dy = a.y.d[i], hy = a.y.h[i], uy = a.y.u[i];
     const double dx = a.x.d[j], hx = a.x.h[j], ux = a.x.u[j];
@@ -235,7 +237,7 @@ grid_eval_kernel(GridArgs a)
         // xyz2lonlat (geointerpolator.py:63-75) around the nearer tie row / column of the pixel's cell
         const int ar = iy + ((uy > 0.5) ? 1 : 0), ac = ix + ((ux > 0.5) ? 1 : 0);
         const long long tie = (long long)ar * a.nx + ac, n = (long long)a.ny * a.nx;
-        const AnchorBT anchor = anchor_bt_setup(kR, a.lon[tie], a.lat[tie], a.V[tie], a.V[n + tie], a.V[2 * n + tie]);
+        const AnchorBT anchor = anchor_bt_unpack(a.anchors + kAnchorPacked * tie, a.lon[tie], a.lat[tie], a.V[tie], a.V[n + tie], a.V[2 * n + tie]);
         anchor_bt_eval(anchor, kR, 0.8, x, y, z, lon, lat);
     }
     __stcs(a.out + t, lon);
@@ -262,10 +264,11 @@ inline AxisWs carve_axis(char*& p, long long m)
 template <int MX, int MY>
 cudaError_t launch_eval(const GridArgs& a, bool geo, cudaStream_t stream)
 {
-    const long long blocks = (a.my * a.mx + 255) / 256;
-    if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    if (geo) grid_eval_kernel<MX, MY, true><<<(unsigned)blocks, 256, 0, stream>>>(a);
-    else grid_eval_kernel<MX, MY, false><<<(unsigned)blocks, 256, 0, stream>>>(a);
+    const long long pieces = (a.mx + 255) / 256;
+    if (a.my > 0x7fffffffLL || pieces > 65535) return cudaErrorInvalidConfiguration;
+    const dim3 blocks((unsigned)a.my, (unsigned)pieces, 1);
+    if (geo) grid_eval_kernel<MX, MY, true><<<blocks, 256, 0, stream>>>(a);
+    else grid_eval_kernel<MX, MY, false><<<blocks, 256, 0, stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -275,7 +278,7 @@ size_t gtp_grid_workspace_bytes(int ny, int nx, long long my, long long mx, int 
 {
     size_t b = axis_bytes(my) + axis_bytes(mx);
     const size_t tie = (size_t)n_comp * ny * nx * 8, rows = (size_t)n_comp * ny * (size_t)mx * 8;
-    if (geo) b += align16(tie);
+    if (geo) b += align16(tie) + align16((size_t)kAnchorPacked * ny * nx * 8);
     if (method_x == GTP_GRID_CUBIC) b += align16(tie) + align16((size_t)3 * nx * 8);
     if (method_y == GTP_GRID_CUBIC) b += 2 * align16(rows) + align16((size_t)3 * ny * 8);
     return b;
@@ -304,14 +307,15 @@ cudaError_t gtp_launch_grid(const double* tie_y, int ny, const double* tie_x, in
     a.V = values; a.Mx = nullptr; a.Z = nullptr; a.My = nullptr;
     a.y = AxisLoc{wy.idx, wy.d, wy.h, wy.u, wy.oob};
     a.x = AxisLoc{wx.idx, wx.d, wx.h, wx.u, wx.oob};
-    a.lon = values; a.lat = values2; a.out = out; a.out2 = out2;
+    a.lon = values; a.lat = values2; a.anchors = nullptr; a.out = out; a.out2 = out2;
     a.fill_oob = (oob_mode == GTP_GRID_OOB_FILL); a.fill = fill;
     a.nearest_y = (method_y == GTP_GRID_NEAREST); a.nearest_x = (method_x == GTP_GRID_NEAREST);
     if (geo) {
         double* xyz = (double*)p; p += align16((size_t)3 * n_tie * 8);
-        grid_xyz_kernel<<<(unsigned)((n_tie + 255) / 256), 256, 0, stream>>>(values, values2, xyz, n_tie);
+        double* anchors = (double*)p; p += align16((size_t)kAnchorPacked * n_tie * 8);
+        grid_xyz_kernel<<<(unsigned)((n_tie + 255) / 256), 256, 0, stream>>>(values, values2, xyz, anchors, n_tie);
         ++count;
-        a.V = xyz;
+        a.V = xyz; a.anchors = anchors;
     }
     if (method_x == GTP_GRID_CUBIC) {
         double* Mx = (double*)p; p += align16((size_t)n_comp * n_tie * 8);
@@ -327,10 +331,11 @@ cudaError_t gtp_launch_grid(const double* tie_y, int ny, const double* tie_x, in
         double* Z = (double*)p; p += align16((size_t)n_rows * 8);
         double* My = (double*)p; p += align16((size_t)n_rows * 8);
         double* coef = (double*)p; p += align16((size_t)3 * ny * 8);
-        const long long blocks = (n_rows + 255) / 256;
-        if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-        if (method_x == GTP_GRID_CUBIC) grid_rows_kernel<3><<<(unsigned)blocks, 256, 0, stream>>>(a, Z);
-        else grid_rows_kernel<1><<<(unsigned)blocks, 256, 0, stream>>>(a, Z);
+        const long long pieces = (mx + 255) / 256;
+        if (pieces > 65535) return cudaErrorInvalidConfiguration;
+        const dim3 blocks((unsigned)(n_comp * ny), (unsigned)pieces, 1);
+        if (method_x == GTP_GRID_CUBIC) grid_rows_kernel<3><<<blocks, 256, 0, stream>>>(a, Z);
+        else grid_rows_kernel<1><<<blocks, 256, 0, stream>>>(a, Z);
         grid_coef_kernel<<<1, 32, 0, stream>>>(tie_y, ny, coef);
         const long long lines = (long long)n_comp * mx;                 // line l: component l / mx, fine column l % mx; points mx apart
         grid_thomas_kernel<<<(unsigned)((lines + 127) / 128), 128, 0, stream>>>(Z, My, lines, mx, (long long)ny * mx, mx, ny, tie_y, coef);

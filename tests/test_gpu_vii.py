@@ -41,6 +41,17 @@ def test_vii_geo_matches_oracle(granule):
     assert dev[0].is_cuda and np.array_equal(dev[0].cpu().numpy(), got[0], equal_nan=True) and np.array_equal(dev[1].cpu().numpy(), got[1], equal_nan=True)
 
 
+@pytest.mark.parametrize("factor", [3, 4])          # 3: the per-pixel kernel; 4 (and 8 above): a thread per tie cell
+def test_vii_geo_other_factors(factor):
+    lon, lat = _vii_like_tie_points(5)             # polar: Cartesian mode
+    exp = vii_oracle.tie_points_geo_interpolation(lon, lat, 4, factor)
+    got = viiinterpolator.tie_points_geo_interpolation(lon, lat, 4, factor)
+    assert got[0].shape == exp[0].shape == (6 * 3 * factor, 420 * factor)
+    dlon = np.abs(got[0] - exp[0]); dlon = np.minimum(dlon, 360.0 - dlon)
+    band = np.abs(np.sin(np.deg2rad(exp[0]))) < 2e-4
+    assert np.nanmax(np.abs(got[1] - exp[1])) <= 1e-10 and np.nanmax(np.where(band, 0.0, dlon)) <= 1e-9
+
+
 def test_vii_generic_arrays_and_dataarray_like():
     rng = np.random.default_rng(3)
     a, b = rng.normal(size=(12, 33)), rng.normal(size=(12, 33))
