@@ -301,7 +301,7 @@ __device__ __forceinline__ void store_fine<2>(double* p, const double (&v)[2])
 }
 
 template <int P>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 legacy_eval_1km_kernel(const double* __restrict__ lon_in, const double* __restrict__ lat_in,
                        const double* __restrict__ Y, const double* __restrict__ M, double* __restrict__ out_lon,
                        double* __restrict__ out_lat, long long n_scans)

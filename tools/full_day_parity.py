@@ -90,6 +90,29 @@ with np.errstate(all="ignore"):
     subs = [testing.modis_granule(g) for g in range(0, 288, 24)]
     l5 = [np.ascontiguousarray(np.concatenate([s[k][2::5, 2::5] for s in subs])) for k in range(2)]
     report("legacy 5km->1km float64", legacy.modis5kmto1km(*l5), legacy_oracle.interpolate(*l5, "5km_1km"))
+    # ... the VII interpolator (every scan has its own tie rows: the 3 sampled scans of a granule are 3 VII scans of 10
+    # tie rows; Cartesian mode) and the generic grid classes (the sampled scans of one granule are one rectilinear grid
+    # each: tie rows 4 r + 1.5, columns 4 c, extrapolating to the 40 x 5416 pixels of the scan)
+    import grid_oracle
+    import vii_oracle
+    from geotiepoints_b200 import viiinterpolator
+    from geotiepoints_b200.geointerpolator import GeoGridInterpolator, GeoSplineInterpolator
+    for factor in (4, 8, 3):
+        got = viiinterpolator.tie_points_geo_interpolation(lon, lat, 10, factor, lat_threshold_use_cartesian=-1.0)
+        xyz = vii_oracle.tie_points_interpolation(list(vii_oracle.lonlat2xyz(lon, lat)), 10, factor)
+        report(f"vii geo (Cartesian) factor {factor}", got, vii_oracle.xyz2lonlat(*xyz, 0.8))
+    ty, tx, fy, fx = 4.0 * np.arange(10) + 1.5, 4.0 * np.arange(1354), np.arange(40.0), np.arange(5416.0)
+    for name, klass, kwargs, okw in (("linear", GeoGridInterpolator, dict(bounds_error=False, fill_value=None), dict(method_y=1, method_x=1)),
+                                     ("cubic", GeoGridInterpolator, dict(bounds_error=False, fill_value=None, method="cubic"), dict(method_y=3, method_x=3)),
+                                     ("spline kx=1 ky=3", GeoSplineInterpolator, dict(kx=1, ky=3), dict(method_y=1, method_x=3, oob=grid_oracle.CLAMP))):
+        got, exp = [[], []], [[], []]
+        for s in range(0, lon.shape[0] // 10, 3):              # one sampled scan per granule
+            rows = slice(10 * s, 10 * s + 10)
+            g_ = klass((ty, tx), lon[rows], lat[rows], **kwargs).interpolate((fy, fx))
+            e_ = grid_oracle.geogrid_interpolate(ty, tx, lon[rows], lat[rows], fy, fx, **okw)
+            for k in (0, 1):
+                got[k].append(g_[k]); exp[k].append(e_[k])
+        report(f"geogrid {name}", [np.concatenate(x) for x in got], [np.concatenate(x) for x in exp])
     # exact-equality counts of the float32 paths (the verdict's "array_equal" question): pixels that differ at all
     for fine, fn in ((250, modisinterpolator.modis_1km_to_250m), (500, modisinterpolator.modis_1km_to_500m)):
         a = [x.astype(np.float32) for x in (lon, lat, satz)]
