@@ -137,6 +137,28 @@ def test_ecef_argument_checks_and_abi_validation():
     assert lib.gtp_simple_interp_xyz_mixed_host(buf, buf, 0, 4, buf, buf, buf, 1, -1) == 0
 
 
+def test_sibling_abi_validation_before_any_device_work():
+    """Legacy, VII and generic-grid entry points validate their arguments before they look for a device."""
+    lib = _capi.lib()
+    buf = np.zeros(64, np.float64).ctypes.data
+    nan = float("nan")
+    assert lib.gtp_legacy_interp_f64(buf, buf, 1, 7, buf, buf, -1, None) == 1
+    assert lib.gtp_legacy_interp_host_f64(buf, buf, -1, 2, buf, buf, -1) == 4
+    assert lib.gtp_vii_geo_interp_f64(buf, buf, 7, 4, 4, 8, 1, 0.8, buf, buf, -1, None) == 4          # 7 tie rows, 4 per scan
+    assert lib.gtp_vii_interp_host_f64(buf, 8, 1, 4, 8, buf, -1) == 4                                  # one tie column
+    grid = lambda *a: lib.gtp_grid_interp_f64(*a, -1, None)       # noqa: E731
+    geo = lambda *a: lib.gtp_geogrid_interp_host_f64(*a, -1)      # noqa: E731
+    assert grid(buf, 4, buf, 4, buf, 1, buf, 2, buf, 2, 2, 1, 0, nan, buf) == 1                        # scheme 2 does not exist
+    assert grid(buf, 4, buf, 4, buf, 1, buf, 2, buf, 2, 1, 1, 3, nan, buf) == 1                        # out-of-range mode 3 neither
+    assert grid(buf, 1, buf, 4, buf, 1, buf, 2, buf, 2, 1, 1, 0, nan, buf) == 4                        # one tie row
+    assert grid(buf, 3, buf, 4, buf, 1, buf, 2, buf, 2, 3, 1, 0, nan, buf) == 4                        # cubic needs 4 points
+    assert grid(buf, 4, buf, 4, buf, 0, buf, 2, buf, 2, 1, 1, 0, nan, buf) == 4                        # no arrays
+    assert grid(buf, 4, buf, 4, buf, 1, buf, 2, buf, 2, 1, 1, 0, nan, None) == 3
+    assert grid(buf, 4, buf, 4, buf, 1, buf, 0, buf, 2, 1, 1, 0, nan, None) == 0                       # nothing to do
+    assert geo(buf, 4, buf, 4, buf, None, buf, 2, buf, 2, 1, 1, 0, nan, buf, buf) == 3
+    assert geo(buf, 4, buf, 4, buf, buf, buf, 2, buf, 2, 0, 3, 2, nan, buf, None) == 3
+
+
 def test_partial_scan_and_wrong_width_are_refused():
     a = np.zeros((15, 1354), np.float32)
     with pytest.raises(ValueError, match="whole scans"):
