@@ -77,25 +77,29 @@ __device__ __forceinline__ AnchorBT anchor_bt_setup(double R, double lon, double
 // takes the reference's formulas (a line of pixels along |lat| = 53.13 deg).
 constexpr int kAnchorPacked = 8;
 
-__device__ __forceinline__ void anchor_bt_pack(const AnchorBT& a, double R, double thr, double* __restrict__ dst)
+// element m of tie point t lives at base[m * n + t] (n tie points): lanes on neighbouring tie points read
+// neighbouring addresses - as 64-byte records the loads of a warp touched 32 sectors per instruction
+__device__ __forceinline__ void anchor_bt_pack(const AnchorBT& a, double R, double thr, double* __restrict__ base, long long n, long long t)
 {
     const bool low = fabs(a.z) < thr * R;
-    double2* const d = reinterpret_cast<double2*>(dst);              // 16-byte aligned
-    d[0] = make_double2(a.ue0, a.ue1);
-    d[1] = make_double2(low ? a.a1 : a.b1, low ? a.a2 : a.b2);
-    d[2] = make_double2(low ? a.a3 : a.b3, low ? a.a4 : a.b4);
-    d[3] = make_double2(low ? a.a5 : a.b5, !a.ok ? 2.0 : (low ? 0.0 : 1.0));
+    double* const d = base + t;
+    d[0] = a.ue0; d[n] = a.ue1;
+    d[2 * n] = low ? a.a1 : a.b1; d[3 * n] = low ? a.a2 : a.b2; d[4 * n] = low ? a.a3 : a.b3;
+    d[5 * n] = low ? a.a4 : a.b4; d[6 * n] = low ? a.a5 : a.b5;
+    d[7 * n] = !a.ok ? 2.0 : (low ? 0.0 : 1.0);
 }
 
-__device__ __forceinline__ AnchorBT anchor_bt_unpack(const double* __restrict__ src, double lon, double lat, double x, double y, double z)
+__device__ __forceinline__ AnchorBT anchor_bt_unpack(const double* __restrict__ base, long long n, long long t, double lon, double lat,
+                                                     double x, double y, double z)
 {
-    const double2* const p = reinterpret_cast<const double2*>(src);
-    const double2 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
+    const double* const p = base + t;
     AnchorBT a;
     a.x = x; a.y = y; a.z = z; a.lon0 = lon; a.lat0 = lat;
-    a.ue0 = q0.x; a.ue1 = q0.y;
-    a.a1 = a.b1 = q1.x; a.a2 = a.b2 = q1.y; a.a3 = a.b3 = q2.x; a.a4 = a.b4 = q2.y; a.a5 = a.b5 = q3.x;
-    a.ok = q3.y < 1.5; a.low = q3.y == 0.0; a.high = q3.y == 1.0;
+    a.ue0 = __ldg(p); a.ue1 = __ldg(p + n);
+    a.a1 = a.b1 = __ldg(p + 2 * n); a.a2 = a.b2 = __ldg(p + 3 * n); a.a3 = a.b3 = __ldg(p + 4 * n);
+    a.a4 = a.b4 = __ldg(p + 5 * n); a.a5 = a.b5 = __ldg(p + 6 * n);
+    const double kind = __ldg(p + 7 * n);
+    a.ok = kind < 1.5; a.low = kind == 0.0; a.high = kind == 1.0;
     return a;
 }
 

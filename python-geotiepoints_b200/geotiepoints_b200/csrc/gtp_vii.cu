@@ -28,9 +28,6 @@ struct ViiGeom {
     long long out_cols;         // (n_act - 1) F
 };
 
-// scratch: x, y, z planes (3 n doubles), then - 16-byte aligned - the packed anchors
-__host__ __device__ inline long long vii_anchor_offset(long long n) { return 3 * n + ((3 * n) & 1); }
-
 __device__ __forceinline__ double lerp_ref(double lo, double hi, double w)
 {
     return lo + (hi - lo) * w;                    // scipy interp1d: y_lo + slope (x - x_lo), x_hi - x_lo = factor
@@ -89,7 +86,7 @@ vii_xyz_kernel(const double* __restrict__ lon, const double* __restrict__ lat, d
     const double x = rc * cl, y = rc * sl, z = kMeanR * sp;
     xyz[t] = x; xyz[n + t] = y; xyz[2 * n + t] = z;
     // the tie point as an anchor of the back-transform (gtp_anchor_bt.cuh), shared by the factor^2 pixels of its cell
-    anchor_bt_pack(anchor_bt_setup(kMeanR, lon[t], lat[t], x, y, z, z_threshold), kMeanR, z_threshold, xyz + vii_anchor_offset(n) + kAnchorPacked * t);
+    anchor_bt_pack(anchor_bt_setup(kMeanR, lon[t], lat[t], x, y, z, z_threshold), kMeanR, z_threshold, xyz + 3 * n, n, t);
 }
 
 __global__ void __launch_bounds__(256)
@@ -103,7 +100,7 @@ vii_geo_cartesian_kernel(const double* __restrict__ lon_in, const double* __rest
     const long long n = g.n_alt * g.n_act;
     const double x = vii_blend(xyz, g, tie, wr, wc), y = vii_blend(xyz + n, g, tie, wr, wc), z = vii_blend(xyz + 2 * n, g, tie, wr, wc);
     // _xyz2lonlat (:157-178), anchor-relative around the pixel's upper-left tie point (gtp_anchor_bt.cuh)
-    const AnchorBT anchor = anchor_bt_unpack(xyz + vii_anchor_offset(n) + kAnchorPacked * tie, lon_in[tie], lat_in[tie], xyz[tie], xyz[n + tie], xyz[2 * n + tie]);
+    const AnchorBT anchor = anchor_bt_unpack(xyz + 3 * n, n, tie, lon_in[tie], lat_in[tie], xyz[tie], xyz[n + tie], xyz[2 * n + tie]);
     double lon, lat;
     anchor_bt_eval(anchor, kMeanR, z_threshold, x, y, z, lon, lat);
     __stcs(out_lon + t, lon);
@@ -132,8 +129,7 @@ vii_geo_cells_kernel(const double* __restrict__ lon_in, const double* __restrict
         left[c] = lerp_ref(d[0], d[g.n_act], wr);                                // vii_blend, :74
         slope[c] = lerp_ref(d[1], d[g.n_act + 1], wr) - left[c];
     }
-    const AnchorBT anchor = anchor_bt_unpack(xyz + vii_anchor_offset(n) + kAnchorPacked * tie, lon_in[tie], lat_in[tie],
-                                             xyz[tie], xyz[n + tie], xyz[2 * n + tie]);
+    const AnchorBT anchor = anchor_bt_unpack(xyz + 3 * n, n, tie, lon_in[tie], lat_in[tie], xyz[tie], xyz[n + tie], xyz[2 * n + tie]);
     double lo[F], la[F];
 #pragma unroll
     for (int k = 0; k < F; ++k) {
@@ -169,7 +165,7 @@ bool vii_grid(const ViiGeom& g, long long n_px, dim3& blocks)
 
 }  // namespace
 
-size_t gtp_vii_workspace_bytes(long long n_alt, long long n_act) { return (size_t)(vii_anchor_offset(n_alt * n_act) + kAnchorPacked * n_alt * n_act) * sizeof(double); }
+size_t gtp_vii_workspace_bytes(long long n_alt, long long n_act) { return (size_t)((3 + kAnchorPacked) * n_alt * n_act) * sizeof(double); }
 
 // b == nullptr: one array
 cudaError_t gtp_launch_vii_interp(const double* a, const double* b, double* out_a, double* out_b,
