@@ -159,3 +159,68 @@ def test_matches_reference_itself():
     assert np.abs(got32[0] - ref64[0]).max() <= 4e-6 and np.abs(got32[1] - ref64[1]).max() <= 4e-6      # half a float32 ulp
     well = np.abs(np.sin(np.deg2rad(ref64[0]))) > 0.5
     assert well.sum() > 1000 and np.abs(got32[0] - ref32[0])[well].max() <= 3e-5 and np.abs(got32[1] - ref32[1]).max() <= 3e-5
+
+
+def _fake_dask_modules():
+    """dask is not in the image: just enough of dask.base / dask.array / dask.array.core for the graphs that
+    interpolator.py:261-284 builds ({(name, i, j): (func, slices)} handed to da.Array)."""
+    import types
+
+    def normalize_chunks(chunks, shape, dtype=None):
+        if chunks == "auto":
+            chunks = shape
+        if isinstance(chunks, int):
+            chunks = (chunks,) * len(shape)
+        out = []
+        for c, n in zip(chunks, shape):
+            if isinstance(c, (tuple, list)):
+                out.append(tuple(c))
+            else:
+                full, rest = divmod(n, c)
+                out.append((c,) * full + ((rest,) if rest else ()))
+        return tuple(out)
+
+    class Array:
+        def __init__(self, dsk, name, shape, chunks, dtype, lead=None):
+            self.dask, self.name, self.shape, self.chunks, self.dtype, self._lead = dsk, name, tuple(shape), tuple(chunks), np.dtype(dtype), lead
+
+        def __getitem__(self, k):
+            assert isinstance(k, int) and self._lead is None and self.chunks[0] == (self.shape[0],)
+            return Array(self.dask, self.name, self.shape[1:], self.chunks[1:], self.dtype, lead=k)
+
+        def compute(self):
+            chunks = self.chunks if self._lead is None else ((1,),) + self.chunks
+            rows = []
+            for i in range(len(chunks[-2])):
+                row = []
+                for j in range(len(chunks[-1])):
+                    key = (self.name,) + ((0,) if self._lead is not None else ()) + (i, j)
+                    func, arg = self.dask[key]
+                    block = np.asarray(func(arg))
+                    row.append(block if self._lead is None else block[self._lead])
+                rows.append(np.concatenate(row, axis=-1))
+            return np.concatenate(rows, axis=-2)
+
+    base = types.ModuleType("dask.base"); base.tokenize = lambda *a, **k: format(abs(hash(repr((a, k)))), "x")
+    core = types.ModuleType("dask.array.core"); core.normalize_chunks = normalize_chunks
+    array = types.ModuleType("dask.array"); array.Array = Array; array.core = core
+    dask = types.ModuleType("dask"); dask.base = base; dask.array = array
+    return {"dask": dask, "dask.base": base, "dask.array": array, "dask.array.core": core}
+
+
+def test_chunked_interpolation_builds_the_references_graph(monkeypatch):
+    """test_chunked_geogrid_interpolation / test_chunked_geospline_interpolation (:247-265, :338-356)"""
+    for name, mod in _fake_dask_modules().items():
+        monkeypatch.setitem(sys.modules, name, mod)
+    lons32, lats32 = TIE_LONS.astype(np.float32), TIE_LATS.astype(np.float32)
+    interpolator = GeoGridInterpolator((Y_POINTS, X_POINTS), lons32, lats32)
+    eager = interpolator.interpolate_to_shape((16, 8))
+    lons, lats = interpolator.interpolate_to_shape((16, 8), chunks=4)
+    assert lons.chunks == ((4, 4, 4, 4), (4, 4)) and lats.chunks == ((4, 4, 4, 4), (4, 4)) and lons.dtype == np.float32
+    assert np.array_equal(lons.compute(), eager[0]) and np.array_equal(lats.compute(), eager[1])
+    lons, lats = interpolator.interpolate_to_shape((16, 8), chunks=(8, 3))
+    assert lons.chunks == ((8, 8), (3, 3, 2)) and np.array_equal(lats.compute(), eager[1])
+    multi = MultipleGridInterpolator((Y_POINTS, X_POINTS), lons32, lats32)
+    a, b = multi.interpolate_to_shape((16, 8), chunks=4)
+    ea, eb = multi.interpolate_to_shape((16, 8))
+    assert a.chunks == ((4, 4, 4, 4), (4, 4)) and np.array_equal(a.compute(), ea) and np.array_equal(b.compute(), eb)
