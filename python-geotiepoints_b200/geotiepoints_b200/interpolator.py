@@ -162,15 +162,11 @@ def _values_dtype(values):
 
 
 def _enumerate_chunk_slices(chunks):
-    """Enumerate chunks with slices (``interpolator.py:303-312``)."""
-    for position in np.ndindex(tuple(map(len, (chunks)))):
-        slices = []
-        for pos, chunk in zip(position, chunks):
-            chunk_size = chunk[pos]
-            offset = sum(chunk[:pos])
-            slices.append(slice(offset, offset + chunk_size))
-
-        yield (position, slices)
+    """(block position, [row slice, column slice, ...]) of every block of a normalised `chunks` tuple - the keys and
+    arguments of the reference's dask graph (``interpolator.py:303-312``)."""
+    starts = [np.concatenate(([0], np.cumsum(sizes))) for sizes in chunks]
+    for position in np.ndindex(*(len(sizes) for sizes in chunks)):
+        yield position, [slice(int(edge[k]), int(edge[k + 1])) for edge, k in zip(starts, position)]
 
 
 class _GridRules:
