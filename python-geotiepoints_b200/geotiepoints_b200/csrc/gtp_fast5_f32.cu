@@ -25,7 +25,7 @@ constexpr int kFineCols = 1354;
 constexpr int kF = 5;
 constexpr int kRows = 10;
 constexpr int kQuadsPerWarp = 30;
-constexpr int kThreads5 = 32;
+constexpr int kThreads5 = 128;        // 4 independent warps (strips) per CTA: they start together and share instruction fetches
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kSpanMax = 152;
 
@@ -92,7 +92,7 @@ __device__ __forceinline__ void copy_row_out(const float2* span_lon, const float
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kThreads5, 16)
+__global__ void __launch_bounds__(kThreads5, 16 * 32 / kThreads5)
 cviirs_fast_5km_f32_kernel(const float* __restrict__ lon, const float* __restrict__ lat, const float* __restrict__ satz,
                            float* __restrict__ out_lon, float* __restrict__ out_lat, long long n_scans, int W, int warps_per_scan)
 {
@@ -163,8 +163,10 @@ cviirs_fast_5km_f32_kernel(const float* __restrict__ lon, const float* __restric
     }
 
     // ---- pixels: row by row, staged in shared memory so that the warp stores contiguous spans ----
-    __shared__ __align__(16) float s_lon[kSpanMax];
-    __shared__ __align__(16) float s_lat[kSpanMax];
+    __shared__ __align__(16) float s_lon_all[kThreads5 / 32][kSpanMax];
+    __shared__ __align__(16) float s_lat_all[kThreads5 / 32][kSpanMax];
+    float* const s_lon = s_lon_all[threadIdx.x >> 5];
+    float* const s_lat = s_lat_all[threadIdx.x >> 5];
     const int i_start = first_warp ? 0 : 2 + kF * kQuadsPerWarp * w;
     const int i_end = last_warp ? kFineCols : 2 + kF * kQuadsPerWarp * (w + 1);
     const int span2 = (i_end - i_start) >> 1;
@@ -213,7 +215,7 @@ cudaError_t gtp_launch_cviirs_fast5_f32(const float* lon, const float* lat, cons
     if ((((uintptr_t)out_lon | (uintptr_t)out_lat) & 7) != 0)
         return gtp_launch_cviirs_generic<float>(lon, lat, satz, out_lon, out_lat, n_scans, cfg, stream, true);
     const int warps_per_scan = (cfg.W - 1 + kQuadsPerWarp - 1) / kQuadsPerWarp;
-    const long long blocks = n_scans * warps_per_scan;
+    const long long blocks = (n_scans * warps_per_scan * 32 + kThreads5 - 1) / kThreads5;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     cviirs_fast_5km_f32_kernel<<<(unsigned)blocks, kThreads5, 0, stream>>>(lon, lat, satz, out_lon, out_lat, n_scans, cfg.W, warps_per_scan);
     return cudaGetLastError();
