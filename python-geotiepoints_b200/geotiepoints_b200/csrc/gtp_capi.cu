@@ -233,16 +233,27 @@ struct HostPipe {
 std::mutex g_pipe_mutex;
 std::vector<HostPipe*> g_idle_pipes;
 
+// called with `device` current
 HostPipe* acquire_pipe(int device)
 {
-    {
-        std::lock_guard<std::mutex> lock(g_pipe_mutex);
-        for (size_t i = 0; i < g_idle_pipes.size(); ++i)
-            if (g_idle_pipes[i]->device == device) {
-                HostPipe* p = g_idle_pipes[i];
-                g_idle_pipes.erase(g_idle_pipes.begin() + i);
-                return p;
-            }
+    for (;;) {
+        HostPipe* p = nullptr;
+        {
+            std::lock_guard<std::mutex> lock(g_pipe_mutex);
+            for (size_t i = 0; i < g_idle_pipes.size(); ++i)
+                if (g_idle_pipes[i]->device == device) {
+                    p = g_idle_pipes[i];
+                    g_idle_pipes.erase(g_idle_pipes.begin() + i);
+                    break;
+                }
+        }
+        if (!p) break;
+        // a set kept from before a cudaDeviceReset / context change holds stale handles: drop it as it is
+        // (its streams and scratch went with the context) and look on
+        const cudaError_t q = p->streams[0] ? cudaStreamQuery(p->streams[0]) : cudaSuccess;
+        if (q == cudaSuccess || q == cudaErrorNotReady) return p;
+        cudaGetLastError();
+        delete p;
     }
     HostPipe* p = new HostPipe;
     p->device = device;
