@@ -102,7 +102,8 @@ grid_xyz_kernel(const double* __restrict__ lon, const double* __restrict__ lat, 
     anchor_bt_pack(anchor_bt_setup(kR, lon[t], lat[t], x, y, z), kR, 0.8, anchors, n, t);
 }
 
-// coef[0 .. m): upper / den, [m .. 2m): 1 / den, [2m .. 3m): lower of the not-a-knot system, m = n - 2 unknowns
+// coef[0 .. m): upper / den, [m .. 2m): 1 / den, [2m .. 3m): lower of the not-a-knot system, m = n - 2 unknowns;
+// [3m .. 3m + n - 1): 6 / h of the n - 1 intervals
 __global__ void grid_coef_kernel(const double* __restrict__ knots, int n, double* __restrict__ coef)
 {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
@@ -118,6 +119,7 @@ __global__ void grid_coef_kernel(const double* __restrict__ knots, int n, double
         coef[k] = cp; coef[m + k] = 1.0 / den; coef[2 * m + k] = lower;
         cp_prev = cp;
     }
+    for (int j = 0; j < n - 1; ++j) coef[3 * m + j] = 6.0 / (knots[j + 1] - knots[j]);
 }
 
 // second derivatives of the not-a-knot spline through n points y[0], y[st], ...: mm[0], mm[st], ...
@@ -128,24 +130,25 @@ __device__ __forceinline__ void thomas_solve(const double* __restrict__ y, doubl
     const double* cp = coef;
     const double* iden = coef + m;
     const double* low = coef + 2 * m;
+    const double* s6 = coef + 3 * m;
     constexpr int kBatch = 8;                                        // loads of eight steps issued together
-    double y0 = y[0], y1 = y[st], dp_prev = 0.0;
+    double y1 = y[st], dp_prev = 0.0;
+    double left = (y1 - y[0]) * s6[0];                               // 6 (y_{k+1} - y_k) / h_k
     for (int k0 = 0; k0 < m; k0 += kBatch) {
-        double yb[kBatch], lb[kBatch], ib[kBatch];
+        double yb[kBatch], lb[kBatch], ib[kBatch], sb[kBatch];
 #pragma unroll
         for (int q = 0; q < kBatch; ++q) {
             const int k = min(k0 + q, m - 1);
-            yb[q] = y[(long long)(k + 2) * st]; lb[q] = low[k]; ib[q] = iden[k];
+            yb[q] = y[(long long)(k + 2) * st]; lb[q] = low[k]; ib[q] = iden[k]; sb[q] = s6[k + 1];
         }
 #pragma unroll
         for (int q = 0; q < kBatch; ++q) {
             const int k = k0 + q;
             if (k < m) {
-                const double x0 = knots[k], x1 = knots[k + 1], x2 = knots[k + 2];
-                const double rhs = 6.0 * ((yb[q] - y1) / (x2 - x1) - (y1 - y0) / (x1 - x0));
-                const double dp = (rhs - lb[q] * dp_prev) * ib[q];
+                const double right = (yb[q] - y1) * sb[q];
+                const double dp = ((right - left) - lb[q] * dp_prev) * ib[q];
                 mm[(long long)(k + 1) * st] = dp;
-                dp_prev = dp; y0 = y1; y1 = yb[q];
+                dp_prev = dp; y1 = yb[q]; left = right;
             }
         }
     }
@@ -357,8 +360,8 @@ size_t gtp_grid_workspace_bytes(int ny, int nx, long long my, long long mx, int 
     size_t b = axis_bytes(my) + axis_bytes(mx);
     const size_t tie = (size_t)n_comp * ny * nx * 8, rows = (size_t)n_comp * ny * (size_t)mx * 8;
     if (geo) b += align16(tie) + align16((size_t)kAnchorPacked * ny * nx * 8);
-    if (method_x == GTP_GRID_CUBIC) b += align16(tie) + align16((size_t)3 * nx * 8);
-    if (method_y == GTP_GRID_CUBIC) b += 2 * align16(rows) + align16((size_t)3 * ny * 8);
+    if (method_x == GTP_GRID_CUBIC) b += align16(tie) + align16((size_t)4 * nx * 8);
+    if (method_y == GTP_GRID_CUBIC) b += 2 * align16(rows) + align16((size_t)4 * ny * 8);
     return b;
 }
 
@@ -397,7 +400,7 @@ cudaError_t gtp_launch_grid(const double* tie_y, int ny, const double* tie_x, in
     }
     if (method_x == GTP_GRID_CUBIC) {
         double* Mx = (double*)p; p += align16((size_t)n_comp * n_tie * 8);
-        double* coef = (double*)p; p += align16((size_t)3 * nx * 8);
+        double* coef = (double*)p; p += align16((size_t)4 * nx * 8);
         grid_coef_kernel<<<1, 32, 0, stream>>>(tie_x, nx, coef);
         const long long lines = (long long)n_comp * ny;                 // line l: row l of the stacked planes, points 1 apart
         grid_thomas_kernel<<<(unsigned)((lines + 127) / 128), 128, 0, stream>>>(a.V, Mx, lines, 1, nx, 1, nx, tie_x, coef);
@@ -408,7 +411,7 @@ cudaError_t gtp_launch_grid(const double* tie_y, int ny, const double* tie_x, in
         const long long n_rows = (long long)n_comp * ny * mx;
         double* Z = (double*)p; p += align16((size_t)n_rows * 8);
         double* My = (double*)p; p += align16((size_t)n_rows * 8);
-        double* coef = (double*)p; p += align16((size_t)3 * ny * 8);
+        double* coef = (double*)p; p += align16((size_t)4 * ny * 8);
         const long long pieces = (mx + 255) / 256;
         if (pieces > 65535) return cudaErrorInvalidConfiguration;
         const dim3 blocks((unsigned)(n_comp * ny), (unsigned)pieces, 1);

@@ -81,7 +81,8 @@ __host__ __device__ inline int col_interval(const LegacyGeom& g, int j)
     return (g.kind == 1) ? j / 2 : j / 4;
 }
 
-// coef[0 .. m): cp (upper / den), coef[m .. 2m): 1 / den, coef[2m .. 3m): lower; m = n - 2 unknowns M_1 .. M_{n-2}
+// coef[0 .. m): cp (upper / den), coef[m .. 2m): 1 / den, coef[2m .. 3m): lower; m = n - 2 unknowns M_1 .. M_{n-2};
+// coef[3m .. 3m + n - 1): 6 / h_j of the n - 1 intervals (the right-hand sides without divisions)
 __global__ void legacy_coef_kernel(double* __restrict__ coef, int kind)
 {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
@@ -98,6 +99,7 @@ __global__ void legacy_coef_kernel(double* __restrict__ coef, int kind)
         coef[k] = cp; coef[m + k] = 1.0 / den; coef[2 * m + k] = lower;
         cp_prev = cp;
     }
+    for (int j = 0; j < n - 1; ++j) coef[3 * m + j] = 6.0 / (aug_col(g, j + 1) - aug_col(g, j));
 }
 
 // Layout of the scratch arrays Y (Cartesian tie points incl. the border columns) and M (second derivatives):
@@ -177,24 +179,25 @@ legacy_thomas_kernel(const double* __restrict__ coef, double* __restrict__ Y, do
     const double* cp = coef;
     const double* iden = coef + m;
     const double* low = coef + 2 * m;
+    const double* s6 = coef + 3 * m;             // 6 / h of interval j
     constexpr int kBatch = 8;
     double y0 = y[0], y1 = y[st], dp_prev = 0.0;
+    double left = (y1 - y0) * s6[0];             // 6 (y_{k+1} - y_k) / h_k of the interval left of point k + 1
     for (int k0 = 0; k0 < m; k0 += kBatch) {
-        double yb[kBatch], lb[kBatch], ib[kBatch];
+        double yb[kBatch], lb[kBatch], ib[kBatch], sb[kBatch];
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {
             const int k = min(k0 + u, m - 1);
-            yb[u] = y[(long long)(k + 2) * st]; lb[u] = low[k]; ib[u] = iden[k];
+            yb[u] = y[(long long)(k + 2) * st]; lb[u] = low[k]; ib[u] = iden[k]; sb[u] = s6[k + 1];
         }
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {
             const int k = k0 + u;
             if (k < m) {
-                const double x0 = aug_col(g, k), x1 = aug_col(g, k + 1), x2 = aug_col(g, k + 2);
-                const double rhs = 6.0 * ((yb[u] - y1) / (x2 - x1) - (y1 - y0) / (x1 - x0));
-                const double dp = (rhs - lb[u] * dp_prev) * ib[u];
+                const double right = (yb[u] - y1) * sb[u];
+                const double dp = ((right - left) - lb[u] * dp_prev) * ib[u];
                 mm[(long long)(k + 1) * st] = dp;
-                dp_prev = dp; y0 = y1; y1 = yb[u];
+                dp_prev = dp; y1 = yb[u]; left = right;
             }
         }
     }
@@ -369,7 +372,7 @@ size_t gtp_legacy_workspace_bytes(int kind, long long n_scans)
 {
     const LegacyGeom g = legacy_geom(kind);
     const size_t rows = (size_t)n_scans * g.L;
-    return (2 * rows * 3 * g.n + 3 * (size_t)(g.n - 2)) * sizeof(double);
+    return (2 * rows * 3 * g.n + 3 * (size_t)(g.n - 2) + (size_t)(g.n - 1)) * sizeof(double);
 }
 
 void gtp_legacy_shape(int kind, int* tie_rows_per_scan, int* tie_cols, int* fine_rows_per_scan, int* fine_cols)
