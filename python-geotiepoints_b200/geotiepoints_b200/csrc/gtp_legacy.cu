@@ -304,7 +304,7 @@ __device__ __forceinline__ void store_fine<2>(double* p, const double (&v)[2])
 }
 
 template <int P>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, P == 4 ? 3 : 4)              // 166 | 128 registers without spills
 legacy_eval_1km_kernel(const double* __restrict__ lon_in, const double* __restrict__ lat_in,
                        const double* __restrict__ Y, const double* __restrict__ M, double* __restrict__ out_lon,
                        double* __restrict__ out_lat, long long n_scans)
@@ -322,29 +322,41 @@ legacy_eval_1km_kernel(const double* __restrict__ lon_in, const double* __restri
     double* olon = out_lon + scan * (long long)g.nf * g.Wf + (long long)i * P;
     double* olat = out_lat + scan * (long long)g.nf * g.Wf + (long long)i * P;
 
-    // the cubic of this interval for one tie row at the P fine columns t = k / P (three components)
-    auto spline_row = [&](int r, double (&v)[3][P]) {
+    // (y, M) of the interval's two ends on one tie row, three components: 12 loads from 12 cache lines
+    struct Raw { double y0[3], y1[3], m0[3], m1[3]; };
+    auto load_row = [&](int r) -> Raw {
+        Raw q;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const long long o = ym_index(c, i, row0 + r, n, n_rows);
-            const double y0 = Y[o], y1 = Y[o + n_rows], m0 = M[o], m1 = M[o + n_rows];
-            const double b = (y1 - y0) * inv_h - h6 * (2.0 * m0 + m1), c2 = 0.5 * m0, c3 = (m1 - m0) * inv_6h;
+            q.y0[c] = Y[o]; q.y1[c] = Y[o + n_rows]; q.m0[c] = M[o]; q.m1[c] = M[o + n_rows];
+        }
+        return q;
+    };
+    // the cubic of this interval for one tie row at the P fine columns t = k / P (three components)
+    auto spline_row = [&](const Raw& q, double (&v)[3][P]) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double b = (q.y1[c] - q.y0[c]) * inv_h - h6 * (2.0 * q.m0[c] + q.m1[c]), c2 = 0.5 * q.m0[c], c3 = (q.m1[c] - q.m0[c]) * inv_6h;
 #pragma unroll
             for (int k = 0; k < P; ++k) {
                 const double t = (double)k / (double)P;
-                v[c][k] = y0 + t * (b + t * (c2 + t * c3));
+                v[c][k] = q.y0[c] + t * (b + t * (c2 + t * c3));
             }
         }
     };
     constexpr double off = (P == 4) ? 1.5 : 0.5;                     // tie row r sits at fine-row index r P + off
     double top[3][P], bot[3][P];
-    spline_row(0, top);
+    Raw cur = load_row(0);
+    spline_row(cur, top);
+    Raw nxt = load_row(1);                                           // always one tie row ahead of the arithmetic
     int jr = 0;
     for (int r = 0; r + 1 < g.L; ++r) {
         const long long tie = (scan * g.L + r) * g.W + i;
-        const AnchorBT anchor = anchor_bt_setup(kR, lon_in[tie], lat_in[tie], Y[ym_index(0, i, row0 + r, n, n_rows)],
-                                                Y[ym_index(1, i, row0 + r, n, n_rows)], Y[ym_index(2, i, row0 + r, n, n_rows)]);
-        spline_row(r + 1, bot);
+        const AnchorBT anchor = anchor_bt_setup(kR, lon_in[tie], lat_in[tie], cur.y0[0], cur.y0[1], cur.y0[2]);
+        spline_row(nxt, bot);
+        cur = nxt;
+        if (r + 2 < g.L) nxt = load_row(r + 2);
         const int j_end = (r + 2 == g.L) ? g.nf : (int)((r + 1) * P + off) + 1;
         for (; jr < j_end; ++jr) {
             const double w = ((double)jr - off) / (double)P - (double)r;
