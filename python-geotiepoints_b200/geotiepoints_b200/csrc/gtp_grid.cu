@@ -252,7 +252,7 @@ grid_eval_kernel(GridArgs a)
 // in the nearer tie row) is loaded once per cell; a pixel is then 9 FP64 operations + the back-transform.  With one
 // thread per pixel the kernel spent ~300 instructions per pixel, three quarters of them on indices, the loads of
 // twelve tie values and of the anchor.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)
 grid_geo_linear4_kernel(GridArgs a, int vector_stores)
 {
     const long long i = blockIdx.x, j0 = 4 * (blockIdx.y * (long long)blockDim.x + threadIdx.x);

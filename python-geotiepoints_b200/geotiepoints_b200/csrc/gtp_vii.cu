@@ -112,7 +112,7 @@ vii_geo_cartesian_kernel(const double* __restrict__ lon_in, const double* __rest
 // is 6 FP64 operations + the back-transform, and a thread stores 32-byte pieces.  The per-pixel kernel above spends
 // 320 instructions per pixel, 240 of them on indices, weights and the loads of the four tie points and the anchor.
 template <int F>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)
 vii_geo_cells_kernel(const double* __restrict__ lon_in, const double* __restrict__ lat_in, const double* __restrict__ xyz,
                      double* __restrict__ out_lon, double* __restrict__ out_lat, ViiGeom g, double z_threshold)
 {
