@@ -224,3 +224,18 @@ def test_chunked_interpolation_builds_the_references_graph(monkeypatch):
     a, b = multi.interpolate_to_shape((16, 8), chunks=4)
     ea, eb = multi.interpolate_to_shape((16, 8))
     assert a.chunks == ((4, 4, 4, 4), (4, 4)) and np.array_equal(a.compute(), ea) and np.array_equal(b.compute(), eb)
+
+
+def test_concurrent_calls_from_threads():
+    """dask's threaded scheduler runs the chunk tasks of one interpolator concurrently (threading)."""
+    from concurrent.futures import ThreadPoolExecutor
+    lon, lat, _ = testing.modis_granule(7, n_scans=10)
+    lon5, lat5 = np.ascontiguousarray(lon[2::5, 2::5]), np.ascontiguousarray(lat[2::5, 2::5])
+    ty, tx = np.arange(2, lon.shape[0], 5.0), np.arange(2, lon.shape[1], 5.0)
+    interpolator = GeoGridInterpolator((ty, tx), lon5, lat5, bounds_error=False, fill_value=None)
+    whole = interpolator.interpolate_to_shape(lon.shape)
+    pieces = [(slice(0, 2), slice(r, r + 10), slice(c, c + 677)) for r in range(0, 100, 10) for c in (0, 677)]
+    with ThreadPoolExecutor(8) as pool:
+        blocks = list(pool.map(interpolator._interpolate_slices, pieces))
+    for (_, rows, cols), block in zip(pieces, blocks):
+        assert np.array_equal(block[0], whole[0][rows, cols]) and np.array_equal(block[1], whole[1][rows, cols])
