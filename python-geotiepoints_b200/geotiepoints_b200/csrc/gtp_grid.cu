@@ -13,14 +13,17 @@
 // (bounds_error = False), or the end value (FITPACK clamps the arguments of RectBivariateSpline).
 //
 // Launches (gtp_launch_grid): grid_locate_kernel per axis (binary search: interval, offset, weight, out-of-range
-// flag of every fine coordinate - 1-D vectors, a few KB); GEO: grid_xyz_kernel (lon / lat -> x / y / z planes);
-// cubic along x: coefficients of the tridiagonal system (one thread; they depend on the knots only), Thomas
-// algorithm per (component, tie row) for the second derivatives along x; cubic along y: grid_rows_kernel
-// evaluates the x-scheme of every tie row at the fine columns (Z: tie rows x fine columns), Thomas per
-// (component, fine column) along y - neighbouring threads on neighbouring addresses; grid_eval_kernel: one thread
-// per output pixel - x-scheme on the two tie rows around it (or Z and its second derivatives), y-scheme, GEO:
-// anchor-relative back-transform around the pixel's tie point (gtp_anchor_bt.cuh; the reference's formulas with
-// library functions where the pixel is further than ~60 km from it) - coalesced 8-byte streaming stores.
+// flag of every fine coordinate - 1-D vectors, a few KB); GEO: grid_xyz_kernel (lon / lat -> x / y / z planes and,
+// per tie point, the anchor of the back-transform: 8 planes); cubic along x: coefficients of the tridiagonal system
+// (one thread; they depend on the knots only), Thomas algorithm per (component, tie row) for the second derivatives
+// along x; cubic along y: grid_rows_kernel evaluates the x-scheme of every tie row at the fine columns (Z: tie rows
+// x fine columns), Thomas per (component, fine column) along y - neighbouring threads on neighbouring addresses.
+// Evaluation: GEO with linear / nearest on both axes (the reference's default): grid_geo_linear4_kernel, a thread
+// per (fine row, four consecutive fine columns) - the cell's tie columns blended along y and its anchor loaded once,
+// four independent back-transform chains, 256-bit stores; everything else: grid_eval_kernel, a thread per output
+// pixel (x-scheme on the two tie rows around it, or Z and its second derivatives; y-scheme; GEO: anchor-relative
+// back-transform - gtp_anchor_bt.cuh; the reference's formulas with library functions where the pixel is further
+// than ~60 km from its tie point), coalesced 8-byte streaming stores.
 #include <cstdint>
 #include <cuda_runtime.h>
 #include <math.h>
