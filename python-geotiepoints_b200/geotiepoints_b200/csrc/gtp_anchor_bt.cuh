@@ -1,4 +1,4 @@
-// gtp_anchor_bt.cuh - anchor-relative xyz -> lon / lat from a displacement (gtp_legacy.cu, gtp_vii.cu).
+// gtp_anchor_bt.cuh - anchor-relative xyz -> lon / lat from a displacement (gtp_legacy.cu, gtp_vii.cu, gtp_grid.cu).
 //
 // The idea of gtp_fast_math.cuh for interpolators that produce plain Cartesian coordinates: every fine pixel
 // lies within ~1.5 tie intervals of a tie point A whose lon / lat are INPUTS.  With (e, h) the displacement in

@@ -7,10 +7,13 @@
 // on lon / lat directly or - any |lat| > 60 deg, longitudes spanning > 180 deg - on Cartesian coordinates of
 // the sphere with the IUGG mean radius (:20) followed by _xyz2lonlat (:157-178).
 //
-// One thread per output pixel (coalesced 8-byte streaming stores); the four tie points of a pixel are loads
-// that `factor` x `factor` neighbouring pixels share.  Cartesian mode: vii_xyz_kernel turns the tie points
-// into x / y / z and into an anchor of the back-transform once (scratch: 88 B per tie point = 88 / factor^2 B per
-// pixel), the pixel kernel blends the three components and back-transforms anchor-relative (gtp_anchor_bt.cuh).  Algorithmic bytes per pixel: 8 n_out written + 8 n_in / factor^2 read.
+// Plain arrays (vii_interp_kernel) and other factors: one thread per output pixel (coalesced 8-byte streaming
+// stores); the four tie points of a pixel are loads that `factor` x `factor` neighbouring pixels share.  Cartesian
+// mode: vii_xyz_kernel turns the tie points into x / y / z and into anchors of the back-transform once (scratch:
+// 88 B per tie point = 88 / factor^2 B per pixel); factors 4 and 8: vii_geo_cells_kernel, a thread per (output row,
+// tie cell) - row weight, along-track blends and anchor once per cell, 256-bit stores -, else
+// vii_geo_cartesian_kernel per pixel; both back-transform anchor-relative (gtp_anchor_bt.cuh).
+// Algorithmic bytes per pixel: 8 n_out written + 8 n_in / factor^2 read.
 #include <cstdint>
 #include <cuda_runtime.h>
 #include <math.h>
