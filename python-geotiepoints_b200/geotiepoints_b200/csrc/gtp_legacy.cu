@@ -228,7 +228,7 @@ legacy_thomas_kernel(const double* __restrict__ coef, double* __restrict__ Y, do
 }
 
 // one thread per (scan, fine column)
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)
 legacy_eval_kernel(const double* __restrict__ lon_in, const double* __restrict__ lat_in,
                    const double* __restrict__ Y, const double* __restrict__ M, double* __restrict__ out_lon,
                    double* __restrict__ out_lat, long long n_scans, int kind)
