@@ -12,7 +12,7 @@ cd $OUT/$NAME
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -I$ROOT/include"
 sed -i 's#../../../include/gtp_b200.h#gtp_b200.h#' *.cu *.cuh *.h 2>/dev/null || true
 # every translation unit of csrc/ (the Makefile's flags: no FMA contraction in the rounding-faithful ones)
-for f in gtp_generic gtp_fast_f32 gtp_fast5_f32 gtp_legacy gtp_vii; do nvcc $FLAGS -fmad=false -c $f.cu -o $f.o & done
+for f in gtp_generic gtp_fast_f32 gtp_fast5_f32 gtp_legacy gtp_vii gtp_grid; do nvcc $FLAGS -fmad=false -c $f.cu -o $f.o & done
 for f in gtp_fast gtp_fast5 gtp_fast_xyz gtp_capi; do nvcc $FLAGS -c $f.cu -o $f.o & done
 wait
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT/libgtp_b200_$NAME.so *.o
