@@ -29,12 +29,12 @@ constexpr int kL = 10;              // tie rows per scan
 constexpr int kQuadColsPerWarp = 31;
 constexpr int kWarpsPerScan = (kW + kQuadColsPerWarp - 1) / kQuadColsPerWarp;   // 44
 #ifndef GTP_FAST_THREADS
-#define GTP_FAST_THREADS 128
+#define GTP_FAST_THREADS 32
 #endif
 constexpr int kThreads = GTP_FAST_THREADS;
 constexpr unsigned kFull = 0xffffffffu;
 #ifndef GTP_FAST_MIN_BLOCKS
-#define GTP_FAST_MIN_BLOCKS 4     // resident CTAs per SM the register allocation is tuned for
+#define GTP_FAST_MIN_BLOCKS 16    // resident CTAs per SM the register allocation is tuned for
 #endif
 
 // the fine rows [0, nrows) of one quad, first row at a_track = s_t0, branch-free per pixel
