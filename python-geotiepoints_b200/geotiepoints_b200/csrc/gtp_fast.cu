@@ -28,14 +28,13 @@ constexpr int kW = 1354;            // tie columns at 1 km
 constexpr int kL = 10;              // tie rows per scan
 constexpr int kQuadColsPerWarp = 31;
 constexpr int kWarpsPerScan = (kW + kQuadColsPerWarp - 1) / kQuadColsPerWarp;   // 44
-#ifndef GTP_FAST_THREADS
-#define GTP_FAST_THREADS 32
-#endif
-constexpr int kThreads = GTP_FAST_THREADS;
+// CTA size, 16 warps per SM either way (measured): one-warp CTAs free their slot as soon as their strip is
+// done, +2 ... 5 % for the short strips of 500 m and +3 % for the MOD03 types; the simple interpolator at 250 m
+// is 2.5 % faster with four warps per CTA
+template <int P, bool SIMPLE>
+struct FastThreads { static constexpr int value = (SIMPLE && P == 4) ? 128 : 32; };
 constexpr unsigned kFull = 0xffffffffu;
-#ifndef GTP_FAST_MIN_BLOCKS
-#define GTP_FAST_MIN_BLOCKS 16    // resident CTAs per SM the register allocation is tuned for
-#endif
+constexpr int kWarpsPerSm = 16;      // resident warps per SM the register allocation is tuned for (128 registers)
 
 // the fine rows [0, nrows) of one quad, first row at a_track = s_t0, branch-free per pixel
 template <int P, int MODE, bool WRAP, typename TOut>
@@ -91,7 +90,7 @@ __device__ __forceinline__ void quad_rows_cold(const Quad* qp, const double* a_c
 // gtp_cviirs_interp_mixed: float32 lon/lat, float32 or int16 * zen_scale + zen_offset
 // zenith angles, float64 MATH throughout, results rounded once to float32 or kept in float64.
 template <int P, bool SIMPLE, typename TIn, typename TZen, typename TOut>
-__global__ void __launch_bounds__(kThreads, GTP_FAST_MIN_BLOCKS)
+__global__ void __launch_bounds__(FastThreads<P, SIMPLE>::value, kWarpsPerSm * 32 / FastThreads<P, SIMPLE>::value)
 modis_fast_1km_f64_kernel(const TIn* __restrict__ lon, const TIn* __restrict__ lat,
                           const TZen* __restrict__ satz, TOut* __restrict__ out_lon,
                           TOut* __restrict__ out_lat, long long n_scans, double zen_scale, double zen_offset)
@@ -101,6 +100,7 @@ modis_fast_1km_f64_kernel(const TIn* __restrict__ lon, const TIn* __restrict__ l
     constexpr int kN = kL * P;           // fine rows per scan
     constexpr int kHalf = P / 2;
 
+    constexpr int kThreads = FastThreads<P, SIMPLE>::value;
     const long long warp_global = (blockIdx.x * (long long)kThreads + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const long long scan = warp_global / kWarpsPerScan;
@@ -292,6 +292,7 @@ cudaError_t launch_fast(const TIn* lon, const TIn* lat, const TZen* satz, TOut* 
                         long long n_scans, double zen_scale, double zen_offset, cudaStream_t stream)
 {
     const long long warps = n_scans * kWarpsPerScan;
+    constexpr int kThreads = FastThreads<P, SIMPLE>::value;
     const long long blocks = (warps * 32 + kThreads - 1) / kThreads;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     modis_fast_1km_f64_kernel<P, SIMPLE, TIn, TZen, TOut><<<(unsigned)blocks, kThreads, 0, stream>>>(
